@@ -1,0 +1,135 @@
+/*
+ * libsummerclip_b200 — C ABI of the B200-native CLIP-search hot path.
+ *
+ * Replaces, for the one path BASELINE.json names, the torch calls made by
+ * myrachins/summer-clip (citations are paths under the reference tree):
+ *   summer_clip/clip_searcher/cache_weights_strategy.py:18-36   (normalise, Q^T K, exp(-b(1-A)))
+ *   summer_clip/clip_searcher/cache_value_strategy.py:14-28     (one-hot / softmax cache values)
+ *   summer_clip/clip_searcher/cache_strategy.py:48-81           (per-class top-k pseudo-labels)
+ *   summer_clip/clip_searcher/image_attention.py:80-83,107-111  (zero-shot logits, W@V, Z+alpha*O)
+ *   summer_clip/clip_searcher/utils.py:15-21, clip_adapter/train_adapter.py:156-159 (top-1/5)
+ *   summer_clip/tip_adapter/utils.py:10-15,99-129               (Tip-Adapter head, search_hp)
+ * The reference has no FFI: its boundary is Python strategy classes.  The Python mirror of those
+ * classes (summer_clip_b200/clip_searcher/...) binds these symbols with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default);
+ *   - return value: 0 on success, negative SC_E* for argument errors, positive cudaError_t
+ *     otherwise; sc_last_error() returns a thread-local message for the last failure;
+ *   - no call allocates caller-visible memory or keeps global mutable state;
+ *   - strides / leading dimensions are in ELEMENTS.
+ */
+#ifndef SUMMER_CLIP_B200_H_
+#define SUMMER_CLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_ABI_VERSION 1
+
+/* element types of caller buffers */
+enum { SC_F16 = 0, SC_BF16 = 1, SC_F32 = 2 };
+/* sc_rowconf modes: rank rows by the raw maximum (TopKStrategy, cache_strategy.py:67-70) or by
+ * the maximum of softmax(scale * row) (TopKProbStrategy, cache_strategy.py:79-81). */
+enum { SC_CONF_RAW = 0, SC_CONF_PROB = 1 };
+/* sc_values_prepare modes: HardCacheStrategy (cache_value_strategy.py:14-17) or
+ * SoftmaxCacheStrategy (cache_value_strategy.py:26-28). */
+enum { SC_VALUES_HARD = 0, SC_VALUES_SOFTMAX = 1 };
+/* error codes */
+enum { SC_OK = 0, SC_EINVAL = -1, SC_EALIGN = -2, SC_ESHAPE = -3, SC_EUNSUPPORTED = -4, SC_EDRIVER = -5 };
+
+int sc_version(void);
+const char* sc_last_error(void);
+
+/* Geometry helpers (host only, no CUDA calls).  The attention kernel consumes
+ *   Qn [Nq, D_pad] bf16, Kn [Nk, D_pad] bf16 (rows L2-normalised, K-major),
+ *   Vt [C_pad, Nk_pad] bf16 (cache values TRANSPOSED, zero padded),
+ * where D_pad = sc_pad_dim(D), Nk_pad = sc_pad_keys(Nk), C_pad = sc_pad_classes(C). */
+int64_t sc_pad_dim(int64_t D);          /* multiple of 64 */
+int64_t sc_pad_keys(int64_t Nk);        /* multiple of 8  */
+int64_t sc_pad_classes(int64_t C);      /* n_slices * slice width (multiple of 16, <= 256) */
+int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C classes */
+
+/* Column L2-normalise + gather + transpose + cast (cache_weights_strategy.py:19-20 fused with the
+ * column gather K[:, idx] of image_attention.py:55).
+ *   src: element (d, n) at src[d*stride_d + n*stride_n], d < D, n < N, dtype src_dtype.
+ *   idx: optional int64[n_out] column indices (NULL: n_out must equal N, identity).
+ *   dst: bf16 [n_out, D_pad]; columns D..D_pad-1 are written as zero.
+ *   normalize: 1 = divide by the column's L2 norm (fp32), 0 = cast only. */
+int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
+                      int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst,
+                      int64_t D_pad, int normalize, void* stream);
+
+/* Per-row confidence and predicted label of a logits bank L[N, C] (leading dim ld):
+ *   SC_CONF_RAW : conf = max_c L, label = first argmax          (cache_strategy.py:68)
+ *   SC_CONF_PROB: conf = max_c softmax(scale * L), same label   (cache_strategy.py:80, :68)
+ * Arithmetic is fp32 whatever the storage type. */
+int sc_rowconf(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, float scale, int mode,
+               float* conf, int32_t* label, void* stream);
+
+/* select_topk_per_label (cache_strategy.py:48-59): for every class c in [0, C) the indices of
+ * the min(k, n_c) most confident rows whose label is c, most confident first; ties are broken by
+ * the smaller row index.  out_idx is int64 [C, k] (unused slots = -1), out_count int32 [C].
+ * The reference's concatenated result is, for c ascending, out_idx[c, :out_count[c]]. */
+size_t sc_topk_workspace_bytes(int64_t N, int32_t C);
+int sc_topk_per_class(const float* conf, const int32_t* label, int64_t N, int32_t C, int32_t k,
+                      int64_t* out_idx, int32_t* out_count, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* Cache values V = f(L[idx]) written TRANSPOSED as bf16 Vt[C_pad, Nk_pad] (zero padded):
+ *   SC_VALUES_HARD   : one_hot(argmax_c L)                      (cache_value_strategy.py:15-16)
+ *   SC_VALUES_SOFTMAX: softmax(scale * L, dim=1), scale = clip_scale*scale  (:27)
+ * idx optional int64[n_out] row gather (image_attention.py:55, L[idx]); labels_override optional
+ * int32[n_out]: if given (HARD mode) it replaces the argmax (replace_outs_with_golds,
+ * image_attention.py:65-66; Tip-Adapter one-hot cache values, tip_adapter/utils.py:62).
+ * ones_row >= 0 additionally sets Vt[ones_row, k] = 1 for k < n_out (row sums for softmax mode). */
+int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C, int64_t ld,
+                      const int64_t* idx, const int32_t* labels_override, int64_t n_out, int mode,
+                      float scale, void* Vt, int64_t C_pad, int64_t Nk_pad, int64_t ones_row,
+                      void* stream);
+
+/* Fused attention (cache_weights_strategy.py:34-35 + image_attention.py:109, never
+ * materialising the [Nq, Nk] matrix):
+ *     O[s, q, c] = sum_{k in split s} exp(beta * (Qn[q].Kn[k] - 1)) * Vt[c, k]
+ * for c < n_cols (n_cols <= C_pad).  O is fp32 [splits, Nq, ldo]; the caller sums the splits
+ * (sc_merge_partials).  splits >= 1 partitions the key tiles so that small query batches still
+ * fill the GPU; splits = 0 lets the library choose (query with sc_attn_splits). */
+int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count);
+int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int64_t Nk,
+                int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
+                int splits, float* O, int64_t ldo, void* stream);
+
+/* out[r, c] = sum_p parts[p, r, c]  (key splits and key-sharded ranks; with the Tip weights
+ * exp(beta(A-1)) <= 1 the running maximum of an LSE merge is the constant 0, so the merge of
+ * partial (m, l, O) triples is a plain sum).  parts: fp32 [n_parts, rows, ld]. `out` may alias
+ * parts[0]. */
+int sc_merge_partials(const float* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld,
+                      float* out, int64_t ld_out, void* stream);
+
+/* Zero-shot logits Z = scale * normalise_cols(X)^T @ T in fp32 (image_attention.py:80-83; with
+ * scale = 1 also the pseudo-label logits bank of save_image_outs.py:25).
+ *   X element (d, n) at X[d*stride_d + n*stride_n]; T is [D, C] row-major with leading dim ldt. */
+int sc_zero_shot_logits(const void* X, int x_dtype, int64_t D, int64_t N, int64_t stride_d,
+                        int64_t stride_n, const void* T, int t_dtype, int64_t C, int64_t ldt,
+                        float scale, int normalize, float* Z, int64_t ldz, void* stream);
+
+/* Epilogue (image_attention.py:111-112, clip_searcher/utils.py:15-21, tip_adapter/utils.py:10-15):
+ * for every alpha a: out = Z + O * alpha  (O optionally divided by rowsum[q] first), prediction =
+ * first argmax, and — if labels are given — the number of rows whose label is the top-1 / within
+ * the top-5 (ties: larger value first, then smaller class index).  `alphas` is a HOST array of
+ * na <= 64 floats.  Z may be NULL (treated as 0).  out_logits (nullable) is fp32 [na, Nq, C];
+ * pred (nullable) int32 [na, Nq]; top1/top5 (nullable) int32 [na], ACCUMULATED into (caller zeroes). */
+int sc_epilogue(const float* Z, int64_t ldz, const float* O, int64_t ldo, const float* rowsum,
+                int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
+                float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUMMER_CLIP_B200_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of libsummerclip_b200.so (the C ABI declared in include/summer_clip_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a symbol is absent the
+import of the product path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+SC_F16, SC_BF16, SC_F32 = 0, 1, 2
+SC_CONF_RAW, SC_CONF_PROB = 0, 1
+SC_VALUES_HARD, SC_VALUES_SOFTMAX = 0, 1
+
+_LIB_PATH = Path(os.environ.get("SUMMER_CLIP_B200_LIB", Path(__file__).resolve().parent / "lib" / "libsummerclip_b200.so"))
+
+# name -> (restype, argtypes); mirrors include/summer_clip_b200.h one to one
+SIGNATURES = {
+    "sc_version": (c_int, []),
+    "sc_last_error": (c_char_p, []),
+    "sc_pad_dim": (c_int64, [c_int64]),
+    "sc_pad_keys": (c_int64, [c_int64]),
+    "sc_pad_classes": (c_int64, [c_int64]),
+    "sc_class_slice": (c_int64, [c_int64]),
+    "sc_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_int, c_void_p]),
+    "sc_rowconf": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p,
+                           c_void_p]),
+    "sc_topk_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "sc_topk_per_class": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    "sc_values_prepare": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                  c_float, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "sc_attn_splits": (c_int, [c_int64, c_int64, c_int64, c_int]),
+    "sc_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                            c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_merge_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "sc_zero_shot_logits": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,
+                                    c_int64, c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_epilogue": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, POINTER(c_float),
+                            c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class SummerClipError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library once; raise if it (or any declared symbol) is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise SummerClipError(
+            f"{_LIB_PATH} not found: build it with `python -m summer_clip_b200.build` "
+            "(there is no CPU or PyTorch fallback for the CLIP-search path)")
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise SummerClipError(f"{_LIB_PATH} does not export {name}") from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().sc_last_error()
+        raise SummerClipError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,410 @@
+// Fused CLIP-search attention for sm_100a:
+//     O[q, c] = sum_k exp(beta * (Qn[q].Kn[k] - 1)) * V[k, c]
+// which is reference  cache_weights_strategy.py:34-35  (A = Q^T K ; W = exp(-beta (1 - A)))
+// followed by         image_attention.py:109           (W @ V)
+// and the Tip-Adapter head  tip_adapter/utils.py:114-116.   The [Nq, Nk] matrix never leaves the SM.
+//
+// One CTA owns a 128-query tile and one class slice (<= 256 classes) and streams the key tiles of
+// its key split.  Per 128-key tile:
+//   GEMM-1  S[128q x 128k]  = Qn_tile . Kn_tile^T      tcgen05.mma, operands TMA-staged (SW128),
+//                                                       fp32 accumulator in TMEM (double buffered)
+//   exp     P = exp2(c1*S - c1), c1 = beta*log2(e)      4 warps: tcgen05.ld -> ex2 -> bf16 -> smem
+//   GEMM-2  O[128q x slice] += P . V_tile               tcgen05.mma, A = P (smem), B = Vt tile,
+//                                                       fp32 accumulator in TMEM for the whole pass
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = exp/epilogue.
+// All operand tiles are K-major rows of 64 bf16 (128 B) with the 128-byte swizzle.
+#include "sc_common.cuh"
+#include "sc_ptx.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+using namespace scptx;
+
+constexpr int kBM = 128;          // queries per CTA (UMMA M)
+constexpr int kBN = 128;          // keys per S tile (UMMA N of GEMM-1 / K extent of GEMM-2)
+constexpr int kBK = 64;           // bf16 per swizzled smem row
+constexpr int kStages = 5;        // operand ring depth
+constexpr int kStageBytes = 32768;  // GEMM-1: Q chunk 16 KB + K chunk 16 KB; GEMM-2: Vt chunk <= 32 KB
+constexpr int kPBytes = 32768;    // one bf16 P tile [128 x 128] as two [128 x 64] swizzled halves
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;    // S0 @0, S1 @128, O @256 (<= 256 columns)
+constexpr int kColS = 0;
+constexpr int kColO = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kPBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct AttnParams {
+  int Nq;
+  int n_dchunks;     // D_pad / 64
+  int n_cols;        // valid output columns (<= C_pad)
+  int slice;         // class-slice width = UMMA N of GEMM-2 (multiple of 16, <= 256)
+  int tiles_total;   // ceil(Nk / 128)
+  int splits;
+  float c1;          // beta * log2(e)
+  float* O;          // [splits, Nq, ldo]
+  long long ldo;
+};
+
+struct Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t p_full[2];
+  uint64_t p_empty[2];
+  uint64_t o_full;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t ring0 = (raw_addr + 1023u) & ~1023u;       // 1024-B aligned (SW128 atoms)
+  const uint32_t pbuf0 = ring0 + kStages * kStageBytes;
+  Bars* bars = reinterpret_cast<Bars*>(smem_raw + (pbuf0 - raw_addr) + 2 * kPBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int c0 = blockIdx.x * p.slice;          // first class of this slice
+  const int q0 = blockIdx.y * kBM;              // first query of this tile
+  const int split = blockIdx.z;
+  const int t0 = static_cast<int>((static_cast<long long>(p.tiles_total) * split) / p.splits);
+  const int t1 = static_cast<int>((static_cast<long long>(p.tiles_total) * (split + 1)) / p.splits);
+  const int T = t1 - t0;
+  const int nd = p.n_dchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars->s_full[b]), 1);
+      mbar_init(smem_u32(&bars->s_empty[b]), 128);
+      mbar_init(smem_u32(&bars->p_full[b]), 128);
+      mbar_init(smem_u32(&bars->p_empty[b]), 1);
+    }
+    mbar_init(smem_u32(&bars->o_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t v_bytes = static_cast<uint32_t>(p.slice) * kBK * 2u;
+      auto load_v = [&](int tile) {
+#pragma unroll 1
+        for (int c = 0; c < kBN / kBK; ++c) {
+          const uint32_t fb = smem_u32(&bars->full[stage]);
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
+          mbar_arrive_expect_tx(fb, v_bytes);
+          tma_load_2d(ring0 + stage * kStageBytes, &tmV, fb, tile * kBN + c * kBK, c0);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      };
+#pragma unroll 1
+      for (int i = 0; i < T; ++i) {
+        const int tile = t0 + i;
+#pragma unroll 1
+        for (int d = 0; d < nd; ++d) {
+          const uint32_t fb = smem_u32(&bars->full[stage]);
+          const uint32_t dst = ring0 + stage * kStageBytes;
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
+          mbar_arrive_expect_tx(fb, kStageBytes);
+          tma_load_2d(dst, &tmQ, fb, d * kBK, q0);
+          tma_load_2d(dst + 16384, &tmK, fb, d * kBK, tile * kBN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (i > 0) load_v(tile - 1);
+      }
+      if (T > 0) load_v(t1 - 1);
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc1 = umma_idesc_bf16(kBM, kBN);
+      const uint32_t idesc2 = umma_idesc_bf16(kBM, static_cast<uint32_t>(p.slice));
+      const uint32_t tmem_o = tmem_base + kColO;
+      auto gemm2 = [&](int j) {
+        const int pb = j & 1;
+        mbar_wait(smem_u32(&bars->p_full[pb]), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kBN / kBK; ++c) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = pbuf0 + pb * kPBytes + c * 16384;
+          const uint32_t b_addr = ring0 + stage * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_ss(tmem_o, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+                    idesc2, (j | c | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bars->empty[stage]));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bars->p_empty[pb]));
+      };
+#pragma unroll 1
+      for (int i = 0; i < T; ++i) {
+        const int sb = i & 1;
+        mbar_wait(smem_u32(&bars->s_empty[sb]), ((i >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_s = tmem_base + kColS + sb * kBN;
+#pragma unroll 1
+        for (int d = 0; d < nd; ++d) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = ring0 + stage * kStageBytes;
+          const uint32_t b_addr = a_addr + 16384;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_ss(tmem_s, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+                    idesc1, (d | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bars->empty[stage]));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bars->s_full[sb]));
+        if (i > 0) gemm2(i - 1);
+      }
+      if (T > 0) gemm2(T - 1);
+      umma_commit(smem_u32(&bars->o_full));
+    }
+  } else {
+    // ===================================================== exp warps (+ epilogue)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // query row within the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float c1 = p.c1;
+    const float neg_c1 = -p.c1;
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+#pragma unroll 1
+    for (int i = 0; i < T; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&bars->s_full[b]), (i >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(smem_u32(&bars->p_empty[b]), ((i >> 1) & 1) ^ 1u);
+      const uint32_t pb = pbuf0 + b * kPBytes;
+#pragma unroll
+      for (int cc = 0; cc < kBN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + lane_addr + kColS + b * kBN + cc * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), c1, neg_c1));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), c1, neg_c1));
+          pk[j] = pack_bf16x2(e0, e1);
+        }
+        // keys cc*32 .. cc*32+31 of this row -> half (cc>>1), 16-byte chunks (cc&1)*4 .. +3
+        const uint32_t half_base = pb + static_cast<uint32_t>(cc >> 1) * 16384u + row_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + j);
+          const uint32_t addr = half_base + ((chunk ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->s_empty[b]));
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bars->p_full[b]));
+    }
+    // ---- epilogue: O slice TMEM -> global partial
+    mbar_wait(smem_u32(&bars->o_full), 0);
+    tc_fence_after();
+    const int q = q0 + row;
+    float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo + c0;
+    const int ncol_here = min(p.slice, p.n_cols - c0);   // may be <= 0 for an all-padding slice
+#pragma unroll 1
+    for (int cc = 0; cc < p.slice / 16; ++cc) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + lane_addr + kColO + cc * 16, r);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = cc * 16 + j;
+          if (c < ncol_here) orow[c] = (T > 0) ? __uint_as_float(r[j]) : 0.0f;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  });
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with row pitch `pitch_elems`; box = [box_rows x 64 cols], SW128.
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems,
+              int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SC_REQUIRE(fn != nullptr, SC_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_elems) * 2u};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SC_REQUIRE(r == CUDA_SUCCESS, SC_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SC_OK;
+}
+
+int class_slice(int64_t C) {
+  // widest slice <= 256 (multiple of 16) that covers C with the fewest, evenly sized slices
+  const int64_t c16 = sc::round_up(C, 16);
+  const int64_t n = sc::ceil_div(c16, 256);
+  return static_cast<int>(sc::round_up(sc::ceil_div(c16, n), 16));
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t sc_pad_dim(int64_t D) { return sc::round_up(D, 64); }
+int64_t sc_pad_keys(int64_t Nk) { return sc::round_up(Nk, 8); }
+int64_t sc_class_slice(int64_t C) { return class_slice(C); }
+int64_t sc_pad_classes(int64_t C) {
+  // n evenly sized slices; idempotent: sc_class_slice(sc_pad_classes(C)) == sc_class_slice(C)
+  const int64_t n = sc::ceil_div(sc::round_up(C, 16), 256);
+  return n * class_slice(C);
+}
+
+int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count) {
+  if (Nq <= 0 || Nk <= 0 || C_pad <= 0) return 1;
+  if (sm_count <= 0) sm_count = 148;
+  const int64_t slice = class_slice(C_pad);
+  const int64_t base = sc::ceil_div(Nq, kBM) * sc::ceil_div(C_pad, slice);
+  const int64_t tiles = sc::ceil_div(Nk, kBN);
+  // cost model: waves * (key tiles per CTA + fixed prologue/epilogue expressed in tiles)
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t smax = tiles < 64 ? tiles : 64;
+  for (int64_t s = 1; s <= smax; ++s) {
+    const double waves = static_cast<double>(sc::ceil_div(base * s, sm_count));
+    const double cost = waves * (static_cast<double>(sc::ceil_div(tiles, s)) + 3.0);
+    if (cost < best_cost * 0.995) { best_cost = cost; best = static_cast<int>(s); }
+  }
+  return best;
+}
+
+int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int64_t Nk,
+                int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
+                int splits, float* O, int64_t ldo, void* stream) {
+  SC_REQUIRE(Qn && Kn && Vt && O, SC_EINVAL, "sc_attn_fwd: null pointer");
+  SC_REQUIRE(Nq > 0 && Nk > 0 && n_cols > 0, SC_ESHAPE, "sc_attn_fwd: empty problem");
+  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_attn_fwd: D_pad=%lld must be a multiple of 64",
+             (long long)D_pad);
+  SC_REQUIRE(Nk_pad >= Nk && Nk_pad % 8 == 0, SC_ESHAPE, "sc_attn_fwd: Nk_pad=%lld must be >= Nk and a multiple of 8",
+             (long long)Nk_pad);
+  const int slice = class_slice(C_pad);
+  SC_REQUIRE(C_pad % slice == 0 && n_cols <= C_pad, SC_ESHAPE,
+             "sc_attn_fwd: C_pad=%lld is not a whole number of %d-wide class slices (use sc_pad_classes)",
+             (long long)C_pad, slice);
+  SC_REQUIRE(ldo >= n_cols, SC_ESHAPE, "sc_attn_fwd: ldo < n_cols");
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(Kn) |
+              reinterpret_cast<uintptr_t>(Vt)) % 16 == 0,
+             SC_EALIGN, "sc_attn_fwd: operand pointers must be 16-byte aligned");
+  SC_REQUIRE(Nq < (1ll << 31) && Nk < (1ll << 31) - 256, SC_ESHAPE, "sc_attn_fwd: Nq/Nk exceed int32 coordinates");
+
+  const int64_t tiles_total = sc::ceil_div(Nk, kBN);
+  if (splits <= 0) {
+    int dev = 0, sms = 148;
+    SC_CUDA(cudaGetDevice(&dev));
+    SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    splits = sc_attn_splits(Nq, Nk, C_pad, sms);
+  }
+  SC_REQUIRE(splits <= tiles_total && splits <= 65535, SC_ESHAPE,
+             "sc_attn_fwd: splits=%d exceeds the %lld key tiles", splits, (long long)tiles_total);
+
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBM)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBN)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmV, Vt, C_pad, Nk_pad, Nk_pad, slice)) != SC_OK) return rc;
+
+  AttnParams p;
+  p.Nq = static_cast<int>(Nq);
+  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.n_cols = static_cast<int>(n_cols);
+  p.slice = slice;
+  p.tiles_total = static_cast<int>(tiles_total);
+  p.splits = splits;
+  p.c1 = beta * 1.4426950408889634f;
+  p.O = O;
+  p.ldo = ldo;
+
+  // per-device attribute; setting it on every call is a few hundred ns and keeps the call stateless
+  SC_CUDA(cudaFuncSetAttribute(sc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+
+  dim3 grid(static_cast<unsigned>(C_pad / slice), static_cast<unsigned>(sc::ceil_div(Nq, kBM)),
+            static_cast<unsigned>(splits));
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: more than 65535 query tiles; chunk the queries");
+  sc_attn_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// Shared host/device helpers for libsummerclip_b200.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/summer_clip_b200.h"
+
+namespace sc {
+
+// thread-local last error (sc_api.cu)
+void set_error(const char* fmt, ...);
+
+#define SC_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ::sc::set_error(__VA_ARGS__);  \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define SC_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::sc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                      __LINE__);                                                         \
+      return static_cast<int>(_e);                                                       \
+    }                                                                                    \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// dispatch on the ABI dtype enum
+#define SC_DISPATCH_DTYPE(dtype, T, ...)                                 \
+  switch (dtype) {                                                       \
+    case SC_F16: { using T = __half; __VA_ARGS__; break; }               \
+    case SC_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }       \
+    case SC_F32: { using T = float; __VA_ARGS__; break; }                \
+    default:                                                             \
+      ::sc::set_error("unsupported dtype %d", (int)(dtype));             \
+      return SC_EINVAL;                                                  \
+  }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// order-preserving float -> uint32 map (larger float => larger key); NaN sorts above +inf,
+// matching torch.topk which treats NaN as the largest value.
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  if (f != f) return 0xFFFFFFFFu;
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+}  // namespace sc

@@ -1,0 +1,201 @@
+// Epilogue-side kernels of the CLIP-search path (all HBM-bound):
+//   sc_merge_partials   : sum of per-split / per-rank partial O tiles (the LSE merge with m == 0)
+//   sc_zero_shot_logits : Z = scale * normalise_cols(X)^T @ T in fp32   image_attention.py:80-83
+//   sc_epilogue         : out = Z + O*alpha, argmax, top-1/top-5 counts  image_attention.py:111-117,
+//                         clip_searcher/utils.py:15-21, clip_adapter/train_adapter.py:156-159,
+//                         tip_adapter/utils.py:10-15
+#include "sc_common.cuh"
+
+namespace {
+
+constexpr int kMaxAlphas = 64;
+struct AlphaList {
+  float a[kMaxAlphas];
+};
+
+__global__ void __launch_bounds__(256)
+merge_kernel(const float* __restrict__ parts, int n_parts, int64_t rows, int64_t cols, int64_t ld,
+             float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = rows * cols;
+  const int64_t part_stride = rows * ld;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    const float* src = parts + r * ld + c;
+    float s = src[0];
+    for (int p = 1; p < n_parts; ++p) s += src[p * part_stride];
+    out[r * ld_out + c] = s;
+  }
+}
+
+// fp32 SIMT GEMM, 64 x 64 output tile per block, 4 x 4 per thread, K step 16.
+//   Z[n, c] = scale / ||X[:, n]|| * sum_d X[d, n] * T[d, c]
+template <typename TX, typename TT>
+__global__ void __launch_bounds__(256)
+zero_shot_kernel(const TX* __restrict__ X, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
+                 const TT* __restrict__ Tm, int64_t C, int64_t ldt, float scale, int normalize,
+                 float* __restrict__ Z, int64_t ldz) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Ts[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;   // class group
+  const int ty = tid >> 4;   // query group
+  const int64_t n0 = static_cast<int64_t>(blockIdx.y) * 64;
+  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const bool n_contig = (stride_n == 1) || (stride_d != 1);
+  float acc[4][4] = {};
+  float ss[4] = {};
+  for (int64_t d0 = 0; d0 < D; d0 += 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = tid + 256 * j;
+      int dd, nn;
+      if (n_contig) { dd = e >> 6; nn = e & 63; } else { nn = e >> 4; dd = e & 15; }
+      const int64_t d = d0 + dd, n = n0 + nn;
+      Xs[dd][nn] = (d < D && n < N) ? sc::to_f32<TX>(X[d * stride_d + n * stride_n]) : 0.f;
+      const int td = e >> 6, tc = e & 63;
+      const int64_t d2 = d0 + td, c = c0 + tc;
+      Ts[td][tc] = (d2 < D && c < C) ? sc::to_f32<TT>(Tm[d2 * ldt + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float xv[4], tv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xv[i] = Xs[k][ty * 4 + i]; tv[i] = Ts[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ss[i] = fmaf(xv[i], xv[i], ss[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], tv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+    const float f = normalize ? scale / sqrtf(ss[i]) : scale;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = c0 + tx * 4 + j;
+      if (c < C) Z[n * ldz + c] = acc[i][j] * f;
+    }
+  }
+}
+
+// one warp per query row; the row (Z and O, 8 KB at C = 1000) is re-read per alpha from L1.
+__global__ void __launch_bounds__(256)
+epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ O, int64_t ldo,
+                const float* __restrict__ rowsum, int64_t Nq, int64_t C, AlphaList alphas, int na,
+                const int32_t* __restrict__ labels, float* __restrict__ out_logits,
+                int32_t* __restrict__ pred, int32_t* __restrict__ top1, int32_t* __restrict__ top5) {
+  __shared__ int32_t s_top1[kMaxAlphas];
+  __shared__ int32_t s_top5[kMaxAlphas];
+  for (int i = threadIdx.x; i < na; i += blockDim.x) { s_top1[i] = 0; s_top5[i] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); q < Nq;
+       q += warps_per_grid) {
+    const float* zrow = Z ? Z + q * ldz : nullptr;
+    const float* orow = O + q * ldo;
+    const float inv = rowsum ? 1.0f / rowsum[q] : 1.0f;
+    const int lab = labels ? labels[q] : -1;
+    for (int ai = 0; ai < na; ++ai) {
+      const float alpha = alphas.a[ai];
+      float vlab = 0.f;
+      if (lab >= 0 && lab < C) {
+        float o = orow[lab];
+        if (rowsum) o *= inv;
+        vlab = __fadd_rn(zrow ? zrow[lab] : 0.f, __fmul_rn(o, alpha));
+      }
+      float best = 0.f;
+      int besti = -1;
+      int ahead = 0;   // classes ranked strictly before the label (value desc, index asc)
+      for (int64_t c = lane; c < C; c += 32) {
+        float o = orow[c];
+        if (rowsum) o *= inv;
+        const float v = __fadd_rn(zrow ? zrow[c] : 0.f, __fmul_rn(o, alpha));
+        if (out_logits) out_logits[(static_cast<int64_t>(ai) * Nq + q) * C + c] = v;
+        if (besti < 0 || v > best) { best = v; besti = static_cast<int>(c); }
+        if (lab >= 0 && (v > vlab || (v == vlab && c < lab))) ++ahead;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi >= 0 && (besti < 0 || ov > best || (ov == best && oi < besti))) { best = ov; besti = oi; }
+        ahead += __shfl_xor_sync(0xffffffffu, ahead, o);
+      }
+      if (lane == 0) {
+        if (pred) pred[static_cast<int64_t>(ai) * Nq + q] = besti;
+        if (lab >= 0 && lab < C) {
+          if (ahead == 0) atomicAdd(&s_top1[ai], 1);
+          if (ahead < 5) atomicAdd(&s_top5[ai], 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
+    if (top1 && s_top1[i]) atomicAdd(&top1[i], s_top1[i]);
+    if (top5 && s_top5[i]) atomicAdd(&top5[i], s_top5[i]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_merge_partials(const float* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld,
+                      float* out, int64_t ld_out, void* stream) {
+  SC_REQUIRE(parts && out, SC_EINVAL, "sc_merge_partials: null pointer");
+  SC_REQUIRE(n_parts >= 1 && rows >= 0 && cols >= 0 && ld >= cols && ld_out >= cols, SC_ESHAPE,
+             "sc_merge_partials: bad shape");
+  if (rows * cols == 0) return SC_OK;
+  const int64_t want = sc::ceil_div(rows * cols, 256);
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+  merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, n_parts, rows, cols, ld, out, ld_out);
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+int sc_zero_shot_logits(const void* X, int x_dtype, int64_t D, int64_t N, int64_t stride_d,
+                        int64_t stride_n, const void* T, int t_dtype, int64_t C, int64_t ldt,
+                        float scale, int normalize, float* Z, int64_t ldz, void* stream) {
+  SC_REQUIRE(X && T && Z, SC_EINVAL, "sc_zero_shot_logits: null pointer");
+  SC_REQUIRE(D > 0 && N >= 0 && C > 0 && ldt >= C && ldz >= C, SC_ESHAPE, "sc_zero_shot_logits: bad shape");
+  if (N == 0) return SC_OK;
+  dim3 grid(static_cast<unsigned>(sc::ceil_div(C, 64)), static_cast<unsigned>(sc::ceil_div(N, 64)));
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_zero_shot_logits: too many rows; chunk the queries");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_DISPATCH_DTYPE(x_dtype, TX, {
+    SC_DISPATCH_DTYPE(t_dtype, TT,
+                      (zero_shot_kernel<TX, TT><<<grid, 256, 0, st>>>(
+                          static_cast<const TX*>(X), D, N, stride_d, stride_n,
+                          static_cast<const TT*>(T), C, ldt, scale, normalize, Z, ldz)));
+  });
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+int sc_epilogue(const float* Z, int64_t ldz, const float* O, int64_t ldo, const float* rowsum,
+                int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
+                float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream) {
+  SC_REQUIRE(O && alphas, SC_EINVAL, "sc_epilogue: null pointer");
+  SC_REQUIRE(na >= 1 && na <= kMaxAlphas, SC_ESHAPE, "sc_epilogue: na=%d must be in [1, %d]", na, kMaxAlphas);
+  SC_REQUIRE(Nq >= 0 && C > 0 && ldo >= C && (Z == nullptr || ldz >= C), SC_ESHAPE, "sc_epilogue: bad shape");
+  if (Nq == 0) return SC_OK;
+  AlphaList al;
+  for (int i = 0; i < na; ++i) al.a[i] = alphas[i];   // alphas is a HOST array
+  const int64_t want = sc::ceil_div(Nq, 8);
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+  epilogue_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      Z, ldz, O, ldo, rowsum, Nq, C, al, na, labels, out_logits, pred, top1, top5);
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// sc_normalize_cast: column L2-normalise + (optional) column gather + transpose + bf16 cast.
+// Reference: cache_weights_strategy.py:19-20 (x / x.norm(dim=0, keepdim=True)) fused with the
+// cache gather K[:, idx] of image_attention.py:55; Tip-Adapter's row normalisation
+// tip_adapter/utils.py:60,84 is the stride_d == 1 case.  HBM-bound: one read of the source bank,
+// one write of the K-major bf16 bank the attention kernel's TMA loads consume.
+#include "sc_common.cuh"
+
+namespace {
+
+// ---- source is feature-major ([D, N], stride_n == 1 fast path; any strides are correct).
+// Block = 32 bank columns.  Pass 1 accumulates the column sums of squares, pass 2 re-reads the
+// 32 x D strip (L2-resident: <= 128 KB per block) and writes it transposed through smem so that
+// both the global reads (along n) and the global writes (along d) are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d,
+                      int64_t stride_n, const int64_t* __restrict__ idx, int64_t n_out,
+                      __nv_bfloat16* __restrict__ dst, int64_t D_pad, int normalize) {
+  __shared__ float tile[64][33];
+  __shared__ float red[8][32];
+  __shared__ float inv_norm[32];
+  __shared__ int64_t col_off[32];
+  const int tx = threadIdx.x & 31;   // column within the strip
+  const int ty = threadIdx.x >> 5;   // 0..7
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 32;
+
+  if (ty == 0) {
+    const int64_t o = n0 + tx;
+    int64_t n = -1;
+    if (o < n_out) n = idx ? idx[o] : o;
+    col_off[tx] = (n >= 0 && n < N) ? n * stride_n : -1;
+  }
+  __syncthreads();
+  const int64_t my_off = col_off[tx];
+
+  if (normalize) {
+    float ss = 0.f;
+    if (my_off >= 0) {
+      for (int64_t d = ty; d < D; d += 8) {
+        const float v = sc::to_f32<T>(src[d * stride_d + my_off]);
+        ss = fmaf(v, v, ss);
+      }
+    }
+    red[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += red[j][tx];
+      inv_norm[tx] = sqrtf(s);   // the NORM; we divide below like the reference does
+    }
+    __syncthreads();
+  }
+  const float nrm = normalize ? inv_norm[tx] : 1.0f;
+
+  for (int64_t d0 = 0; d0 < D_pad; d0 += 64) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t d = d0 + ty + 8 * j;
+      float v = 0.f;
+      if (d < D && my_off >= 0) {
+        v = sc::to_f32<T>(src[d * stride_d + my_off]);
+        if (normalize) v = v / nrm;
+      }
+      tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+    // write: 32 rows (n) x 64 d; thread handles two adjacent d of one row per step
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = ty + 8 * j;            // strip column -> output row
+      const int64_t o = n0 + r;
+      if (o < n_out) {
+        const int d = 2 * tx;
+        __nv_bfloat162 pk = __floats2bfloat162_rn(tile[d][r], tile[d + 1][r]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + o * D_pad + d0 + d) = pk;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- source rows are contiguous along d (stride_d == 1): one warp per output row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_n,
+                 const int64_t* __restrict__ idx, int64_t n_out, __nv_bfloat16* __restrict__ dst,
+                 int64_t D_pad, int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (o >= n_out) return;
+  const int64_t n = idx ? idx[o] : o;
+  const bool ok = (n >= 0 && n < N);
+  const T* row = src + (ok ? n : 0) * stride_n;
+  float nrm = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    if (ok)
+      for (int64_t d = lane; d < D; d += 32) {
+        const float v = sc::to_f32<T>(row[d]);
+        ss = fmaf(v, v, ss);
+      }
+    nrm = sqrtf(sc::warp_sum(ss));
+  }
+  for (int64_t d = 2 * lane; d < D_pad; d += 64) {
+    float a = 0.f, b = 0.f;
+    if (ok && d < D) a = sc::to_f32<T>(row[d]) / nrm;
+    if (ok && d + 1 < D) b = sc::to_f32<T>(row[d + 1]) / nrm;
+    *reinterpret_cast<__nv_bfloat162*>(dst + o * D_pad + d) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+}  // namespace
+
+extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N,
+                                 int64_t stride_d, int64_t stride_n, const int64_t* idx,
+                                 int64_t n_out, void* dst, int64_t D_pad, int normalize,
+                                 void* stream) {
+  SC_REQUIRE(src && dst, SC_EINVAL, "sc_normalize_cast: null pointer");
+  SC_REQUIRE(D > 0 && N >= 0 && n_out >= 0, SC_ESHAPE, "sc_normalize_cast: bad shape");
+  SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE,
+             "sc_normalize_cast: D_pad=%lld must be >= D and a multiple of 64", (long long)D_pad);
+  SC_REQUIRE(idx != nullptr || n_out == N, SC_ESHAPE, "sc_normalize_cast: n_out must equal N without idx");
+  SC_REQUIRE(reinterpret_cast<uintptr_t>(dst) % 4 == 0, SC_EALIGN, "sc_normalize_cast: dst misaligned");
+  if (n_out == 0) return SC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride_d == 1 && stride_n != 1) {
+    const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 8));
+    SC_DISPATCH_DTYPE(src_dtype, T,
+                      (norm_rows_kernel<T><<<blocks, 256, 0, st>>>(
+                          static_cast<const T*>(src), D, N, stride_n, idx, n_out,
+                          static_cast<__nv_bfloat16*>(dst), D_pad, normalize)));
+  } else {
+    const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
+    SC_DISPATCH_DTYPE(src_dtype, T,
+                      (norm_transpose_kernel<T><<<blocks, 256, 0, st>>>(
+                          static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,
+                          static_cast<__nv_bfloat16*>(dst), D_pad, normalize)));
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}

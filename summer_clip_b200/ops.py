@@ -1,0 +1,240 @@
+"""Torch-facing wrappers over the C ABI: device memory and streams come from PyTorch, every
+computation is a call into libsummerclip_b200.so.  CPU tensors are rejected (no fallback)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (SC_BF16, SC_CONF_PROB, SC_CONF_RAW, SC_F16, SC_F32, SC_VALUES_HARD, SC_VALUES_SOFTMAX, check)
+
+_DTYPES = {torch.float16: SC_F16, torch.bfloat16: SC_BF16, torch.float32: SC_F32}
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; expected float16, bfloat16 or float32") from None
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SummerClipError(f"{name} must be a CUDA tensor: the CLIP-search path has no CPU fallback")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pad_dim(D: int) -> int:
+    return int(_lib.load().sc_pad_dim(D))
+
+
+def pad_keys(Nk: int) -> int:
+    return int(_lib.load().sc_pad_keys(Nk))
+
+
+def pad_classes(C: int) -> int:
+    return int(_lib.load().sc_pad_classes(C))
+
+
+def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Tensor] = None,
+                   normalize: bool = True) -> torch.Tensor:
+    """x: [D, N] if feature_major (the reference's on-disk layout, save_features.py:36) else [N, D];
+    any strides.  Returns bf16 [n_out, D_pad], rows L2-normalised, optionally gathered by idx."""
+    _cuda(x, "x")
+    assert x.dim() == 2
+    if feature_major:
+        D, N = x.shape
+        stride_d, stride_n = x.stride()
+    else:
+        N, D = x.shape
+        stride_n, stride_d = x.stride()
+    if idx is not None:
+        idx = _cuda(idx, "idx").to(torch.int64).contiguous()
+        n_out = idx.numel()
+    else:
+        n_out = N
+    D_pad = pad_dim(D)
+    out = torch.empty((n_out, D_pad), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sc_normalize_cast(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
+                                            _ptr(out), D_pad, int(normalize), _stream()), "sc_normalize_cast")
+    return out
+
+
+def rowconf(L: torch.Tensor, scale: float = 1.0, prob: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(confidence fp32 [N], predicted label int32 [N]) of a logits bank L [N, C]."""
+    _cuda(L, "L")
+    assert L.dim() == 2 and L.stride(1) == 1
+    N, C = L.shape
+    conf = torch.empty(N, dtype=torch.float32, device=L.device)
+    label = torch.empty(N, dtype=torch.int32, device=L.device)
+    with torch.cuda.device(L.device):
+        check(_lib.load().sc_rowconf(_ptr(L), _code(L), N, C, L.stride(0) if N > 1 else C, float(scale),
+                                     SC_CONF_PROB if prob else SC_CONF_RAW, _ptr(conf), _ptr(label), _stream()),
+              "sc_rowconf")
+    return conf, label
+
+
+def topk_per_class(conf: torch.Tensor, label: torch.Tensor, n_classes: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(int64 [C, k] row indices, most confident first, -1 padded; int32 [C] counts)."""
+    _cuda(conf, "conf"), _cuda(label, "label")
+    conf = conf.to(torch.float32).contiguous()
+    label = label.to(torch.int32).contiguous()
+    N = conf.numel()
+    lib = _lib.load()
+    ws_bytes = int(lib.sc_topk_workspace_bytes(N, n_classes))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=conf.device)
+    off = (-ws.data_ptr()) % 256
+    out_idx = torch.empty((n_classes, k), dtype=torch.int64, device=conf.device)
+    out_count = torch.empty(n_classes, dtype=torch.int32, device=conf.device)
+    with torch.cuda.device(conf.device):
+        check(lib.sc_topk_per_class(_ptr(conf), _ptr(label), N, n_classes, k, _ptr(out_idx), _ptr(out_count),
+                                    ctypes.c_void_p(ws.data_ptr() + off), ws_bytes, _stream()), "sc_topk_per_class")
+    return out_idx, out_count
+
+
+def select_topk_per_label(conf: torch.Tensor, label: torch.Tensor, n_classes: int, k: int) -> torch.Tensor:
+    """Reference-shaped result of cache_strategy.py:48-59: LongTensor of selected row indices, classes
+    ascending, most confident first within a class."""
+    out_idx, _ = topk_per_class(conf, label, n_classes, k)
+    flat = out_idx.reshape(-1)
+    return flat[flat >= 0]
+
+
+def values_prepare(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torch.Tensor] = None,
+                   labels: Optional[torch.Tensor] = None, softmax_scale: Optional[float] = None,
+                   ones_row: bool = False) -> torch.Tensor:
+    """Transposed bf16 cache values Vt [C_pad, Nk_pad].  softmax_scale=None -> one-hot (argmax of L, or
+    `labels` if given); otherwise softmax(softmax_scale * L, dim=1).  ones_row appends a row of ones at
+    index n_classes (row sums come out of GEMM-2 as an extra class)."""
+    dev = (L if L is not None else labels).device
+    if L is not None:
+        _cuda(L, "L")
+        assert L.dim() == 2 and L.stride(1) == 1
+        N, C = L.shape
+        assert C == n_classes
+        ld = L.stride(0) if N > 1 else C
+    else:
+        N, C, ld = 0, n_classes, n_classes
+    if labels is not None:
+        labels = _cuda(labels, "labels").to(torch.int32).contiguous()
+        n_out = labels.numel()
+    elif idx is not None:
+        idx = _cuda(idx, "idx").to(torch.int64).contiguous()
+        n_out = idx.numel()
+    else:
+        n_out = N
+    C_eff = n_classes + (1 if ones_row else 0)
+    C_pad, Nk_pad = pad_classes(C_eff), pad_keys(max(n_out, 1))
+    Vt = torch.empty((C_pad, Nk_pad), dtype=torch.bfloat16, device=dev)
+    mode = SC_VALUES_HARD if softmax_scale is None else SC_VALUES_SOFTMAX
+    with torch.cuda.device(dev):
+        check(_lib.load().sc_values_prepare(_ptr(L), _code(L) if L is not None else SC_F32, N, C, ld, _ptr(idx),
+                                            _ptr(labels), n_out, mode,
+                                            float(softmax_scale) if softmax_scale is not None else 1.0, _ptr(Vt),
+                                            C_pad, Nk_pad, n_classes if ones_row else -1, _stream()),
+              "sc_values_prepare")
+    return Vt
+
+
+def attn_splits(Nq: int, Nk: int, C_pad: int, device=None) -> int:
+    sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
+    return int(_lib.load().sc_attn_splits(Nq, Nk, C_pad, sms))
+
+
+def merge_partials(parts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum fp32 partials [n_parts, rows, cols] over the first dimension."""
+    _cuda(parts, "parts")
+    assert parts.dim() == 3 and parts.dtype == torch.float32 and parts.is_contiguous()
+    n_parts, rows, cols = parts.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        check(_lib.load().sc_merge_partials(_ptr(parts), n_parts, rows, cols, cols, _ptr(out), out.stride(0),
+                                            _stream()), "sc_merge_partials")
+    return out
+
+
+def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, n_cols: int, beta: float,
+             splits: int = 0, merge: bool = True) -> torch.Tensor:
+    """O[q, c] = sum_k exp(beta (Qn[q].Kn[k] - 1)) Vt[c, k]  ->  fp32 [Nq, n_cols] (or the
+    [splits, Nq, n_cols] partials when merge=False)."""
+    for t, n in ((Qn, "Qn"), (Kn, "Kn"), (Vt, "Vt")):
+        _cuda(t, n)
+        assert t.dtype == torch.bfloat16 and t.is_contiguous(), f"{n} must be contiguous bf16"
+    Nq, D_pad = Qn.shape
+    assert Kn.shape[1] == D_pad and Kn.shape[0] >= n_keys
+    C_pad, Nk_pad = Vt.shape
+    if splits <= 0:
+        splits = attn_splits(Nq, n_keys, C_pad, Qn.device)
+    O = torch.empty((splits, Nq, n_cols), dtype=torch.float32, device=Qn.device)
+    with torch.cuda.device(Qn.device):
+        check(_lib.load().sc_attn_fwd(_ptr(Qn), _ptr(Kn), _ptr(Vt), Nq, n_keys, D_pad, n_cols, C_pad, Nk_pad,
+                                      float(beta), splits, _ptr(O), n_cols, _stream()), "sc_attn_fwd")
+    if not merge:
+        return O
+    if splits == 1:
+        return O[0]
+    return merge_partials(O)
+
+
+def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scale: float = 100.0,
+                     normalize: bool = True) -> torch.Tensor:
+    """Z = scale * normalise(X)^T @ T in fp32 (image_attention.py:80-83).  T is [D, C]."""
+    _cuda(X, "X"), _cuda(T, "T")
+    if feature_major:
+        D, N = X.shape
+        stride_d, stride_n = X.stride()
+    else:
+        N, D = X.shape
+        stride_n, stride_d = X.stride()
+    assert T.dim() == 2 and T.shape[0] == D
+    if T.stride(1) != 1:
+        T = T.contiguous()
+    C = T.shape[1]
+    Z = torch.empty((N, C), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.load().sc_zero_shot_logits(_ptr(X), _code(X), D, N, stride_d, stride_n, _ptr(T), _code(T), C,
+                                              T.stride(0), float(scale), int(normalize), _ptr(Z), C, _stream()),
+              "sc_zero_shot_logits")
+    return Z
+
+
+def epilogue(Z: Optional[torch.Tensor], O: torch.Tensor, alphas: Sequence[float],
+             labels: Optional[torch.Tensor] = None, rowsum: Optional[torch.Tensor] = None,
+             want_logits: bool = False, want_pred: bool = True):
+    """out = Z + O * alpha for each alpha; returns dict(pred int32 [na, Nq], top1/top5 int32 [na] counts,
+    logits fp32 [na, Nq, C] if requested)."""
+    _cuda(O, "O")
+    assert O.dtype == torch.float32 and O.stride(1) == 1
+    Nq, C = O.shape
+    if Z is not None:
+        _cuda(Z, "Z")
+        assert Z.dtype == torch.float32 and Z.shape == O.shape and Z.stride(1) == 1
+    na = len(alphas)
+    dev = O.device
+    arr = (ctypes.c_float * na)(*[float(a) for a in alphas])
+    pred = torch.empty((na, Nq), dtype=torch.int32, device=dev) if want_pred else None
+    logits = torch.empty((na, Nq, C), dtype=torch.float32, device=dev) if want_logits else None
+    top1 = top5 = None
+    if labels is not None:
+        labels = _cuda(labels, "labels").to(torch.int32).contiguous()
+        top1 = torch.zeros(na, dtype=torch.int32, device=dev)
+        top5 = torch.zeros(na, dtype=torch.int32, device=dev)
+    if rowsum is not None:
+        rowsum = _cuda(rowsum, "rowsum").to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        check(_lib.load().sc_epilogue(_ptr(Z), Z.stride(0) if Z is not None else C, _ptr(O), O.stride(0),
+                                      _ptr(rowsum), Nq, C, arr, na, _ptr(labels), _ptr(logits), _ptr(pred),
+                                      _ptr(top1), _ptr(top5), _stream()), "sc_epilogue")
+    return {"pred": pred, "top1": top1, "top5": top5, "logits": logits}
