@@ -48,8 +48,8 @@ int sc_version(void);
 const char* sc_last_error(void);
 
 /* Geometry helpers (host only, no CUDA calls).  The attention kernel consumes
- *   Qn [Nq, D_pad] bf16, Kn [Nk, D_pad] bf16 (rows L2-normalised, K-major),
- *   Vt [C_pad, Nk_pad] bf16 (cache values TRANSPOSED, zero padded),
+ *   Qn [Nq, D_pad], Kn [Nk, D_pad] (bf16 or fp16; rows L2-normalised, K-major),
+ *   Vt [C_pad, Nk_pad] (same type; cache values TRANSPOSED, zero padded),
  * where D_pad = sc_pad_dim(D), Nk_pad = sc_pad_keys(Nk), C_pad = sc_pad_classes(C). */
 int64_t sc_pad_dim(int64_t D);          /* multiple of 64 */
 int64_t sc_pad_keys(int64_t Nk);        /* multiple of 8  */
@@ -60,10 +60,11 @@ int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C cla
  * column gather K[:, idx] of image_attention.py:55).
  *   src: element (d, n) at src[d*stride_d + n*stride_n], d < D, n < N, dtype src_dtype.
  *   idx: optional int64[n_out] column indices (NULL: n_out must equal N, identity).
- *   dst: bf16 [n_out, D_pad]; columns D..D_pad-1 are written as zero.
+ *   dst: [n_out, D_pad] of dst_dtype (SC_BF16 or SC_F16 — the tensor-core operand type, see
+ *        sc_attn_fwd); columns D..D_pad-1 are written as zero.
  *   normalize: 1 = divide by the column's L2 norm (fp32), 0 = cast only. */
 int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
-                      int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst,
+                      int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst, int dst_dtype,
                       int64_t D_pad, int normalize, void* stream);
 
 /* Per-row confidence and predicted label of a logits bank L[N, C] (leading dim ld):
@@ -82,7 +83,8 @@ int sc_topk_per_class(const float* conf, const int32_t* label, int64_t N, int32_
                       int64_t* out_idx, int32_t* out_count, void* workspace, size_t ws_bytes,
                       void* stream);
 
-/* Cache values V = f(L[idx]) written TRANSPOSED as bf16 Vt[C_pad, Nk_pad] (zero padded):
+/* Cache values V = f(L[idx]) written TRANSPOSED as Vt[C_pad, Nk_pad] (vt_dtype SC_BF16 or SC_F16,
+ * zero padded):
  *   SC_VALUES_HARD   : one_hot(argmax_c L)                      (cache_value_strategy.py:15-16)
  *   SC_VALUES_SOFTMAX: softmax(scale * L, dim=1), scale = clip_scale*scale  (:27)
  * idx optional int64[n_out] row gather (image_attention.py:55, L[idx]); labels_override optional
@@ -91,17 +93,20 @@ int sc_topk_per_class(const float* conf, const int32_t* label, int64_t N, int32_
  * ones_row >= 0 additionally sets Vt[ones_row, k] = 1 for k < n_out (row sums for softmax mode). */
 int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C, int64_t ld,
                       const int64_t* idx, const int32_t* labels_override, int64_t n_out, int mode,
-                      float scale, void* Vt, int64_t C_pad, int64_t Nk_pad, int64_t ones_row,
-                      void* stream);
+                      float scale, void* Vt, int vt_dtype, int64_t C_pad, int64_t Nk_pad,
+                      int64_t ones_row, void* stream);
 
 /* Fused attention (cache_weights_strategy.py:34-35 + image_attention.py:109, never
  * materialising the [Nq, Nk] matrix):
  *     O[s, q, c] = sum_{k in split s} exp(beta * (Qn[q].Kn[k] - 1)) * Vt[c, k]
- * for c < n_cols (n_cols <= C_pad).  O is fp32 [splits, Nq, ldo]; the caller sums the splits
+ * for c < n_cols (n_cols <= C_pad).  Qn, Kn, Vt (and the on-chip weights P) all have type op_dtype:
+ * SC_BF16 or SC_F16, both with fp32 accumulation at the same tensor-core rate; every operand of
+ * this path lies in [-1, 1], where fp16 carries 3 more mantissa bits than bf16.
+ * O is fp32 [splits, Nq, ldo]; the caller sums the splits
  * (sc_merge_partials).  splits >= 1 partitions the key tiles so that small query batches still
  * fill the GPU; splits = 0 lets the library choose (query with sc_attn_splits). */
 int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count);
-int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int64_t Nk,
+int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,
                 int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
                 int splits, float* O, int64_t ldo, void* stream);
 

@@ -201,12 +201,16 @@ def search_hp(search_scale, search_step, cache_keys, cache_values, features, lab
 
 # --------------------------------------------------------------------------- synthetic banks
 def synthetic_banks(n_query: int, n_key: int, dim: int, n_classes: int, seed: int, sigma: float = 1.0,
-                    sigma_text: float = 0.5, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+                    sigma_text: float = 3.0, shared: float = 1.0, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
     """clustered banks stored feature-major ([D, N]) like save_features.py:36.
-    prototypes mu_c ~ N(0, I) normalised; x = mu_y + sigma/sqrt(D) * eps (left UN-normalised, random
-    positive scale per sample); T[:, c] = normalise(mu_c + sigma_text/sqrt(D) * eps); L = K_norm^T T."""
+    Class prototypes mu_c = normalise(shared * u0 + g_c / sqrt(D)) share a common direction u0 (CLIP
+    embeddings of different classes are far from orthogonal; with shared = 1 prototypes have cosine
+    ~0.5).  Samples x = mu_y + sigma / sqrt(D) * eps are left UN-normalised (random positive scale);
+    the text classifier T[:, c] = normalise(mu_c + sigma_text / sqrt(D) * eps) is a noisy copy of the
+    prototypes so zero-shot accuracy is well below 100 %; L = K_norm^T T (save_image_outs.py:25)."""
     g = torch.Generator().manual_seed(seed)
-    protos = torch.nn.functional.normalize(torch.randn(n_classes, dim, generator=g), dim=1)
+    u0 = torch.nn.functional.normalize(torch.randn(dim, generator=g), dim=0)
+    protos = torch.nn.functional.normalize(shared * u0 + torch.randn(n_classes, dim, generator=g) / dim ** 0.5, dim=1)
     yq = torch.randint(0, n_classes, (n_query,), generator=g)
     yk = torch.randint(0, n_classes, (n_key,), generator=g)
     s = sigma / dim ** 0.5

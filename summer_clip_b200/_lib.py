@@ -25,16 +25,16 @@ SIGNATURES = {
     "sc_pad_classes": (c_int64, [c_int64]),
     "sc_class_slice": (c_int64, [c_int64]),
     "sc_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
-                                  c_void_p, c_int64, c_int, c_void_p]),
+                                  c_void_p, c_int, c_int64, c_int, c_void_p]),
     "sc_rowconf": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p,
                            c_void_p]),
     "sc_topk_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "sc_topk_per_class": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
     "sc_values_prepare": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
-                                  c_float, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+                                  c_float, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "sc_attn_splits": (c_int, [c_int64, c_int64, c_int64, c_int]),
-    "sc_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+    "sc_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                             c_float, c_int, c_void_p, c_int64, c_void_p]),
     "sc_merge_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "sc_zero_shot_logits": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,

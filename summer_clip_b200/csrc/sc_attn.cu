@@ -43,6 +43,8 @@ struct AttnParams {
   int tiles_total;   // ceil(Nk / 128)
   int splits;
   float c1;          // beta * log2(e)
+  float c0;          // exponent offset: -c1 (+ kPShift for fp16 operands)
+  float o_scale;     // 2^-kPShift undoes the offset in the epilogue
   float* O;          // [splits, Nq, ldo]
   long long ldo;
 };
@@ -58,17 +60,26 @@ struct Bars {
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (kF16)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// fp16 weights are stored as 2^kPShift * exp(beta (A - 1)) <= 2^kPShift * (1 + eps): the offset moves
+// small weights out of the fp16 subnormal range at no cost (folded into the exponent FMA) and is
+// removed from the fp32 accumulator in the epilogue.
+constexpr float kPShift = 8.0f;
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -153,8 +164,8 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc1 = umma_idesc_bf16(kBM, kBN);
-      const uint32_t idesc2 = umma_idesc_bf16(kBM, static_cast<uint32_t>(p.slice));
+      const uint32_t idesc1 = umma_idesc_16b(kBM, kBN, kF16);
+      const uint32_t idesc2 = umma_idesc_16b(kBM, static_cast<uint32_t>(p.slice), kF16);
       const uint32_t tmem_o = tmem_base + kColO;
       auto gemm2 = [&](int j) {
         const int pb = j & 1;
@@ -208,7 +219,8 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = quad * 32 + lane;          // query row within the tile
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float c1 = p.c1;
-    const float neg_c1 = -p.c1;
+    const float neg_c1 = p.c0;
+    const float o_scale = p.o_scale;
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
 #pragma unroll 1
@@ -228,7 +240,7 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < 16; ++j) {
           const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), c1, neg_c1));
           const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), c1, neg_c1));
-          pk[j] = pack_bf16x2(e0, e1);
+          pk[j] = pack_16x2<kF16>(e0, e1);
         }
         // keys cc*32 .. cc*32+31 of this row -> half (cc>>1), 16-byte chunks (cc&1)*4 .. +3
         const uint32_t half_base = pb + static_cast<uint32_t>(cc >> 1) * 16384u + row_off;
@@ -261,7 +273,7 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int c = cc * 16 + j;
-          if (c < ncol_here) orow[c] = (T > 0) ? __uint_as_float(r[j]) : 0.0f;
+          if (c < ncol_here) orow[c] = (T > 0) ? __uint_as_float(r[j]) * o_scale : 0.0f;
         }
       }
     }
@@ -296,16 +308,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] with row pitch `pitch_elems`; box = [box_rows x 64 cols], SW128.
+// 16-bit row-major [rows, cols] with row pitch `pitch_elems`; box = [box_rows x 64 cols], SW128.
 int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems,
-              int box_rows) {
+              int box_rows, bool is_f16) {
   EncodeTiledFn fn = get_encode_fn();
   SC_REQUIRE(fn != nullptr, SC_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_elems) * 2u};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+  CUresult r = fn(m, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SC_REQUIRE(r == CUDA_SUCCESS, SC_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -350,11 +362,13 @@ int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count) {
   return best;
 }
 
-int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int64_t Nk,
+int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,
                 int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
                 int splits, float* O, int64_t ldo, void* stream) {
   SC_REQUIRE(Qn && Kn && Vt && O, SC_EINVAL, "sc_attn_fwd: null pointer");
+  SC_REQUIRE(op_dtype == SC_F16 || op_dtype == SC_BF16, SC_EINVAL, "sc_attn_fwd: op_dtype must be SC_F16 or SC_BF16");
   SC_REQUIRE(Nq > 0 && Nk > 0 && n_cols > 0, SC_ESHAPE, "sc_attn_fwd: empty problem");
+  const bool f16 = (op_dtype == SC_F16);
   SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_attn_fwd: D_pad=%lld must be a multiple of 64",
              (long long)D_pad);
   SC_REQUIRE(Nk_pad >= Nk && Nk_pad % 8 == 0, SC_ESHAPE, "sc_attn_fwd: Nk_pad=%lld must be >= Nk and a multiple of 8",
@@ -381,9 +395,9 @@ int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int6
 
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBM)) != SC_OK) return rc;
-  if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBN)) != SC_OK) return rc;
-  if ((rc = make_tmap(&tmV, Vt, C_pad, Nk_pad, Nk_pad, slice)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBM, f16)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBN, f16)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmV, Vt, C_pad, Nk_pad, Nk_pad, slice, f16)) != SC_OK) return rc;
 
   AttnParams p;
   p.Nq = static_cast<int>(Nq);
@@ -393,16 +407,19 @@ int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int64_t Nq, int6
   p.tiles_total = static_cast<int>(tiles_total);
   p.splits = splits;
   p.c1 = beta * 1.4426950408889634f;
+  p.c0 = -p.c1 + (f16 ? kPShift : 0.0f);
+  p.o_scale = f16 ? exp2f(-kPShift) : 1.0f;
   p.O = O;
   p.ldo = ldo;
 
   // per-device attribute; setting it on every call is a few hundred ns and keeps the call stateless
-  SC_CUDA(cudaFuncSetAttribute(sc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  auto kernel = f16 ? sc_attn_kernel<true> : sc_attn_kernel<false>;
+  SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
 
   dim3 grid(static_cast<unsigned>(C_pad / slice), static_cast<unsigned>(sc::ceil_div(Nq, kBM)),
             static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: more than 65535 query tiles; chunk the queries");
-  sc_attn_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }

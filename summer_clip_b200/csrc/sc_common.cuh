@@ -43,6 +43,37 @@ __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// two fp32 -> one 32-bit word holding two 16-bit operands (lo in the low half)
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// dispatch on the tensor-core operand type (fp16 or bf16)
+#define SC_DISPATCH_OP(dtype, T, ...)                                          \
+  switch (dtype) {                                                             \
+    case SC_F16: { using T = __half; __VA_ARGS__; break; }                     \
+    case SC_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }             \
+    default:                                                                   \
+      ::sc::set_error("operand dtype %d must be SC_F16 or SC_BF16", (int)(dtype)); \
+      return SC_EINVAL;                                                        \
+  }
+
 // dispatch on the ABI dtype enum
 #define SC_DISPATCH_DTYPE(dtype, T, ...)                                 \
   switch (dtype) {                                                       \

@@ -1,4 +1,4 @@
-// sc_normalize_cast: column L2-normalise + (optional) column gather + transpose + bf16 cast.
+// sc_normalize_cast: column L2-normalise + (optional) column gather + transpose + bf16/fp16 cast.
 // Reference: cache_weights_strategy.py:19-20 (x / x.norm(dim=0, keepdim=True)) fused with the
 // cache gather K[:, idx] of image_attention.py:55; Tip-Adapter's row normalisation
 // tip_adapter/utils.py:60,84 is the stride_d == 1 case.  HBM-bound: one read of the source bank,
@@ -11,11 +11,11 @@ namespace {
 // Block = 32 bank columns.  Pass 1 accumulates the column sums of squares, pass 2 re-reads the
 // 32 x D strip (L2-resident: <= 128 KB per block) and writes it transposed through smem so that
 // both the global reads (along n) and the global writes (along d) are coalesced.
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d,
                       int64_t stride_n, const int64_t* __restrict__ idx, int64_t n_out,
-                      __nv_bfloat16* __restrict__ dst, int64_t D_pad, int normalize) {
+                      TO* __restrict__ dst, int64_t D_pad, int normalize) {
   __shared__ float tile[64][33];
   __shared__ float red[8][32];
   __shared__ float inv_norm[32];
@@ -72,8 +72,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
       const int64_t o = n0 + r;
       if (o < n_out) {
         const int d = 2 * tx;
-        __nv_bfloat162 pk = __floats2bfloat162_rn(tile[d][r], tile[d + 1][r]);
-        *reinterpret_cast<__nv_bfloat162*>(dst + o * D_pad + d0 + d) = pk;
+        *reinterpret_cast<uint32_t*>(dst + o * D_pad + d0 + d) = sc::pack2<TO>(tile[d][r], tile[d + 1][r]);
       }
     }
     __syncthreads();
@@ -81,10 +80,10 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
 }
 
 // ---- source rows are contiguous along d (stride_d == 1): one warp per output row.
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_n,
-                 const int64_t* __restrict__ idx, int64_t n_out, __nv_bfloat16* __restrict__ dst,
+                 const int64_t* __restrict__ idx, int64_t n_out, TO* __restrict__ dst,
                  int64_t D_pad, int normalize) {
   const int lane = threadIdx.x & 31;
   const int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -106,7 +105,7 @@ norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride
     float a = 0.f, b = 0.f;
     if (ok && d < D) a = sc::to_f32<T>(row[d]) / nrm;
     if (ok && d + 1 < D) b = sc::to_f32<T>(row[d + 1]) / nrm;
-    *reinterpret_cast<__nv_bfloat162*>(dst + o * D_pad + d) = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<uint32_t*>(dst + o * D_pad + d) = sc::pack2<TO>(a, b);
   }
 }
 
@@ -114,8 +113,8 @@ norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride
 
 extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N,
                                  int64_t stride_d, int64_t stride_n, const int64_t* idx,
-                                 int64_t n_out, void* dst, int64_t D_pad, int normalize,
-                                 void* stream) {
+                                 int64_t n_out, void* dst, int dst_dtype, int64_t D_pad,
+                                 int normalize, void* stream) {
   SC_REQUIRE(src && dst, SC_EINVAL, "sc_normalize_cast: null pointer");
   SC_REQUIRE(D > 0 && N >= 0 && n_out >= 0, SC_ESHAPE, "sc_normalize_cast: bad shape");
   SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE,
@@ -126,16 +125,20 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (stride_d == 1 && stride_n != 1) {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 8));
-    SC_DISPATCH_DTYPE(src_dtype, T,
-                      (norm_rows_kernel<T><<<blocks, 256, 0, st>>>(
-                          static_cast<const T*>(src), D, N, stride_n, idx, n_out,
-                          static_cast<__nv_bfloat16*>(dst), D_pad, normalize)));
+    SC_DISPATCH_OP(dst_dtype, TO, {
+      SC_DISPATCH_DTYPE(src_dtype, T,
+                        (norm_rows_kernel<T, TO><<<blocks, 256, 0, st>>>(
+                            static_cast<const T*>(src), D, N, stride_n, idx, n_out,
+                            static_cast<TO*>(dst), D_pad, normalize)));
+    });
   } else {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
-    SC_DISPATCH_DTYPE(src_dtype, T,
-                      (norm_transpose_kernel<T><<<blocks, 256, 0, st>>>(
-                          static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,
-                          static_cast<__nv_bfloat16*>(dst), D_pad, normalize)));
+    SC_DISPATCH_OP(dst_dtype, TO, {
+      SC_DISPATCH_DTYPE(src_dtype, T,
+                        (norm_transpose_kernel<T, TO><<<blocks, 256, 0, st>>>(
+                            static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,
+                            static_cast<TO*>(dst), D_pad, normalize)));
+    });
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;

@@ -212,11 +212,12 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// UMMA instruction descriptor, kind::f16: bf16 x bf16 -> fp32, A and B K-major, dense.
-//   c_format[4,6)=1 (F32)  a_format[7,10)=1 (BF16)  b_format[10,13)=1 (BF16)
+// UMMA instruction descriptor, kind::f16: (bf16 | fp16)^2 -> fp32, A and B K-major, dense.
+//   c_format[4,6)=1 (F32)  a_format[7,10), b_format[10,13): 0 = F16, 1 = BF16
 //   a_major bit15=0  b_major bit16=0  n_dim[17,23)=N>>3  m_dim[24,29)=M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_16b(uint32_t M, uint32_t N, bool is_f16) {
+  const uint32_t fmt = is_f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace scptx

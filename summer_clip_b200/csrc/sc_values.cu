@@ -9,11 +9,11 @@
 namespace {
 
 // HARD: Vt is pre-zeroed; one warp per cache row scatters a single 1.0.
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 values_hard_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
                    const int64_t* __restrict__ idx, const int32_t* __restrict__ labels_override,
-                   int64_t n_out, __nv_bfloat16* __restrict__ Vt, int64_t Nk_pad) {
+                   int64_t n_out, TO* __restrict__ Vt, int64_t Nk_pad) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   for (int64_t o = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -26,18 +26,19 @@ values_hard_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
       if (r < 0 || r >= N) continue;
       lab = sc::row_argmax<T, false>(L + r * ld, C, lane).i;
     }
-    if (lane == 0 && lab >= 0 && lab < C) Vt[static_cast<int64_t>(lab) * Nk_pad + o] = __float2bfloat16(1.0f);
+    if (lane == 0 && lab >= 0 && lab < C) Vt[static_cast<int64_t>(lab) * Nk_pad + o] = sc::from_f32<TO>(1.0f);
   }
 }
 
 // SOFTMAX: block = 32 cache rows.  Each warp computes 4 row softmaxes into a [C][32] bf16 smem
 // tile; the tile is then written out class by class (64 contiguous bytes per class row).
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 values_softmax_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
                       const int64_t* __restrict__ idx, int64_t n_out, float scale,
-                      __nv_bfloat16* __restrict__ Vt, int64_t Nk_pad) {
-  extern __shared__ __nv_bfloat16 tile[];   // [C][32 + 2] (pad: conflict-free column writes)
+                      TO* __restrict__ Vt, int64_t Nk_pad) {
+  extern __shared__ uint16_t tile_raw[];    // [C][32 + 2] (pad: conflict-free column writes)
+  TO* tile = reinterpret_cast<TO*>(tile_raw);
   constexpr int kLd = 34;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -48,7 +49,7 @@ values_softmax_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
     int64_t r = -1;
     if (o < n_out) r = idx ? idx[o] : o;
     if (r < 0 || r >= N) {
-      for (int64_t c = lane; c < C; c += 32) tile[c * kLd + col] = __float2bfloat16(0.f);
+      for (int64_t c = lane; c < C; c += 32) tile[c * kLd + col] = sc::from_f32<TO>(0.f);
       continue;
     }
     const T* row = L + r * ld;
@@ -58,7 +59,7 @@ values_softmax_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
     const float inv = 1.0f / s;
     for (int64_t c = lane; c < C; c += 32) {
       const float e = expf(__fmul_rn(sc::to_f32<T>(row[c]), scale) - tmax);
-      tile[c * kLd + col] = __float2bfloat16(e * inv);
+      tile[c * kLd + col] = sc::from_f32<TO>(e * inv);
     }
   }
   __syncthreads();
@@ -70,17 +71,18 @@ values_softmax_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
   }
 }
 
-__global__ void ones_row_kernel(__nv_bfloat16* __restrict__ row, int64_t n) {
+template <typename TO>
+__global__ void ones_row_kernel(TO* __restrict__ row, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) row[i] = __float2bfloat16(1.0f);
+  if (i < n) row[i] = sc::from_f32<TO>(1.0f);
 }
 
 }  // namespace
 
 extern "C" int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C, int64_t ld,
                                  const int64_t* idx, const int32_t* labels_override, int64_t n_out,
-                                 int mode, float scale, void* Vt, int64_t C_pad, int64_t Nk_pad,
-                                 int64_t ones_row, void* stream) {
+                                 int mode, float scale, void* Vt, int vt_dtype, int64_t C_pad,
+                                 int64_t Nk_pad, int64_t ones_row, void* stream) {
   SC_REQUIRE(Vt, SC_EINVAL, "sc_values_prepare: null Vt");
   SC_REQUIRE(L || (labels_override && mode == SC_VALUES_HARD), SC_EINVAL, "sc_values_prepare: null L");
   SC_REQUIRE(C > 0 && C_pad >= C && Nk_pad >= n_out && n_out >= 0, SC_ESHAPE, "sc_values_prepare: bad shape");
@@ -89,31 +91,34 @@ extern "C" int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C,
   SC_REQUIRE(ones_row < C_pad, SC_ESHAPE, "sc_values_prepare: ones_row outside Vt");
   SC_REQUIRE(L == nullptr || ld >= C, SC_ESHAPE, "sc_values_prepare: ld < C");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SC_CUDA(cudaMemsetAsync(Vt, 0, static_cast<size_t>(C_pad) * Nk_pad * sizeof(__nv_bfloat16), st));
+  SC_REQUIRE(vt_dtype == SC_F16 || vt_dtype == SC_BF16, SC_EINVAL, "sc_values_prepare: vt_dtype must be SC_F16 or SC_BF16");
+  SC_CUDA(cudaMemsetAsync(Vt, 0, static_cast<size_t>(C_pad) * Nk_pad * 2, st));
   if (n_out > 0) {
-    __nv_bfloat16* vt = static_cast<__nv_bfloat16*>(Vt);
-    if (mode == SC_VALUES_HARD) {
-      const int64_t want = sc::ceil_div(n_out, 8);
-      const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
-      if (L == nullptr) dtype = SC_F32;
-      SC_DISPATCH_DTYPE(dtype, T,
-                        (values_hard_kernel<T><<<blocks, 256, 0, st>>>(
-                            static_cast<const T*>(L), N, C, ld, idx, labels_override, n_out, vt, Nk_pad)));
-    } else {
-      const size_t smem = static_cast<size_t>(C) * 34 * sizeof(__nv_bfloat16);
-      SC_REQUIRE(smem <= 200 * 1024, SC_EUNSUPPORTED, "sc_values_prepare: C=%lld too large for the softmax tile", (long long)C);
-      const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
-      SC_DISPATCH_DTYPE(dtype, T, {
-        SC_CUDA(cudaFuncSetAttribute(values_softmax_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-        values_softmax_kernel<T><<<blocks, 256, smem, st>>>(static_cast<const T*>(L), N, C, ld, idx,
-                                                            n_out, scale, vt, Nk_pad);
-      });
-    }
-    if (ones_row >= 0) {
-      ones_row_kernel<<<static_cast<unsigned>(sc::ceil_div(n_out, 256)), 256, 0, st>>>(
-          vt + ones_row * Nk_pad, n_out);
-    }
+    if (L == nullptr) dtype = SC_F32;
+    SC_DISPATCH_OP(vt_dtype, TO, {
+      TO* vt = static_cast<TO*>(Vt);
+      if (mode == SC_VALUES_HARD) {
+        const int64_t want = sc::ceil_div(n_out, 8);
+        const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+        SC_DISPATCH_DTYPE(dtype, T,
+                          (values_hard_kernel<T, TO><<<blocks, 256, 0, st>>>(
+                              static_cast<const T*>(L), N, C, ld, idx, labels_override, n_out, vt, Nk_pad)));
+      } else {
+        const size_t smem = static_cast<size_t>(C) * 34 * 2;
+        SC_REQUIRE(smem <= 200 * 1024, SC_EUNSUPPORTED, "sc_values_prepare: C=%lld too large for the softmax tile", (long long)C);
+        const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
+        SC_DISPATCH_DTYPE(dtype, T, {
+          SC_CUDA(cudaFuncSetAttribute(values_softmax_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+          values_softmax_kernel<T, TO><<<blocks, 256, smem, st>>>(static_cast<const T*>(L), N, C, ld, idx,
+                                                                  n_out, scale, vt, Nk_pad);
+        });
+      }
+      if (ones_row >= 0) {
+        ones_row_kernel<TO><<<static_cast<unsigned>(sc::ceil_div(n_out, 256)), 256, 0, st>>>(
+            vt + ones_row * Nk_pad, n_out);
+      }
+    });
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;

@@ -10,7 +10,22 @@ import torch
 from . import _lib
 from ._lib import (SC_BF16, SC_CONF_PROB, SC_CONF_RAW, SC_F16, SC_F32, SC_VALUES_HARD, SC_VALUES_SOFTMAX, check)
 
+import os
+
 _DTYPES = {torch.float16: SC_F16, torch.bfloat16: SC_BF16, torch.float32: SC_F32}
+
+# Tensor-core operand type of the attention path (Qn, Kn, Vt and the on-chip weights P); fp32
+# accumulation either way, same tcgen05 rate.  Every operand lies in [-1, 1], where fp16 has 3 more
+# mantissa bits than bf16 (DESIGN.md "Precision").  Override with SUMMER_CLIP_B200_OP_DTYPE=bf16.
+OP_DTYPE = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "f16": torch.float16, "fp16": torch.float16,
+            "float16": torch.float16}[os.environ.get("SUMMER_CLIP_B200_OP_DTYPE", "fp16").lower()]
+
+
+def _op(dtype: Optional[torch.dtype]) -> torch.dtype:
+    dtype = OP_DTYPE if dtype is None else dtype
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError(f"operand dtype must be float16 or bfloat16, got {dtype}")
+    return dtype
 
 
 def _code(t: torch.Tensor) -> int:
@@ -47,9 +62,11 @@ def pad_classes(C: int) -> int:
 
 
 def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Tensor] = None,
-                   normalize: bool = True) -> torch.Tensor:
+                   normalize: bool = True, op_dtype: Optional[torch.dtype] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [D, N] if feature_major (the reference's on-disk layout, save_features.py:36) else [N, D];
-    any strides.  Returns bf16 [n_out, D_pad], rows L2-normalised, optionally gathered by idx."""
+    any strides.  Returns [n_out, D_pad] of op_dtype, rows L2-normalised, optionally gathered by idx.
+    `out` (optional) is a preallocated contiguous [>= n_out, D_pad] buffer of op_dtype."""
     _cuda(x, "x")
     assert x.dim() == 2
     if feature_major:
@@ -64,10 +81,15 @@ def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Ten
     else:
         n_out = N
     D_pad = pad_dim(D)
-    out = torch.empty((n_out, D_pad), dtype=torch.bfloat16, device=x.device)
+    op_dtype = _op(op_dtype if out is None else out.dtype)
+    if out is None:
+        out = torch.empty((n_out, D_pad), dtype=op_dtype, device=x.device)
+    else:
+        assert out.is_cuda and out.is_contiguous() and out.shape[1] == D_pad and out.shape[0] >= n_out
     with torch.cuda.device(x.device):
         check(_lib.load().sc_normalize_cast(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
-                                            _ptr(out), D_pad, int(normalize), _stream()), "sc_normalize_cast")
+                                            _ptr(out), _code(out), D_pad, int(normalize), _stream()),
+              "sc_normalize_cast")
     return out
 
 
@@ -113,8 +135,8 @@ def select_topk_per_label(conf: torch.Tensor, label: torch.Tensor, n_classes: in
 
 def values_prepare(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torch.Tensor] = None,
                    labels: Optional[torch.Tensor] = None, softmax_scale: Optional[float] = None,
-                   ones_row: bool = False) -> torch.Tensor:
-    """Transposed bf16 cache values Vt [C_pad, Nk_pad].  softmax_scale=None -> one-hot (argmax of L, or
+                   ones_row: bool = False, op_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Transposed cache values Vt [C_pad, Nk_pad] of op_dtype.  softmax_scale=None -> one-hot (argmax of L, or
     `labels` if given); otherwise softmax(softmax_scale * L, dim=1).  ones_row appends a row of ones at
     index n_classes (row sums come out of GEMM-2 as an extra class)."""
     dev = (L if L is not None else labels).device
@@ -136,13 +158,13 @@ def values_prepare(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torc
         n_out = N
     C_eff = n_classes + (1 if ones_row else 0)
     C_pad, Nk_pad = pad_classes(C_eff), pad_keys(max(n_out, 1))
-    Vt = torch.empty((C_pad, Nk_pad), dtype=torch.bfloat16, device=dev)
+    Vt = torch.empty((C_pad, Nk_pad), dtype=_op(op_dtype), device=dev)
     mode = SC_VALUES_HARD if softmax_scale is None else SC_VALUES_SOFTMAX
     with torch.cuda.device(dev):
         check(_lib.load().sc_values_prepare(_ptr(L), _code(L) if L is not None else SC_F32, N, C, ld, _ptr(idx),
                                             _ptr(labels), n_out, mode,
                                             float(softmax_scale) if softmax_scale is not None else 1.0, _ptr(Vt),
-                                            C_pad, Nk_pad, n_classes if ones_row else -1, _stream()),
+                                            _code(Vt), C_pad, Nk_pad, n_classes if ones_row else -1, _stream()),
               "sc_values_prepare")
     return Vt
 
@@ -171,7 +193,8 @@ def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, 
     [splits, Nq, n_cols] partials when merge=False)."""
     for t, n in ((Qn, "Qn"), (Kn, "Kn"), (Vt, "Vt")):
         _cuda(t, n)
-        assert t.dtype == torch.bfloat16 and t.is_contiguous(), f"{n} must be contiguous bf16"
+        assert t.dtype == Qn.dtype and t.dtype in (torch.float16, torch.bfloat16) and t.is_contiguous(), \
+            f"{n} must be contiguous fp16/bf16 (all three of one type)"
     Nq, D_pad = Qn.shape
     assert Kn.shape[1] == D_pad and Kn.shape[0] >= n_keys
     C_pad, Nk_pad = Vt.shape
@@ -179,7 +202,7 @@ def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, 
         splits = attn_splits(Nq, n_keys, C_pad, Qn.device)
     O = torch.empty((splits, Nq, n_cols), dtype=torch.float32, device=Qn.device)
     with torch.cuda.device(Qn.device):
-        check(_lib.load().sc_attn_fwd(_ptr(Qn), _ptr(Kn), _ptr(Vt), Nq, n_keys, D_pad, n_cols, C_pad, Nk_pad,
+        check(_lib.load().sc_attn_fwd(_ptr(Qn), _ptr(Kn), _ptr(Vt), _code(Qn), Nq, n_keys, D_pad, n_cols, C_pad, Nk_pad,
                                       float(beta), splits, _ptr(O), n_cols, _stream()), "sc_attn_fwd")
     if not merge:
         return O
