@@ -1,0 +1,393 @@
+"""Benchmark of the CLIP-search hot path (BASELINE.json metric: queries/sec on the ImageNet-shaped
+search, 50k queries x 1.28M keys x 1024-d, 1000 classes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full pass of the hot path over the query bank: normalise/cast the queries, zero-shot
+logits, fused attention against the resident key bank, cross-split/rank merge, alpha epilogue with
+accuracy counters.  The key bank (normalised K-major keys + transposed one-hot values) is built once
+before the timed region, like the reference's loaded caches; its build time is reported separately.
+With N > 1 the KEY bank is sharded across ranks (strong scaling): NCCL all-gather of the partial O
+tiles + merge kernel.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (Nq, Nk, D, C, description)
+    "imagenet_rn50": (50000, 1281167, 1024, 1000, "cfg3 ImageNet CLIP-search RN50: 50k val x 1.28M train keys x 1024-d, 1000 classes, hard values, beta=5.5, alpha=1"),
+    "imagenet_vitl14": (50000, 1281167, 768, 1000, "cfg4 ImageNet CLIP-search ViT-L/14: 768-d"),
+    "tip_imagenet_16shot": (50000, 16000, 1024, 1000, "cfg2 Tip-Adapter ImageNet 16-shot cache head"),
+    "sun397": (19850, 19850, 1024, 397, "cfg1 SUN397-shaped image attention"),
+    "tiny": (2048, 16384, 256, 100, "smoke-sized"),
+}
+BETA, ALPHA = 5.5, 1.0
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": float(p["bf16_tflops"]), "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", 0.0)),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    except Exception:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons DURING the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_banks(torch, nq, nk_lo, nk_hi, dim, n_classes, seed, device):
+    """Synthetic clustered banks in the reference's on-disk layout: fp16 feature-major
+    [D, N] image features (save_features.py:36), fp16 logits bank L = K_norm^T T [N, C]
+    (save_image_outs.py:25).  Only keys [nk_lo, nk_hi) are generated (this rank's shard)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    u0 = torch.nn.functional.normalize(torch.randn(dim, generator=g, device=device), dim=0)
+    protos = torch.nn.functional.normalize(u0 + torch.randn(n_classes, dim, generator=g, device=device) / dim ** 0.5, dim=1)
+    text = torch.nn.functional.normalize(protos + 3.0 / dim ** 0.5 * torch.randn(n_classes, dim, generator=g, device=device), dim=1)
+    yq = torch.randint(0, n_classes, (nq,), generator=g, device=device)
+    q = (protos[yq] + torch.randn(nq, dim, generator=g, device=device) / dim ** 0.5)
+    q_bank = q.t().contiguous().half()
+    n_local = nk_hi - nk_lo
+    k_bank = torch.empty((dim, n_local), dtype=torch.float16, device=device)
+    outs = torch.empty((n_local, n_classes), dtype=torch.float16, device=device)
+    gk = torch.Generator(device=device)
+    step = 1 << 16
+    for s in range(0, n_local, step):
+        e = min(n_local, s + step)
+        gk.manual_seed(seed * 1000003 + (nk_lo + s))          # chunk-seeded: shards of different world sizes agree
+        yk = torch.randint(0, n_classes, (e - s,), generator=gk, device=device)
+        x = protos[yk] + torch.randn(e - s, dim, generator=gk, device=device) / dim ** 0.5
+        k_bank[:, s:e] = x.t().half()
+        outs[s:e] = (torch.nn.functional.normalize(x, dim=1) @ text.t()).half()
+    return q_bank, k_bank, outs, text.t().contiguous(), yq.int()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from summer_clip_b200 import build as _build, ops
+    from summer_clip_b200.searcher import ClipSearcher, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CLIP-search path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    if rank == 0:
+        _build.build_library()
+    if world > 1:
+        dist.barrier()
+    if args.op_dtype:
+        ops.OP_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.op_dtype]
+
+    nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
+    if args.nq:
+        nq = args.nq
+    lo, hi = shard_range(nk, rank, world)
+    q_bank, k_bank, outs, text, labels = make_banks(torch, nq, lo, hi, dim, n_classes, seed=3, device=device)
+
+    searcher = ClipSearcher(device, group=None)          # the shard is generated locally; merge is done below
+    searcher.set_text(text)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    searcher.set_cache(k_bank, outs)                      # normalise+transpose+cast keys, one-hot values (transposed)
+    torch.cuda.synchronize()
+    bank_build_ms = (time.perf_counter() - t0) * 1e3
+    n_local = hi - lo
+    del k_bank, outs
+    c_pad = searcher.vt.shape[0]
+    splits = ops.attn_splits(nq, n_local, c_pad, device)
+
+    q_host = q_bank.cpu().pin_memory()
+    labels_host = labels.cpu().pin_memory()
+    labels_dev = labels
+    stream = torch.cuda.current_stream()
+    launches = {"n": 0}
+
+    def step_device(time_attn=None):
+        """Inputs resident in HBM."""
+        qn = ops.normalize_cast(q_bank, True)
+        z = ops.zero_shot_logits(q_bank, True, searcher.text)
+        if time_attn is not None:
+            time_attn[0].record(stream)
+        part = ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits, merge=False)
+        if time_attn is not None:
+            time_attn[1].record(stream)
+        o = ops.merge_partials(part) if splits > 1 else part[0]
+        launches["n"] += 3 + int(splits > 1)
+        if world > 1:
+            gathered = torch.empty((world, nq, n_classes), dtype=torch.float32, device=device)
+            dist.all_gather_into_tensor(gathered, o.contiguous(), group=group)
+            o = ops.merge_partials(gathered)
+            launches["n"] += 1
+        res = ops.epilogue(z, o, [ALPHA], labels=labels_dev)
+        launches["n"] += 1
+        return res
+
+    def step_e2e():
+        """Host buffers in, host result out: H2D of the query bank, D2H of predictions + counters."""
+        q_dev = q_host.to(device, non_blocking=True)
+        lab = labels_host.to(device, non_blocking=True)
+        qn = ops.normalize_cast(q_dev, True)
+        z = ops.zero_shot_logits(q_dev, True, searcher.text)
+        o = ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits)
+        if world > 1:
+            gathered = torch.empty((world, nq, n_classes), dtype=torch.float32, device=device)
+            dist.all_gather_into_tensor(gathered, o.contiguous(), group=group)
+            o = ops.merge_partials(gathered)
+        res = ops.epilogue(z, o, [ALPHA], labels=lab)
+        pred = res["pred"].to("cpu", non_blocking=True)
+        counts = torch.stack([res["top1"], res["top5"]]).to("cpu", non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pred, counts
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing
+    for _ in range(args.warmup):
+        res = step_device()
+    sync_all()
+    launches["n"] = 0
+    attn_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        res = step_device(attn_events[i])
+    ev1.record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    attn_ms = sum(a.elapsed_time(b) for a, b in attn_events) / args.steps
+    gpu_launches = launches["n"]
+    top1 = int(res["top1"][0])
+
+    # ---------------- end-to-end timing (host buffers)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pred, counts = step_e2e()
+    sync_all()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = read_peaks()
+    ms_per_step = total_ms / args.steps
+    qps = nq / (ms_per_step * 1e-3)
+    flops = 2.0 * nq * n_local * (dim + n_classes)                  # 2*Nq*Nk*(D + C) per launch
+    achieved = flops / (attn_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "attn_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload if world == 1 else "", None)
+    except Exception:
+        pass
+    out = {
+        "metric": "clip_search_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16" if ops.OP_DTYPE == torch.float16 else "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
+                   "n_classes": n_classes, "beta": BETA, "alpha": ALPHA, "values": "hard (one-hot of argmax L)",
+                   "sharding": f"key-sharded x{world}, all-gather + sum merge" if world > 1 else "single GPU",
+                   "key_splits_per_gpu": splits, "accumulate": "fp32",
+                   "l2": "inputs larger than L2: key bank + values = %.2f GB per GPU" % (2 * n_local * (dim + c_pad) / 1e9),
+                   "bank_build_ms": bank_build_ms, "top1_count": top1},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                     "kernel": "sc_attn_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
+                     "peak_source": peaks["source"] + " burst (cuBLAS bf16 8192^3)",
+                     "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None},
+        "e2e": {"value": nq / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": q_host.numel() * q_host.element_size() + labels_host.numel() * 4,
+                "d2h_bytes_per_step": pred.numel() * 4 + counts.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": gpu_launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(nq, nk, dim, n_classes, budget_s=args.cpu_budget)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(nq, nk, dim, n_classes, budget_s=20.0, steps=1):
+    """The oracle port of the reference path (normalise both banks, Q^T K, exp, one-hot, @, Z + alpha*O,
+    top-1/5) timed on the host cores with torch fp32 on a bounded sample of the same workload; cost is
+    linear in queries and keys, so the sample time is scaled to the full key bank."""
+    import torch
+    from oracle import clip_search_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sq = min(nq, 1024)
+    sk = min(nk, 131072)
+    banks = orc.synthetic_banks(sq, sk, dim, n_classes, seed=3)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"].long()
+
+    def once():
+        Z = orc.zero_shot_logits(Q, T)
+        O = orc.image_attention(Q, K, orc.hard_values(L), BETA, chunk=256)
+        out = orc.searcher_logits(Z, O, ALPHA)
+        return orc.compute_accuracy(out, labels)
+
+    once()                                                      # warm-up
+    best = float("inf")
+    t_all = time.perf_counter()
+    for _ in range(3):
+        t0 = time.perf_counter()
+        once()
+        best = min(best, time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    full_time = best * (nk / sk)                                # seconds for `sq` queries against the full bank
+    return {"value": sq / full_time, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{sq} queries x {sk} keys x {dim}-d, {n_classes} classes (fp32 torch CPU, best of 3, {best:.2f} s), "
+                      f"scaled linearly to {nk} keys",
+            "sample_seconds": best, "gflops": 2.0 * sq * sk * (dim + n_classes) / best / 1e9}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is a pure
+    Python repo without a build or an installable package, and /root/reference is absent on the GPU
+    box, so the timed code is the oracle port (kind "port"), all host threads, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
+    if args.nq:
+        nq = args.nq
+    import torch
+    from oracle import clip_search_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sq, sk = min(nq, 512), min(nk, 65536)
+    banks = orc.synthetic_banks(sq, sk, dim, n_classes, seed=3)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"].long()
+
+    def step():
+        Z = orc.zero_shot_logits(Q, T)
+        O = orc.image_attention(Q, K, orc.hard_values(L), BETA, chunk=256)
+        return orc.compute_accuracy(orc.searcher_logits(Z, O, ALPHA), labels)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    sample_s = (time.perf_counter() - t0) / args.steps
+    full_s = sample_s * (nk / sk) * (nq / sq)                   # one full pass of the workload, linear scaling
+    qps = nq / full_s
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = f"{sq} queries x {sk} keys per step (fp32 torch CPU), scaled linearly to {nq} x {nk}"
+    out = {"impl": "reference", "metric": "clip_search_queries_per_sec", "value": qps, "unit": "queries/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
+                      "n_classes": n_classes, "beta": BETA, "alpha": ALPHA},
+           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="imagenet_rn50", choices=sorted(WORKLOADS))
+    ap.add_argument("--nq", type=int, default=0, help="override the number of queries (debug)")
+    ap.add_argument("--op-dtype", default="", choices=["", "fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+"""B200 mirror of summer_clip/clip_searcher/image_attention.py — the CLIP-search sweep driver.
+
+Same trainer shape (setup_* hooks + train_loop), same config keys (conf/image_attention.yaml:21-44),
+same loop nest and the same JSON records in the same order (image_attention.py:89-120), but:
+  * the four nested loops share work — one gather+normalise of the cache per cache strategy, one values
+    build per (cache, value strategy), one fused attention launch per (cache, beta, value strategy)
+    and ONE epilogue launch for all alphas with on-device accuracy counters (the reference does a
+    top-k + host sync per alpha);
+  * inputs the reference derives from the CLIP towers or image datasets (text classifier, labels)
+    are read from files: `data.text_features_path` (T [D, C]) or `data.clip_logits_path`,
+    `data.labels_path`, `cache.labels_path`.  Encoder forward passes are outside this path.
+
+    python -m summer_clip_b200.clip_searcher.image_attention path/to/image_attention.yaml [key=value ...]
+"""
+from __future__ import annotations
+
+import sys
+import typing as tp
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..searcher import ClipSearcher
+from ..utils import hydra_utils
+from ..utils.config import Config, load_config
+from ..utils.log_utils import JsonLinesLogger
+from .cache_strategy import CacheStrategy, IndexedCacheStrategy
+from .cache_value_strategy import GoldCacheValues, HardCacheStrategy, SoftmaxCacheStrategy
+from .cache_weights_strategy import NormalizedBank
+from .utils import TensorsNumpySaver, compute_accuracy
+
+
+def _load_tensor(path: tp.Union[str, Path], device) -> torch.Tensor:
+    path = Path(path)
+    if path.suffix == ".npy":
+        return torch.from_numpy(np.load(path)).to(device)
+    return torch.load(path, map_location=device)
+
+
+class ImageAttention:
+    def __init__(self, cfg: tp.Mapping, run_dir: tp.Union[str, Path] = ".") -> None:
+        self.cfg = cfg if isinstance(cfg, Config) else Config(cfg)
+        self.run_dir = Path(run_dir)
+
+    # ---- setup hooks, in the order of BaseTrainer.setup (utils/trainer.py:62-70)
+    def setup_device(self) -> None:
+        dev = (self.cfg.get("meta") or {}).get("device") or "cuda"
+        self.device = torch.device(dev)
+        if self.device.type != "cuda":
+            raise ops._lib.SummerClipError("image_attention runs on the CUDA path only (no CPU fallback)")
+
+    def setup_logger(self) -> None:
+        name = (self.cfg.get("exp") or {}).get("name", "image_attention")
+        self.logger = JsonLinesLogger(name, self.run_dir / "image_attention.log")
+        self.gold_labels_saver = TensorsNumpySaver(self.run_dir / "gold_labels")
+        self.cache_saver = TensorsNumpySaver(self.run_dir / "cache_ids")
+        self.preds_saver = TensorsNumpySaver(self.run_dir / "preds_ids")
+
+    def setup_dataset(self) -> None:
+        self.test_labels = _load_tensor(self.cfg.data.labels_path, self.device).to(torch.int32)
+        self.cache_labels: tp.Optional[torch.Tensor] = None
+        if self.cfg.cache.get("labels_path"):
+            self.cache_labels = _load_tensor(self.cfg.cache.labels_path, self.device).to(torch.int32)
+        if self.cfg.run_saves.save_labels:
+            self.save_labels()
+
+    def save_labels(self) -> None:
+        self.gold_labels_saver.save_named_tensor(self.test_labels, "test_labels")
+        if self.cache_labels is not None:
+            self.gold_labels_saver.save_named_tensor(self.cache_labels, "cache_labels")
+
+    def setup_model(self) -> None:
+        self.searcher = ClipSearcher(self.device)
+        self.test_image_features = _load_tensor(self.cfg.data.image_features_path, self.device)
+        if self.cfg.data.get("clip_logits_path"):
+            self.clip_logits = _load_tensor(self.cfg.data.clip_logits_path, self.device).float().contiguous()
+        else:
+            self.clip_logits = self.compute_clip_logits(_load_tensor(self.cfg.data.text_features_path, self.device))
+        self.test_q_norm = ops.normalize_cast(self.test_image_features, feature_major=True)
+        self.origin_cache_image_features = _load_tensor(self.cfg.cache.image_features_path, self.device)
+        self.origin_cache_image_outs = _load_tensor(self.cfg.cache.image_outs_path, self.device)
+        self.logger.log_info(f"original-data-size: {self.origin_cache_image_outs.shape[0]}")
+
+    def setup(self) -> None:
+        self.setup_device()
+        self.setup_logger()
+        self.setup_dataset()
+        self.setup_model()
+
+    # ---- the path
+    def compute_clip_logits(self, test_text_features: torch.Tensor) -> torch.Tensor:
+        """image_attention.py:80-83 — 100 * normalise(Q)^T @ T (fp32 kernel)."""
+        return ops.zero_shot_logits(self.test_image_features, True, test_text_features, scale=100.0)
+
+    def logits_to_preds(self, logits: torch.Tensor) -> torch.Tensor:
+        return ops.epilogue(None, logits.float().contiguous(), [1.0])["pred"][0].long()
+
+    def build_cache(self, cache_strategy: CacheStrategy, image_features: torch.Tensor, image_outs: torch.Tensor):
+        """image_attention.py:48-70.  Returns (cache keys as a NormalizedBank, (image_outs, idx) or gold
+        labels for the value strategies, info)."""
+        if not isinstance(cache_strategy, IndexedCacheStrategy):
+            feats, outs = cache_strategy.transform(image_features, image_outs)
+            return NormalizedBank(ops.normalize_cast(feats, feature_major=True)), (outs, None, None), {}
+        samples_inds = cache_strategy.select(image_features, image_outs)
+        cache_info: tp.Dict[str, tp.Any] = dict(cache_size=int(samples_inds.numel()))
+        if self.cfg.run_saves.save_cache_inds:
+            cache_info["cache_inds_path"] = str(self.cache_saver.save_tensor(samples_inds))
+        gold = None
+        if self.cache_labels is not None:
+            cache_labels = self.cache_labels[samples_inds]
+            eval_top1, eval_top5 = compute_accuracy(image_outs[samples_inds], cache_labels)
+            cache_info.update(dict(acc1=eval_top1, acc5=eval_top5))
+            if self.cfg.cache.get("replace_outs_with_golds", False):
+                gold = cache_labels
+                onehot = torch.nn.functional.one_hot(cache_labels.long(), num_classes=image_outs.shape[1]).float()
+                eval_top1, eval_top5 = compute_accuracy(onehot, cache_labels)
+                cache_info.update(dict(acc1_replace=eval_top1, acc5_replace=eval_top5))
+        k_norm = ops.normalize_cast(image_features, feature_major=True, idx=samples_inds)   # gather + norm + cast
+        return NormalizedBank(k_norm), (image_outs, samples_inds, gold), cache_info
+
+    @torch.no_grad()
+    def train_loop(self) -> None:
+        clip_logits = self.clip_logits
+        eval_top1, eval_top5 = compute_accuracy(clip_logits, self.test_labels)
+        zeroshot_info: tp.Dict[str, tp.Any] = dict(acc1=eval_top1, acc5=eval_top5)
+        if self.cfg.run_saves.save_preds:
+            zeroshot_info["preds_path"] = str(self.preds_saver.save_tensor(self.logits_to_preds(clip_logits)))
+        if self.cfg.run_saves.save_logits:
+            zeroshot_info["logits_path"] = str(self.preds_saver.save_tensor(clip_logits))
+        self.logger.log_info(dict(**zeroshot_info, type="zero_shot"))
+
+        alphas = [float(a) for a in self.cfg.cache.alpha]
+        n_q = self.test_labels.shape[0]
+        q_bank = NormalizedBank(self.test_q_norm)
+        for cache_strategy_cfg in self.cfg.cache_strategies.values():
+            for cache_strategy, cache_strategy_params in hydra_utils.instantiate_all(self._strategy_cfg(cache_strategy_cfg)):
+                k_bank, (outs, idx, gold), cache_info = self.build_cache(
+                    cache_strategy, self.origin_cache_image_features, self.origin_cache_image_outs)
+                self.logger.log_info(dict(**cache_info, cache_strategy=cache_strategy_params, type="cache_info"))
+                value_cache: tp.Dict[int, tp.Any] = {}
+                for weights_strategy, weights_params in hydra_utils.instantiate_all(self.cfg.cache_weights_strategy):
+                    cache_weights = weights_strategy.transform(q_bank, k_bank)
+                    for vi, (value_strategy, value_params) in enumerate(hydra_utils.instantiate_all(self.cfg.cache_value_strategy)):
+                        if vi not in value_cache:
+                            if gold is not None:
+                                value_cache[vi] = GoldCacheValues(outs.shape[1]).transform(gold)
+                            elif isinstance(value_strategy, (HardCacheStrategy, SoftmaxCacheStrategy)):
+                                value_cache[vi] = value_strategy.transform(outs, idx=idx)
+                            else:
+                                value_cache[vi] = value_strategy.transform(outs if idx is None else outs[idx])
+                        cache_logits = cache_weights @ value_cache[vi]
+                        res = ops.epilogue(clip_logits, cache_logits, alphas, labels=self.test_labels,
+                                           want_pred=bool(self.cfg.run_saves.save_preds))
+                        top1, top5 = res["top1"].cpu().tolist(), res["top5"].cpu().tolist()   # one D2H per beta
+                        for ai, alpha in enumerate(self.cfg.cache.alpha):
+                            searcher_info: tp.Dict[str, tp.Any] = dict(
+                                cache_strategy=cache_strategy_params, cache_value_strategy=value_params,
+                                cache_weights_strategy=weights_params, alpha=alpha,
+                                acc1=100.0 * top1[ai] / n_q, acc5=100.0 * top5[ai] / n_q)
+                            if self.cfg.run_saves.save_preds:
+                                searcher_info["preds_path"] = str(self.preds_saver.save_tensor(res["pred"][ai].long()))
+                            self.logger.log_info_wandb(dict(**searcher_info, type="searcher_result"))
+
+    def _strategy_cfg(self, cfg: tp.Mapping) -> dict:
+        """`cache_dataset: [${cache.dataset}]` entries (conf/cache_strategy/topk_per_gold.yaml:3-4) carry a
+        dataset object in the reference; here the gold-label strategies take the loaded label tensor."""
+        out = dict(cfg)
+        if "cache_dataset" in out:
+            out.pop("cache_dataset")
+            out["cache_labels"] = [self.cache_labels]
+        return out
+
+
+def run_trainer(trainer_cls, cfg, run_dir=".") -> "ImageAttention":
+    """utils/trainer.py:125-133 (seeds as in set_random_state :113-122)."""
+    import random
+    seed = int((cfg.get("meta") or {}).get("random_state", 42))
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    trainer = trainer_cls(cfg, run_dir)
+    trainer.setup()
+    trainer.train_loop()
+    return trainer
+
+
+def run(argv: tp.Optional[tp.Sequence[str]] = None) -> ImageAttention:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    import yaml
+    overrides: dict = {}
+    for item in argv[1:]:
+        key, value = item.split("=", 1)
+        cur = overrides
+        parts = key.split(".")
+        for p in parts[:-1]:
+            cur = cur.setdefault(p, {})
+        cur[parts[-1]] = yaml.safe_load(value)
+    cfg = load_config(argv[0], overrides)
+    return run_trainer(ImageAttention, cfg, run_dir=(cfg.get("run_dir") or "."))
+
+
+if __name__ == "__main__":
+    run()

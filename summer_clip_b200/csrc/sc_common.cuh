@@ -100,6 +100,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // matching torch.topk which treats NaN as the largest value.
 __device__ __forceinline__ uint32_t float_order_key(float f) {
   if (f != f) return 0xFFFFFFFFu;
+  if (f == 0.0f) return 0x80000000u;   // -0.0 and +0.0 compare equal in torch
   uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }

@@ -1,0 +1,85 @@
+"""B200 mirror of the hot-path part of summer_clip/tip_adapter/utils.py: the training-free
+Tip-Adapter head (tip_adapter.py:58-68) and the (beta, alpha) grid search `search_hp` (:99-129).
+
+The reference recomputes Q@K, exp, @V and the zero-shot GEMM for each of the 200 x 20 grid points
+(13.4 PFLOP executed at ImageNet scale).  Here the operands are cast once, each beta is one fused
+attention launch and its 20 alphas are one epilogue launch with on-device accuracy counters; the
+search order and the strict `>` (first best wins) are the reference's.
+CLIP feature extraction (build_cache_model / pre_load_features) is outside this path: the cached
+`keys_*.pt`, `values_*.pt`, `*_f.pt`, `*_l.pt` tensors are the inputs.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+
+from .. import ops
+from ..clip_searcher.cache_value_strategy import CacheValues
+
+
+def cls_acc(output: torch.Tensor, target: torch.Tensor, topk: int = 1) -> float:
+    """tip_adapter/utils.py:10-15 — top-k accuracy in percent (k in {1, 5})."""
+    res = ops.epilogue(None, output.float().contiguous(), [1.0], labels=target, want_pred=False)
+    if topk == 1:
+        correct = int(res["top1"][0])
+    elif topk == 5:
+        correct = int(res["top5"][0])
+    else:
+        raise NotImplementedError("cls_acc supports topk in {1, 5}")
+    return 100 * correct / target.shape[0]
+
+
+class TipAdapterHead:
+    """Operands of the Tip-Adapter head in kernel layout.  features [Nq, D] (row-normalised by the caller,
+    tip_adapter/utils.py:84), cache_keys [D, Nk] (any strides — the reference passes a permuted view,
+    utils.py:61), cache_values [Nk, C] one-hot, clip_weights [D, C]."""
+
+    def __init__(self, cache_keys: torch.Tensor, cache_values: torch.Tensor, features: torch.Tensor,
+                 clip_weights: torch.Tensor, adapter: tp.Optional[torch.nn.Module] = None) -> None:
+        if adapter is not None:            # Tip-Adapter-F: affinity = adapter(features), weight [Nk, D]
+            self.k = ops.normalize_cast(adapter.weight.detach(), feature_major=False, normalize=False)
+        else:
+            self.k = ops.normalize_cast(cache_keys, feature_major=True, normalize=False)
+        self.n_keys = self.k.shape[0]
+        self.q = ops.normalize_cast(features, feature_major=False, normalize=False)
+        self.values = cache_values if isinstance(cache_values, CacheValues) else CacheValues.from_dense(cache_values)
+        self.n_classes = self.values.n_classes
+        self.clip_logits = ops.zero_shot_logits(features, False, clip_weights, scale=100.0, normalize=False)
+
+    def cache_logits(self, beta: float) -> torch.Tensor:
+        """exp(-(beta - beta * features @ cache_keys)) @ cache_values."""
+        return ops.attn_fwd(self.q, self.k, self.values.vt(self.q.dtype), self.n_keys, self.n_classes, beta)
+
+    def logits(self, beta: float, alpha: float) -> torch.Tensor:
+        """tip_logits = clip_logits + cache_logits * alpha (tip_adapter.py:68)."""
+        return ops.epilogue(self.clip_logits, self.cache_logits(beta), [alpha], want_logits=True, want_pred=False)["logits"][0]
+
+    def top1_counts(self, beta: float, alphas: tp.Sequence[float], labels: torch.Tensor) -> torch.Tensor:
+        return ops.epilogue(self.clip_logits, self.cache_logits(beta), alphas, labels=labels, want_pred=False)["top1"]
+
+
+def search_hp(cfg, cache_keys, cache_values, features, labels, clip_weights, adapter=None):
+    """tip_adapter/utils.py:99-129."""
+    best_beta, best_alpha = 0, 0
+    if cfg['search_hp'] == True:  # noqa: E712  (the reference's own test)
+        beta_list = [i * (cfg['search_scale'][0] - 0.1) / cfg['search_step'][0] + 0.1 for i in range(cfg['search_step'][0])]
+        alpha_list = [i * (cfg['search_scale'][1] - 0.1) / cfg['search_step'][1] + 0.1 for i in range(cfg['search_step'][1])]
+
+        head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
+        n = labels.shape[0]
+        counts = torch.stack([head.top1_counts(beta, alpha_list, labels) for beta in beta_list]).cpu()  # one D2H
+
+        best_acc = 0
+        for bi, beta in enumerate(beta_list):
+            for ai, alpha in enumerate(alpha_list):
+                acc = 100 * int(counts[bi, ai]) / n
+                if acc > best_acc:
+                    print("New best setting, beta: {:.2f}, alpha: {:.2f}; accuracy: {:.2f}".format(beta, alpha, acc))
+                    best_acc = acc
+                    best_beta = beta
+                    best_alpha = alpha
+
+        print("\nAfter searching, the best accuarcy: {:.2f}.\n".format(best_acc))
+
+    return best_beta, best_alpha

@@ -1,0 +1,65 @@
+"""Hydra-free mirror of summer_clip/utils/hydra_utils.py.
+
+The reference selects its strategy plug-ins by `_target_` strings in Hydra YAML and expands list
+valued parameters into a Cartesian grid (`instantiate_all`, hydra_utils.py:38-50).  hydra/omegaconf
+are not installable in this environment, so this module implements the same contract on plain
+dict configs.  `_target_` strings that name the reference package (`summer_clip.…`) resolve to the
+same class name inside this package, which is what makes the CUDA path a drop-in for the YAML.
+"""
+from __future__ import annotations
+
+import copy
+import importlib
+import itertools
+import typing as tp
+
+_PREFIX_MAP = (("summer_clip.", "summer_clip_b200."),)
+
+
+def load_obj(obj_path: str, default_obj_path: str = "") -> tp.Any:
+    """hydra_utils.py:9-27 — import `pkg.mod.Name`."""
+    obj_path_list = obj_path.rsplit(".", 1)
+    obj_path = obj_path_list.pop(0) if len(obj_path_list) > 1 else default_obj_path
+    obj_name = obj_path_list[0]
+    module_obj = importlib.import_module(obj_path)
+    if not hasattr(module_obj, obj_name):
+        raise AttributeError(f"Object `{obj_name}` cannot be loaded from `{obj_path}`.")
+    return getattr(module_obj, obj_name)
+
+
+def type_full_name(type_: type) -> tp.Optional[str]:
+    """hydra_utils.py:30-36."""
+    if type_ is None:
+        return None
+    module = type_.__module__
+    if module is None or module == str.__module__:
+        return type_.__name__
+    return f"{module}.{type_.__name__}"
+
+
+def resolve_target(target: str) -> str:
+    for old, new in _PREFIX_MAP:
+        if target.startswith(old) and not target.startswith(new):
+            return new + target[len(old):]
+    return target
+
+
+def instantiate(cfg: tp.Mapping[str, tp.Any], **overrides: tp.Any) -> tp.Any:
+    """hydra.utils.instantiate for the flat configs this path uses (nested `_target_` dicts recurse)."""
+    params = {k: v for k, v in cfg.items() if k != "_target_"}
+    params.update(overrides)
+    for k, v in list(params.items()):
+        if isinstance(v, dict) and "_target_" in v:
+            params[k] = instantiate(v)
+    return load_obj(resolve_target(cfg["_target_"]))(**params)
+
+
+def instantiate_all(cfg: tp.Mapping[str, tp.Any]) -> tp.Iterator[tp.Tuple[tp.Any, tp.Dict[str, tp.Any]]]:
+    """hydra_utils.py:38-50 — every non-`_target_` key holds a LIST; yield (instance, params) for the
+    Cartesian product in key order.  The yielded params dict keeps the ORIGINAL `_target_` string, so
+    log records are identical to the reference's (notebooks map by class name)."""
+    cfg_dict = copy.deepcopy(dict(cfg))
+    target = cfg_dict.pop("_target_")
+    for param_values in itertools.product(*cfg_dict.values()):
+        param_to_value = dict(zip(cfg_dict.keys(), param_values))
+        yield instantiate({"_target_": target, **param_to_value}), {"_target_": target, **copy.deepcopy(param_to_value)}

@@ -1,0 +1,404 @@
+"""Parity of the CUDA path (called through the C ABI via summer_clip_b200.ops / the strategy classes)
+against (a) the golden outputs of the reference's own code and (b) the CPU oracle on seeded banks.
+
+Acceptance (BASELINE.json north_star): pseudo-label indices and top-k sets bit-exact; output
+logits within 2e-3 max-abs after softmax; argmax agreement >= 99.9 %.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_search_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SOFTMAX_TOL = 2e-3       # north_star: max-abs after softmax
+ARGMAX_AGREE = 0.999     # north_star: argmax agreement
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_lib):
+    from summer_clip_b200 import ops as _ops
+    assert torch.cuda.is_available()
+    return _ops
+
+
+def assert_logits_match(out: torch.Tensor, ref: torch.Tensor, what: str = ""):
+    out, ref = out.detach().float().cpu(), ref.detach().float().cpu()
+    diff = (torch.softmax(out, dim=1) - torch.softmax(ref, dim=1)).abs().max().item()
+    assert diff <= SOFTMAX_TOL, f"{what}: softmax max-abs {diff:.3e} > {SOFTMAX_TOL}"
+    agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+    n = out.shape[0]
+    assert agree >= min(ARGMAX_AGREE, 1.0 - 1.0 / n), f"{what}: argmax agreement {agree:.5f}"
+    return diff, agree
+
+
+def cuda(x, dtype=None):
+    t = torch.from_numpy(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ----------------------------------------------------------------------------- selection (bit-exact)
+@pytest.fixture(scope="module")
+def sel(golden_dir):
+    return np.load(golden_dir / "selection.npz")
+
+
+def test_rowconf_matches_reference(ops, sel):
+    outs = cuda(sel["image_outs"])
+    conf, label = ops.rowconf(outs, prob=False)
+    assert np.array_equal(label.cpu().numpy(), sel["label"])
+    assert np.array_equal(conf.cpu().numpy(), sel["conf_raw"])            # max is exact
+    conf_p, label_p = ops.rowconf(outs, scale=orc.CLIP_SCALE, prob=True)
+    assert np.array_equal(label_p.cpu().numpy(), sel["label"])
+    np.testing.assert_allclose(conf_p.cpu().numpy(), sel["conf_prob"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("k", [1, 4, 16, 64])
+def test_topk_strategies_bit_exact_vs_reference_golden(ops, sel, k):
+    from summer_clip_b200.clip_searcher.cache_strategy import TopKProbStrategy, TopKStrategy
+    outs = cuda(sel["image_outs"])
+    feats = torch.empty(1, outs.shape[0], device="cuda")
+    idx = TopKStrategy(k).select(feats, outs)
+    assert idx.dtype == torch.int64
+    assert np.array_equal(idx.cpu().numpy(), sel[f"topk_{k}"])
+    idx_p = TopKProbStrategy(k, orc.CLIP_SCALE).select(feats, outs)
+    assert np.array_equal(idx_p.cpu().numpy(), sel[f"topk_prob_{k}"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_selection_vs_oracle_sun397_shape(ops, dtype):
+    """19 850 x 397 logits bank (config 1 shape), k = 16, raw and prob ranking, incl. fp16 storage (ties!)."""
+    from summer_clip_b200.clip_searcher.cache_strategy import TopKProbStrategy, TopKStrategy
+    g = torch.Generator().manual_seed(21)
+    outs = (0.25 + 0.02 * torch.randn(19850, 397, generator=g)).to(dtype)
+    feats = torch.empty(1, 1, device="cuda")
+    got = TopKStrategy(16).select(feats, outs.cuda()).cpu().numpy()
+    assert np.array_equal(got, orc.topk_select(outs, 16))                  # fp16 ties -> index-ascending policy
+    got_p = TopKProbStrategy(16, orc.CLIP_SCALE).select(feats, outs.cuda()).cpu().numpy()
+    want_p = orc.topk_prob_select(outs, 16)
+    if not np.array_equal(got_p, want_p):
+        # the two softmax sums may differ in the last ulp: then the SETS per class must still agree
+        # wherever the oracle's k/(k+1) boundary is not a near-tie
+        conf, label = orc.row_confidence(outs, prob=True)
+        conf, label = conf.numpy(), label.numpy()
+        for c in np.unique(label):
+            a, b = set(got_p[label[got_p] == c].tolist()), set(want_p[label[want_p] == c].tolist())
+            if a != b:
+                vals = np.sort(conf[label == c])[::-1]
+                k = min(16, vals.size)
+                assert k < vals.size and abs(vals[k - 1] - vals[k]) <= 4e-7 * vals[k - 1], f"class {c} differs off a tie"
+
+
+def test_selection_edge_cases(ops):
+    # empty classes, classes with fewer than k members, k larger than N, a single row, all rows one class
+    conf = cuda(np.array([0.9, 0.1, 0.5, 0.5, 0.7], dtype=np.float32))
+    label = cuda(np.array([2, 2, 0, 0, 2], dtype=np.int32))
+    idx, cnt = ops.topk_per_class(conf, label, 4, 2)
+    assert cnt.cpu().tolist() == [2, 0, 2, 0]
+    assert idx.cpu().tolist() == [[2, 3], [-1, -1], [0, 4], [-1, -1]]      # tie 0.5/0.5 -> smaller index first
+    assert ops.select_topk_per_label(conf, label, 4, 64).cpu().tolist() == [2, 3, 0, 4, 1]
+    one = ops.select_topk_per_label(cuda(np.array([0.3], dtype=np.float32)), cuda(np.array([1], dtype=np.int32)), 3, 5)
+    assert one.cpu().tolist() == [1 - 1]
+    n = 70000
+    g = torch.Generator().manual_seed(5)
+    c = torch.rand(n, generator=g)
+    big = ops.select_topk_per_label(c.cuda(), torch.zeros(n, dtype=torch.int32).cuda(), 1, 1000).cpu().numpy()
+    assert np.array_equal(big, np.argsort(-c.numpy(), kind="stable")[:1000])   # radix-select path, one huge bucket
+    neg = cuda(np.array([-1.0, -0.0, 0.0, -3.5, float("-inf")], dtype=np.float32))
+    order = ops.select_topk_per_label(neg, torch.zeros(5, dtype=torch.int32).cuda(), 1, 5).cpu().tolist()
+    assert order == [1, 2, 0, 3, 4]                                        # -0.0 == 0.0, then index ascending
+
+
+# ----------------------------------------------------------------------------- attention vs reference golden
+@pytest.fixture(scope="module")
+def att(golden_dir):
+    return np.load(golden_dir / "image_attention.npz")
+
+
+@pytest.mark.parametrize("op_dtype", [torch.float16, torch.bfloat16])
+def test_image_attention_sweep_vs_reference_golden(ops, att, op_dtype, monkeypatch):
+    from summer_clip_b200.clip_searcher.cache_value_strategy import HardCacheStrategy, SoftmaxCacheStrategy
+    from summer_clip_b200.clip_searcher.cache_weights_strategy import TipAdapterWeightsStrategy, _BANKS
+    monkeypatch.setattr(ops, "OP_DTYPE", op_dtype)
+    _BANKS.clear()
+    Q, K, L = cuda(att["test_image_features"]), cuda(att["cache_image_features"]), cuda(att["cache_image_outs"])
+    Z = cuda(att["clip_logits"])
+    labels = cuda(att["test_labels"])
+    idx = cuda(att["cache_idx"])
+    Kc, Lc = K[:, idx], L[idx]                                             # reference loop: image_attention.py:54-55
+    strategies = [HardCacheStrategy(), SoftmaxCacheStrategy(orc.CLIP_SCALE, 0.1), SoftmaxCacheStrategy(orc.CLIP_SCALE, 10.0)]
+    for vi, vstrat in enumerate(strategies):
+        values = vstrat.transform(Lc)
+        np.testing.assert_allclose(values.dense().cpu().numpy(), att[f"values_{vi}"], atol=4e-3 if op_dtype == torch.bfloat16 else 5e-4)
+        for bi, beta in enumerate(att["betas"]):
+            weights = TipAdapterWeightsStrategy(float(beta)).transform(Q, Kc)      # un-normalised [D, N] banks in
+            assert weights.shape == (Q.shape[1], idx.numel())
+            cache_logits = weights @ values                                         # the reference's own expression
+            ref = torch.from_numpy(att[f"cache_logits_v{vi}_b{bi}"])
+            rel = (cache_logits.cpu() - ref).abs().max().item() / ref.abs().max().item()
+            assert rel < (6e-3 if op_dtype == torch.bfloat16 else 1e-3), (vi, bi, rel)
+            res = ops.epilogue(Z, cache_logits, att["alphas"].tolist(), labels=labels, want_logits=True)
+            for ai, alpha in enumerate(att["alphas"]):
+                want = torch.from_numpy(att["clip_logits"]) + ref * float(alpha)
+                if op_dtype == torch.float16:
+                    assert_logits_match(res["logits"][ai], want, f"v{vi} b{bi} a{ai}")
+                acc = att[f"acc_v{vi}_b{bi}"][ai]
+                n = labels.numel()
+                assert abs(100.0 * int(res["top1"][ai]) / n - acc[0]) <= 100.0 / n + 1e-9
+                assert abs(100.0 * int(res["top5"][ai]) / n - acc[1]) <= 100.0 / n + 1e-9
+
+
+def test_materialized_weights_vs_reference_golden(ops, att):
+    from summer_clip_b200.clip_searcher.cache_weights_strategy import TipAdapterWeightsStrategy
+    Q, K = cuda(att["test_image_features"]), cuda(att["cache_image_features"])
+    idx = cuda(att["cache_idx"])
+    W = TipAdapterWeightsStrategy(5.5).transform(Q, K[:, idx]).materialize()
+    np.testing.assert_allclose(W.cpu().numpy(), att["weights_b5.5"], rtol=0, atol=3e-3)
+
+
+def test_all_logits_cache_and_zero_shot_vs_golden(ops, att):
+    Q, K, L, T = (cuda(att[n]) for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    Z = ops.zero_shot_logits(Q, True, T)
+    np.testing.assert_allclose(Z.cpu().numpy(), att["clip_logits"], rtol=0, atol=2e-4)
+    Qn, Kn = ops.normalize_cast(Q, True), ops.normalize_cast(K, True)
+    Vt = ops.values_prepare(L, L.shape[1])
+    O = ops.attn_fwd(Qn, Kn, Vt, K.shape[1], L.shape[1], 5.5)
+    ref = torch.from_numpy(att["cache_logits_all_hard_b5.5"])
+    assert (O.cpu() - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+    from summer_clip_b200.clip_searcher.utils import compute_accuracy
+    assert np.allclose(compute_accuracy(Z, cuda(att["test_labels"])), att["acc_zero_shot"])
+
+
+def test_tip_adapter_head_and_search_vs_golden(ops, golden_dir, capsys):
+    from summer_clip_b200.tip_adapter import utils as tip_utils
+    tip = np.load(golden_dir / "tip_adapter.npz")
+    feats = cuda(tip["features"], torch.float16)                           # Tip-Adapter caches are fp16
+    keys = cuda(tip["cache_keys"].T.copy(), torch.float16).t()             # [D, Nk] permuted VIEW (utils.py:61)
+    assert not keys.is_contiguous()
+    vals = torch.nn.functional.one_hot(cuda(tip["cache_labels"]).long(), 11).half()
+    clip_w = cuda(tip["clip_weights"], torch.float16)
+    labels = cuda(tip["test_labels"])
+    head = tip_utils.TipAdapterHead(keys, vals, feats, clip_w)
+    out = head.logits(5.5, 1.0)
+    assert_logits_match(out, torch.from_numpy(tip["tip_logits"]), "tip head")
+    assert abs(tip_utils.cls_acc(out, labels) - float(tip["acc_tip"])) <= 100.0 / labels.numel() + 1e-9
+    cfg = {"search_hp": True, "search_scale": tip["search_scale"].tolist(), "search_step": tip["search_step"].tolist()}
+    best_beta, best_alpha = tip_utils.search_hp(cfg, keys, vals, feats, labels, clip_w)
+    printed = capsys.readouterr().out
+    assert "After searching, the best accuarcy" in printed
+    # fp16 inputs can move a near-tie in accuracy: the found optimum must be as good as the reference's
+    _, _, ref_best = orc.search_hp(cfg["search_scale"], cfg["search_step"], torch.from_numpy(tip["cache_keys"]),
+                                   orc.onehot_values(torch.from_numpy(tip["cache_labels"]), 11),
+                                   torch.from_numpy(tip["features"]), torch.from_numpy(tip["test_labels"]),
+                                   torch.from_numpy(tip["clip_weights"]))
+    got_acc = tip_utils.cls_acc(head.logits(best_beta, best_alpha), labels)
+    assert got_acc >= ref_best - 100.0 / labels.numel() - 1e-9
+    assert (best_beta, best_alpha) == (pytest.approx(float(tip["best_beta"])), pytest.approx(float(tip["best_alpha"]))) \
+        or got_acc >= ref_best - 1e-9
+
+
+# ----------------------------------------------------------------------------- vs the oracle on seeded banks
+@pytest.mark.parametrize("shape", [(1000, 6000, 512, 397, torch.float16), (777, 4097, 1024, 1000, torch.float32),
+                                   (130, 129, 768, 100, torch.float32)])
+def test_fused_path_vs_oracle(ops, shape):
+    """Ragged Nq / Nk (not multiples of 128), D in {512, 768, 1024}, C in {100, 397, 1000}, fp16 and fp32 banks."""
+    from summer_clip_b200.searcher import ClipSearcher
+    nq, nk, dim, c, dtype = shape
+    banks = orc.synthetic_banks(nq, nk, dim, c, seed=31, sigma=0.5, sigma_text=0.8, shared=2.0, dtype=dtype)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"]
+    betas, alphas = [1.0, 5.5, 11.5], [0.0, 0.5, 1.0, 4.0]
+    s = ClipSearcher("cuda")
+    s.set_text(T.float())
+    Zref = orc.zero_shot_logits(Q.float(), T.float())
+    for hard in (True, False):
+        s.set_cache(K, L, softmax_scale=None if hard else orc.CLIP_SCALE * 0.1)
+        V = orc.hard_values(L.float()) if hard else orc.softmax_values(L.float(), orc.CLIP_SCALE, 0.1)
+        res = s.search(Q, betas, alphas, labels=labels, want_logits=True)
+        for r, beta in zip(res, betas):
+            Oref = orc.image_attention(Q, K, V, beta)
+            for ai, alpha in enumerate(alphas):
+                want = orc.searcher_logits(Zref, Oref, alpha)
+                assert_logits_match(r["logits"][ai], want, f"{shape} hard={hard} beta={beta} alpha={alpha}")
+                c1, c5 = orc.accuracy_counts(want, labels.long())
+                assert abs(int(r["top1"][ai]) - c1) <= max(1, nq // 1000)
+                assert abs(int(r["top5"][ai]) - c5) <= max(1, nq // 1000)
+                assert torch.equal(r["pred"][ai].long().cpu(), r["logits"][ai].argmax(1).cpu())
+
+
+def test_pseudo_label_cache_pipeline_vs_oracle(ops):
+    """select (TopKProb k=8) -> gather -> attention, the default CLIP-search configuration."""
+    from summer_clip_b200.clip_searcher.cache_strategy import TopKProbStrategy
+    from summer_clip_b200.searcher import ClipSearcher
+    banks = orc.synthetic_banks(600, 9000, 512, 100, seed=32, sigma=0.5, sigma_text=0.8, shared=3.0)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    idx = TopKProbStrategy(8, orc.CLIP_SCALE).select(K.cuda(), L.cuda())
+    want_idx = orc.topk_prob_select(L, 8)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    s = ClipSearcher("cuda")
+    s.set_text(T)
+    s.set_cache(K, L, idx=idx)
+    res = s.search(Q, [5.5], [1.0, 2.0], labels=banks["test_labels"], want_logits=True)[0]
+    widx = torch.from_numpy(want_idx)
+    Oref = orc.image_attention(Q, K[:, widx], orc.hard_values(L[widx]), 5.5)
+    Zref = orc.zero_shot_logits(Q, T)
+    for ai, alpha in enumerate([1.0, 2.0]):
+        assert_logits_match(res["logits"][ai], orc.searcher_logits(Zref, Oref, alpha), f"alpha={alpha}")
+
+
+# ----------------------------------------------------------------------------- structural properties
+def test_key_splits_and_shards_sum_to_the_whole(ops):
+    g = torch.Generator().manual_seed(41)
+    nq, nk, dim, c = 300, 5000, 256, 300
+    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
+    L = torch.randn(nk, c, generator=g).cuda()
+    Vt = ops.values_prepare(L, c, softmax_scale=1.0)
+    whole = ops.attn_fwd(Qn, Kn, Vt, nk, c, 3.0, splits=1)
+    for splits in (2, 7, 40):
+        parts = ops.attn_fwd(Qn, Kn, Vt, nk, c, 3.0, splits=splits, merge=False)
+        assert parts.shape == (splits, nq, c)
+        torch.testing.assert_close(ops.merge_partials(parts), whole, rtol=1e-5, atol=1e-5)
+    # key shards as the multi-GPU path cuts them (128-aligned contiguous ranges) merge to the same result
+    from summer_clip_b200.searcher import shard_range
+    shards = []
+    for r in range(3):
+        lo, hi = shard_range(nk, r, 3)
+        idx = torch.arange(lo, hi, device="cuda")
+        vt = ops.values_prepare(L, c, idx=idx, softmax_scale=1.0)
+        shards.append(ops.attn_fwd(Qn, Kn[lo:hi].contiguous(), vt, hi - lo, c, 3.0))
+    torch.testing.assert_close(ops.merge_partials(torch.stack(shards)), whole, rtol=1e-5, atol=1e-5)
+
+
+def test_linearity_and_rowsum_properties(ops):
+    g = torch.Generator().manual_seed(42)
+    nq, nk, dim, c = 257, 1111, 128, 50
+    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
+    L = torch.randn(nk, c, generator=g).cuda()
+    hard = ops.values_prepare(L, c, ones_row=True)
+    O = ops.attn_fwd(Qn, Kn, hard, nk, c + 1, 2.0)
+    # one-hot values: the class columns partition the keys, so they add up to the all-ones column
+    torch.testing.assert_close(O[:, :c].sum(1), O[:, c], rtol=2e-5, atol=1e-5)
+    # beta = 0 -> every weight is 1 -> O counts the keys per class exactly
+    O0 = ops.attn_fwd(Qn, Kn, hard, nk, c + 1, 0.0)
+    counts = torch.bincount(L.argmax(1), minlength=c).float()
+    assert torch.equal(O0[:, :c], counts.expand(nq, c))
+    assert torch.all(O0[:, c] == nk)
+    # weights are bounded by exp(beta * (1 - 1)) = 1 up to rounding and positive
+    assert O.min().item() >= 0.0
+
+
+def test_tiny_and_degenerate_shapes(ops):
+    g = torch.Generator().manual_seed(43)
+    for nq, nk, dim, c in [(1, 1, 64, 1), (3, 2, 100, 7), (128, 128, 64, 16), (129, 257, 192, 257)]:
+        Q, K = torch.randn(nq, dim, generator=g), torch.randn(nk, dim, generator=g)
+        L = torch.randn(nk, c, generator=g)
+        Qn, Kn = ops.normalize_cast(Q.cuda(), False), ops.normalize_cast(K.cuda(), False)
+        Vt = ops.values_prepare(L.cuda(), c)
+        O = ops.attn_fwd(Qn, Kn, Vt, nk, c, 4.0)
+        ref = orc.image_attention(Q.t(), K.t(), orc.hard_values(L), 4.0)
+        torch.testing.assert_close(O.cpu(), ref, rtol=0, atol=2e-3 * max(1.0, ref.abs().max().item()))
+
+
+def test_cpu_tensors_are_rejected(ops):
+    from summer_clip_b200._lib import SummerClipError
+    with pytest.raises(SummerClipError):
+        ops.normalize_cast(torch.randn(8, 8), True)
+    with pytest.raises(SummerClipError):
+        ops.rowconf(torch.randn(8, 8))
+
+
+def test_image_attention_runner_matches_oracle_sweep(ops, tmp_path):
+    """The hydra-free ImageAttention trainer on .pt banks: same records, same order, accuracies equal to the
+    oracle's sweep (image_attention.py:89-120)."""
+    import json
+    from summer_clip_b200.clip_searcher.image_attention import ImageAttention, run_trainer
+    from summer_clip_b200.utils.config import load_config
+    from pathlib import Path
+    banks = orc.synthetic_banks(500, 3000, 256, 40, seed=51, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    paths = {}
+    for name, t in banks.items():
+        paths[name] = tmp_path / f"{name}.pt"
+        torch.save(t, paths[name])
+    conf = Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf" / "image_attention.yaml"
+    cfg = load_config(conf, {
+        "data": {"image_features_path": str(paths["test_image_features"]), "text_features_path": str(paths["text_features"]),
+                 "labels_path": str(paths["test_labels"])},
+        "cache": {"image_features_path": str(paths["cache_image_features"]), "image_outs_path": str(paths["cache_image_outs"]),
+                  "labels_path": str(paths["cache_labels"]), "alpha": [0.0, 1.0, 4.0]},
+        "cache_weights_strategy": {"beta": [1.0, 5.5]},
+        "run_saves": {"save_cache_inds": True},
+        "cache_strategies": {"topk": {"topk": [2, 16]}, "topk_prob": {"topk": [4]},
+                             "per_pred_class_random": {"topk": [2]}, "global_random": {"topk": [1]}},
+    })
+    trainer = run_trainer(ImageAttention, cfg, run_dir=tmp_path / "run")
+    records = [json.loads(l) for l in (tmp_path / "run" / "image_attention.log").read_text().splitlines()]
+    kinds = [r.get("type") for r in records]
+    assert kinds[0] is None and kinds[1] == "zero_shot"
+    n_caches = 2 + 1 + 1 + 1 + 1
+    assert kinds.count("cache_info") == n_caches and kinds.count("searcher_result") == n_caches * 2 * 3
+    # oracle sweep over the deterministic strategies
+    Q, K, L, T = (banks[n].float() for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"].long()
+    Z = orc.zero_shot_logits(Q, T)
+    zs = next(r for r in records if r.get("type") == "zero_shot")
+    assert np.allclose([zs["acc1"], zs["acc5"]], orc.compute_accuracy(Z, labels), atol=0.2 + 1e-9)
+    results = [r for r in records if r.get("type") == "searcher_result"]
+    assert set(results[0]) >= {"cache_strategy", "cache_value_strategy", "cache_weights_strategy", "alpha", "acc1", "acc5", "message"}
+    assert results[0]["cache_strategy"]["_target_"] == "summer_clip.clip_searcher.cache_strategy.TopKStrategy"
+    for strat, sel in (("TopKStrategy", lambda k: orc.topk_select(banks["cache_image_outs"], k)),
+                       ("TopKProbStrategy", lambda k: orc.topk_prob_select(banks["cache_image_outs"], k)),
+                       ("AllLogitsStrategy", lambda k: orc.all_logits_select(L))):
+        for r in results:
+            if not r["cache_strategy"]["_target_"].endswith(strat):
+                continue
+            idx = torch.from_numpy(sel(r["cache_strategy"].get("topk", 0)))
+            O = orc.image_attention(Q, K[:, idx], orc.hard_values(L[idx]), r["cache_weights_strategy"]["beta"])
+            acc = orc.compute_accuracy(orc.searcher_logits(Z, O, r["alpha"]), labels)
+            assert abs(r["acc1"] - acc[0]) <= 0.2 + 1e-9 and abs(r["acc5"] - acc[1]) <= 0.2 + 1e-9, r
+    info = [r for r in records if r.get("type") == "cache_info"]
+    assert info[0]["cache_size"] == len(orc.topk_select(banks["cache_image_outs"], 2)) and "acc1" in info[0]
+    saved = np.load(info[0]["cache_inds_path"])
+    assert np.array_equal(saved, orc.topk_select(banks["cache_image_outs"], 2))
+
+
+# ----------------------------------------------------------------------------- full BASELINE size
+@pytest.mark.parametrize("nq", [4096])
+def test_full_size_key_bank_properties(ops, nq):
+    """Config-3 key bank (1 281 167 keys x 1024-d, 1000 classes) against a query block: the oracle cannot
+    run this size, so check size-independent properties — key shards sum to the whole, one-hot class
+    columns sum to the ones column, beta = 0 counts keys — plus a sampled exact check of a few rows."""
+    nk, dim, c = 1281167, 1024, 1000
+    g = torch.Generator(device="cuda").manual_seed(61)
+    protos = torch.nn.functional.normalize(torch.randn(c, dim, generator=g, device="cuda"), dim=1)
+    yk = torch.randint(0, c, (nk,), generator=g, device="cuda")
+    Kn = torch.empty((nk, dim), dtype=ops.OP_DTYPE, device="cuda")
+    step = 1 << 17
+    for s in range(0, nk, step):
+        e = min(nk, s + step)
+        x = protos[yk[s:e]] + torch.randn(e - s, dim, generator=g, device="cuda") / dim ** 0.5
+        ops.normalize_cast(x, False, out=Kn[s:e])
+    yq = torch.randint(0, c, (nq,), generator=g, device="cuda")
+    Qn = ops.normalize_cast(protos[yq] + torch.randn(nq, dim, generator=g, device="cuda") / dim ** 0.5, False)
+    Vt = ops.values_prepare(None, c, labels=yk.int(), ones_row=True)
+    O = ops.attn_fwd(Qn, Kn, Vt, nk, c + 1, 5.5)
+    torch.testing.assert_close(O[:, :c].sum(1), O[:, c], rtol=1e-4, atol=1e-3)
+    from summer_clip_b200.searcher import shard_range
+    parts = []
+    for r in range(8):
+        lo, hi = shard_range(nk, r, 8)
+        vt = ops.values_prepare(None, c, labels=yk[lo:hi].int(), ones_row=True)
+        parts.append(ops.attn_fwd(Qn, Kn[lo:hi], vt, hi - lo, c + 1, 5.5))
+    torch.testing.assert_close(ops.merge_partials(torch.stack(parts)), O, rtol=1e-4, atol=1e-3)
+    # sampled rows against fp32 torch on the same device (chunked; 8 rows x 1.28M keys)
+    rows = torch.tensor([0, 1, 127, 128, 1000, 2047, 4000, nq - 1], device="cuda")
+    A = Qn[rows].float() @ Kn.float().t()
+    W = torch.exp(5.5 * (A - 1.0))
+    ref = torch.zeros(rows.numel(), c, device="cuda").index_add_(1, yk, W)
+    torch.testing.assert_close(O[rows][:, :c], ref, rtol=2e-3, atol=1e-2)
+    O0 = ops.attn_fwd(Qn[:128].contiguous(), Kn, Vt, nk, c + 1, 0.0)
+    assert torch.all(O0[:, c] == nk)
