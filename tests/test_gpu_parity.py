@@ -139,7 +139,8 @@ def test_image_attention_sweep_vs_reference_golden(ops, att, op_dtype, monkeypat
             cache_logits = weights @ values                                         # the reference's own expression
             ref = torch.from_numpy(att[f"cache_logits_v{vi}_b{bi}"])
             rel = (cache_logits.cpu() - ref).abs().max().item() / ref.abs().max().item()
-            assert rel < (6e-3 if op_dtype == torch.bfloat16 else 1e-3), (vi, bi, rel)
+            # bf16 operands (opt-in) carry 3 fewer mantissa bits: ~8x the fp16 error, largest at beta = 11.5
+            assert rel < (2e-2 if op_dtype == torch.bfloat16 else 1e-3), (vi, bi, rel)
             res = ops.epilogue(Z, cache_logits, att["alphas"].tolist(), labels=labels, want_logits=True)
             for ai, alpha in enumerate(att["alphas"]):
                 want = torch.from_numpy(att["clip_logits"]) + ref * float(alpha)
