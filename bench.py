@@ -160,6 +160,8 @@ def run_ours(args):
     del k_bank, outs
     c_pad = searcher.vt.shape[0]
     splits = ops.attn_splits(nq, n_local, c_pad, device)
+    if os.environ.get("SC_BENCH_SPLITS"):                  # tuning knob for A/B runs
+        splits = int(os.environ["SC_BENCH_SPLITS"])
 
     q_host = q_bank.cpu().pin_memory()
     labels_host = labels.cpu().pin_memory()

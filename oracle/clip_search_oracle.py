@@ -120,7 +120,7 @@ def accuracy_counts(output: torch.Tensor, target: torch.Tensor, topk: Sequence[i
     """clip_adapter/train_adapter.py:156-159 — number of rows whose target is within the top-k."""
     pred = output.topk(max(topk), 1, True, True)[1].t()
     correct = pred.eq(target.view(1, -1).expand_as(pred))
-    return [float(correct[:k].reshape(-1).float().sum(0, keepdim=True).cpu().numpy()) for k in topk]
+    return [float(correct[:k].reshape(-1).float().sum().item()) for k in topk]
 
 
 def compute_accuracy(outputs: torch.Tensor, target: torch.Tensor, topk: Sequence[int] = (1, 5)) -> List[float]:

@@ -111,6 +111,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// pull a tile into L2 only (no smem destination, no completion): hides DRAM latency of a later load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
 // multicast variant: the tile lands at the same smem offset in every CTA of cta_mask and
 // signals the same-offset mbarrier in each.
 __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst_smem, const CUtensorMap* m,
@@ -220,4 +227,34 @@ __host__ __device__ constexpr uint32_t umma_idesc_16b(uint32_t M, uint32_t N, bo
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+}  // namespace scptx
+
+// ---------------------------------------------------------------- clusters / DSMEM
+namespace scptx {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// bulk copy from this CTA's smem into a peer's smem; completion (bytes) on the PEER's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
+                                                  uint32_t mbar_cluster) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+      "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 }  // namespace scptx

@@ -182,10 +182,17 @@ def test_tip_adapter_head_and_search_vs_golden(ops, golden_dir, capsys):
     vals = torch.nn.functional.one_hot(cuda(tip["cache_labels"]).long(), 11).half()
     clip_w = cuda(tip["clip_weights"], torch.float16)
     labels = cuda(tip["test_labels"])
+    # fp32 inputs: against the reference's golden logits
+    head32 = tip_utils.TipAdapterHead(cuda(tip["cache_keys"]), vals, cuda(tip["features"]), cuda(tip["clip_weights"]))
+    out32 = head32.logits(5.5, 1.0)
+    assert_logits_match(out32, torch.from_numpy(tip["tip_logits"]), "tip head fp32 inputs")
+    assert abs(tip_utils.cls_acc(out32, labels) - float(tip["acc_tip"])) <= 100.0 / labels.numel() + 1e-9
+    # fp16 caches (what tip_adapter/utils.py saves on a GPU): against the oracle on the SAME fp16-rounded inputs
     head = tip_utils.TipAdapterHead(keys, vals, feats, clip_w)
     out = head.logits(5.5, 1.0)
-    assert_logits_match(out, torch.from_numpy(tip["tip_logits"]), "tip head")
-    assert abs(tip_utils.cls_acc(out, labels) - float(tip["acc_tip"])) <= 100.0 / labels.numel() + 1e-9
+    want16 = orc.tip_head(feats.float().cpu(), keys.float().cpu(), orc.onehot_values(torch.from_numpy(tip["cache_labels"]), 11),
+                          clip_w.float().cpu(), 5.5, 1.0)
+    assert_logits_match(out, want16, "tip head fp16 inputs")
     cfg = {"search_hp": True, "search_scale": tip["search_scale"].tolist(), "search_step": tip["search_step"].tolist()}
     best_beta, best_alpha = tip_utils.search_hp(cfg, keys, vals, feats, labels, clip_w)
     printed = capsys.readouterr().out
@@ -262,7 +269,7 @@ def test_key_splits_and_shards_sum_to_the_whole(ops):
     for splits in (2, 7, 40):
         parts = ops.attn_fwd(Qn, Kn, Vt, nk, c, 3.0, splits=splits, merge=False)
         assert parts.shape == (splits, nq, c)
-        torch.testing.assert_close(ops.merge_partials(parts), whole, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(ops.merge_partials(parts), whole, rtol=2e-4, atol=1e-4)   # fp32 summation order differs
     # key shards as the multi-GPU path cuts them (128-aligned contiguous ranges) merge to the same result
     from summer_clip_b200.searcher import shard_range
     shards = []
@@ -271,7 +278,7 @@ def test_key_splits_and_shards_sum_to_the_whole(ops):
         idx = torch.arange(lo, hi, device="cuda")
         vt = ops.values_prepare(L, c, idx=idx, softmax_scale=1.0)
         shards.append(ops.attn_fwd(Qn, Kn[lo:hi].contiguous(), vt, hi - lo, c, 3.0))
-    torch.testing.assert_close(ops.merge_partials(torch.stack(shards)), whole, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ops.merge_partials(torch.stack(shards)), whole, rtol=2e-4, atol=1e-4)
 
 
 def test_linearity_and_rowsum_properties(ops):
@@ -387,14 +394,14 @@ def test_full_size_key_bank_properties(ops, nq):
     Qn = ops.normalize_cast(protos[yq] + torch.randn(nq, dim, generator=g, device="cuda") / dim ** 0.5, False)
     Vt = ops.values_prepare(None, c, labels=yk.int(), ones_row=True)
     O = ops.attn_fwd(Qn, Kn, Vt, nk, c + 1, 5.5)
-    torch.testing.assert_close(O[:, :c].sum(1), O[:, c], rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(O[:, :c].sum(1), O[:, c], rtol=1e-3, atol=1e-3)   # 1.28M-term fp32 sums, different order
     from summer_clip_b200.searcher import shard_range
     parts = []
     for r in range(8):
         lo, hi = shard_range(nk, r, 8)
         vt = ops.values_prepare(None, c, labels=yk[lo:hi].int(), ones_row=True)
         parts.append(ops.attn_fwd(Qn, Kn[lo:hi], vt, hi - lo, c + 1, 5.5))
-    torch.testing.assert_close(ops.merge_partials(torch.stack(parts)), O, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(ops.merge_partials(torch.stack(parts)), O, rtol=1e-3, atol=1e-3)
     # sampled rows against fp32 torch on the same device (chunked; 8 rows x 1.28M keys)
     rows = torch.tensor([0, 1, 127, 128, 1000, 2047, 4000, nq - 1], device="cuda")
     A = Qn[rows].float() @ Kn.float().t()
