@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+] + (["-DSC_ATTN_TIMING_EXPERIMENTS"] if os.environ.get("SC_BUILD_EXPERIMENTS") else []) + [
 ]
 
 

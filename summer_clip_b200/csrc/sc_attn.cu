@@ -23,6 +23,14 @@
 #include <cstdlib>
 #include <mutex>
 
+namespace sc {
+// sc_attn_pair.cu
+int attn_pair_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                     const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk,
+                     int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices,
+                     float beta, int splits, float* O, int64_t ldo, cudaStream_t st);
+}  // namespace sc
+
 namespace {
 
 using namespace scptx;
@@ -235,7 +243,7 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const uint32_t b_addr = ring0 + stage * kStageBytes;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              umma_ss(tmem_o, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+              if (!(p.dbg_skip & 32)) umma_ss(tmem_o, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
                       idesc2, (i | c | k) != 0 ? 1u : 0u);
             }
             umma_commit(smem_u32(&bars->empty[stage]));
@@ -264,7 +272,7 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const uint32_t b_addr = a_addr + 16384;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
-              umma_ss(tmem_s, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+              if (!(p.dbg_skip & 16)) umma_ss(tmem_s, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
                       idesc1, (d | k) != 0 ? 1u : 0u);
             }
             umma_commit(smem_u32(&bars->empty[stage]));
@@ -298,7 +306,7 @@ sc_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       mbar_wait(smem_u32(&bars->p_empty), (own & 1) ^ 1u);   // every consumer retired my previous tile
 #pragma unroll
-      for (int cc = 0; cc < kBN / 32; ++cc) {
+      for (int cc = 0; cc < ((p.dbg_skip & 8) ? 0 : kBN / 32); ++cc) {
         uint32_t rg[32];
         tmem_ld_32x32(tmem_base + lane_addr + kColS + b * kBN + cc * 32, rg);
         tmem_ld_wait();
@@ -499,6 +507,17 @@ int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, in
   }
   SC_REQUIRE(splits <= tiles_total && splits <= 65535, SC_ESHAPE,
              "sc_attn_fwd: splits=%d exceeds the %lld key tiles", splits, (long long)tiles_total);
+
+  // Kernel choice: the CTA-pair (cta_group::2) kernel is the default; SC_ATTN_IMPL=cluster selects the
+  // single-CTA-MMA cluster kernel below (A/B runs and a cross-check in the tests).
+  const char* impl = std::getenv("SC_ATTN_IMPL");
+  if (impl == nullptr || impl[0] != 'c') {
+    int rcp = sc::attn_pair_launch(&make_tmap, Qn, Kn, Vt, f16, Nq, Nk, D_pad, n_cols, C_pad, Nk_pad, slice,
+                                   n_slices, beta, splits, O, ldo, static_cast<cudaStream_t>(stream));
+    if (rcp != SC_OK) return rcp;
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+  }
 
   CUtensorMap tmQ, tmK, tmV;
   int rc;
