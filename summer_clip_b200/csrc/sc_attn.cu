@@ -29,6 +29,11 @@ int attn_pair_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_
                      const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk,
                      int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices,
                      float beta, int splits, float* O, int64_t ldo, cudaStream_t st);
+// sc_attn_t.cu
+int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                  const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk, int64_t D_pad,
+                  int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices, float beta,
+                  int splits, float* O, int64_t ldo, cudaStream_t st);
 }  // namespace sc
 
 namespace {
@@ -511,6 +516,15 @@ int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, in
   // Kernel choice: the CTA-pair (cta_group::2) kernel is the default; SC_ATTN_IMPL=cluster selects the
   // single-CTA-MMA cluster kernel below (A/B runs and a cross-check in the tests).
   const char* impl = std::getenv("SC_ATTN_IMPL");
+  // default: the transposed pair kernel (sc_attn_t.cu) when the class slices fill whole clusters;
+  // SC_ATTN_IMPL=pair | cluster select the other two kernels (A/B runs, cross-checks in the tests)
+  if ((impl == nullptr || impl[0] == 't') && (n_slices == 2 || n_slices % 4 == 0)) {
+    int rct = sc::attn_t_launch(&make_tmap, Qn, Kn, Vt, f16, Nq, Nk, D_pad, n_cols, C_pad, Nk_pad, slice, n_slices,
+                                beta, splits, O, ldo, static_cast<cudaStream_t>(stream));
+    if (rct != SC_OK) return rct;
+    SC_CUDA(cudaGetLastError());
+    return SC_OK;
+  }
   if (impl == nullptr || impl[0] != 'c') {
     int rcp = sc::attn_pair_launch(&make_tmap, Qn, Kn, Vt, f16, Nq, Nk, D_pad, n_cols, C_pad, Nk_pad, slice,
                                    n_slices, beta, splits, O, ldo, static_cast<cudaStream_t>(stream));

@@ -1,0 +1,494 @@
+// Transposed CTA-pair variant of the fused CLIP-search attention kernel ("T").
+//
+// Same maths and reference lines as sc_attn.cu (cache_weights_strategy.py:33-36, image_attention.py:109,
+// tip_adapter/utils.py:114-116), different operand roles.  All 2*NPAIR CTAs of a cluster work on the SAME
+// 128-query tile; CTA `rank` owns the class slice blockIdx.x and one key tile per round (tile r*CS+rank).
+//   GEMM-1  S^T[256k x 128q]      (cta_group::2, M = the two CTAs' key tiles)
+//           A = Kn tile chunk (own 128 keys)            B = Qn chunk, 64 queries per CTA (SHARED by the pair)
+//   exp     P^T = exp2(c1*S^T + c0): TMEM lane = key, thread writes its row of 128 query weights
+//   GEMM-2  O^T[256c x 128q] +=   (M = 128 classes of each CTA, per 128-class block of its slice)
+//           A = Vt rows (own classes, K-major)           B = P^T, MN-major, 64 queries per CTA (SHARED)
+// Because P^T is the B operand of a pair MMA, each CTA needs only the half of every weight tile that
+// covers "its" 64 queries: the DSMEM exchange is 16 KB per (tile, destination) instead of 32 KB, the
+// weight slots shrink to 16 KB and the operand ring grows to 6 stages.  (Measured on the non-transposed
+// pair kernel: the 32 KB x 3 exchange per tile sits on a serial chain with single-buffered slots and
+// costs ~75 ms of a 309 ms pass.)
+#include "sc_common.cuh"
+#include "sc_ptx.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
+
+namespace {
+
+using namespace scptx;
+
+constexpr int kBQ = 128;             // queries per cluster tile (UMMA N)
+constexpr int kBN = 128;             // keys per tile = TMEM lanes of S^T
+constexpr int kBK = 64;              // 16-bit elements per swizzled smem row
+constexpr int kSub = 24576;          // one 64-wide K chunk: Kn chunk 16 KB + Qn half 8 KB
+// A ring stage holds CPS (1 or 2) K chunks for GEMM-1 / the Vt boxes of CPS 128-class blocks for GEMM-2.
+// CPS = 2 halves the barrier round trips (measured: on-chip time 250 -> 165 ms) but leaves only 3 stages in
+// flight against ~2 us of loaded TMA latency (full pass 296 -> 321 ms); CPS = 1 is the default.
+constexpr int kHalf = 16384;         // half of a weight tile: [128 keys x 64 queries] MN-major SW128
+constexpr int kThreads = 192;
+constexpr int kExpThreads = 128;
+constexpr int kTmemCols = 512;       // S^T0 @0, S^T1 @128, O^T blocks @256 (+128)
+constexpr int kColO = 256;
+constexpr int kMaxStages = 8;
+constexpr int kMaxCluster = 4;
+constexpr int kSmemPayload = 7 * 32768;
+constexpr int kSmemBytes = kSmemPayload + 1024 + 512;
+constexpr float kPShift = 8.0f;      // see sc_attn.cu
+
+struct TParams {
+  int Nq;
+  int n_dchunks;
+  int n_cols;
+  int slice;        // classes per CTA
+  int n_mb;         // 128-class blocks per CTA = ceil(slice / 128)
+  int tiles_total;
+  int splits;
+  int dbg;          // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit0/1/2 skip Q/V/K loads,
+                    // 3 exp math, 4/5 GEMM-1/2 MMAs, 6 shrink the exchange to 1 KB
+  float c1, c0, o_scale;
+  float* O;
+  long long ldo;
+};
+
+struct Bars {
+  uint64_t full[kMaxStages];       // leader: TMA bytes of BOTH CTAs landed
+  uint64_t empty[kMaxStages];      // both: pair MMAs reading the stage retired
+  uint64_t s_full[2];              // both
+  uint64_t s_empty[2];             // leader: 8 warp-elected arrivals (4 per CTA)
+  uint64_t p_full[kMaxCluster];    // both: my half-slot for source CTA `src` is full
+  uint64_t p_peer[kMaxCluster];    // leader: the odd CTA's half-slot is full (relay)
+  uint64_t p_empty;                // both: every consumer pair retired GEMM-2 on MY last tile
+  uint64_t o_full;                 // both
+  uint32_t tmem_slot;
+};
+
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  uint32_t r;
+  if (kF16)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kF16, int NPAIR, int CPS>
+__global__ void __launch_bounds__(kThreads, 1)
+sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const TParams p) {
+  constexpr int CS = 2 * NPAIR;                                            // cluster size
+  constexpr int kStage = CPS * kSub;
+  constexpr int NS = (kSmemPayload - (CS + 1) * kHalf) / kStage;           // 6 (CS=4) / 7 (CS=2) stages
+  static_assert(NS <= kMaxStages && NS >= 2, "ring depth");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t ring0 = (raw_addr + 1023u) & ~1023u;
+  const uint32_t slot0 = ring0 + NS * kStage;                              // CS half-tile slots (by source)
+  const uint32_t stag0 = slot0 + CS * kHalf;                               // the other half of MY tile
+  Bars* bars = reinterpret_cast<Bars*>(smem_raw + (stag0 - raw_addr) + kHalf);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // == blockIdx.x % CS
+  const int h = static_cast<int>(rank & 1);       // which 64-query half of P^T this CTA feeds to its pair
+  const uint32_t leader = rank & ~1u;
+  const bool is_leader = (h == 0);
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
+
+  const int c0 = blockIdx.x * p.slice;            // first class of this CTA
+  const int q0 = blockIdx.y * kBQ;
+  const int split = blockIdx.z;
+  const int t0 = static_cast<int>((static_cast<long long>(p.tiles_total) * split) / p.splits);
+  const int t1 = static_cast<int>((static_cast<long long>(p.tiles_total) * (split + 1)) / p.splits);
+  const int T = t1 - t0;
+  const int R = (T + CS - 1) / CS;
+  const int nd = p.n_dchunks;
+  const int n_mb = p.n_mb;
+  const int pair_first = static_cast<int>(leader);   // round r is active for my pair iff r*CS + pair_first < T
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars->s_full[b]), 1);
+      mbar_init(smem_u32(&bars->s_empty[b]), 8);
+    }
+    for (int s = 0; s < CS; ++s) {
+      mbar_init(smem_u32(&bars->p_full[s]), 1);
+      mbar_init(smem_u32(&bars->p_peer[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->p_empty), NPAIR);
+    mbar_init(smem_u32(&bars->o_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(&bars->tmem_slot), kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  const uint32_t xbytes = (p.dbg & 64) ? 1024u : static_cast<uint32_t>(kHalf);   // exchange unit
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs; warp-uniform, elected issue)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full0 = smem_u32(&bars->full[0]);
+    const uint32_t full0c = mapa(full0, leader);
+    const uint32_t empty0 = smem_u32(&bars->empty[0]);
+    auto load_v_round = [&](int rr) {
+#pragma unroll 1
+      for (int src = 0; src < CS; ++src) {
+        const int i = rr * CS + src;
+        if (i >= T) break;
+#pragma unroll 1
+        for (int c = 0; c < kBN / kBK; ++c) {
+#pragma unroll 1
+          for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
+            const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
+            mbar_wait(empty0 + stage * 8, phase ^ 1u);
+            if (elect_one()) {
+              if (p.dbg & 2) {
+                if (is_leader) mbar_arrive(full0 + stage * 8);
+              } else {
+                if (is_leader) mbar_arrive_expect_tx(full0 + stage * 8, 2u * 16384u * static_cast<uint32_t>(nblk));
+                for (int u = 0; u < nblk; ++u)
+                  tma_load_2d_cg2(ring0 + stage * kStage + u * kSub, &tmV, full0c + stage * 8,
+                                  (t0 + i) * kBN + c * kBK, c0 + (mb0 + u) * 128);     // my classes x 64 keys
+              }
+            }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    };
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+      if (r * CS + pair_first < T) {
+        const int krow = (t0 + r * CS + static_cast<int>(rank)) * kBN;   // my key tile (may be past the split: unused)
+#pragma unroll 1
+        for (int d = 0; d < nd; d += CPS) {
+          const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
+          mbar_wait(empty0 + stage * 8, phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t kb = (p.dbg & 4) ? 0u : 16384u, qb = (p.dbg & 1) ? 0u : 8192u;
+            if (is_leader) {
+              if (kb + qb) mbar_arrive_expect_tx(full0 + stage * 8, 2u * (kb + qb) * static_cast<uint32_t>(nsub));
+              else mbar_arrive(full0 + stage * 8);
+            }
+            for (int u = 0; u < nsub; ++u) {
+              const uint32_t dst = ring0 + stage * kStage + u * kSub;
+              if (kb) tma_load_2d_cg2(dst, &tmK, full0c + stage * 8, (d + u) * kBK, krow);                  // 128 keys
+              if (qb) tma_load_2d_cg2(dst + 16384, &tmQ, full0c + stage * 8, (d + u) * kBK, q0 + h * 64);   // 64 queries
+            }
+          }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if (r > 0) load_v_round(r - 1);
+    }
+    if (R > 0) load_v_round(R - 1);
+  } else if (warp == 1) {
+    const uint32_t pfull0 = smem_u32(&bars->p_full[0]);
+    const uint32_t ppeer0 = smem_u32(&bars->p_peer[0]);
+    if (elect_one()) {                      // arm the half-slots fed by the other CTAs for round 0
+      for (int src = 0; src < CS; ++src)
+        if (src != static_cast<int>(rank) && src < T) mbar_arrive_expect_tx(pfull0 + src * 8, xbytes);
+    }
+    __syncwarp();
+    if (is_leader) {
+      // ===================================================== MMA issuer for the pair
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc1 = umma_idesc_16b(256, kBQ, kF16);                 // A, B K-major
+      const uint32_t idesc2 = umma_idesc_16b(256, kBQ, kF16) | (1u << 16);    // B (P^T) MN-major
+      const uint32_t tmem_o = tmem_base + kColO;
+      const uint32_t full0 = smem_u32(&bars->full[0]);
+      const uint32_t empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t pempty = smem_u32(&bars->p_empty);
+      auto gemm2_round = [&](int rr) {
+#pragma unroll 1
+        for (int src = 0; src < CS; ++src) {
+          const int i = rr * CS + src;
+          if (i >= T) break;
+          mbar_wait(pfull0 + src * 8, rr & 1);
+          mbar_wait(ppeer0 + src * 8, rr & 1);
+          tc_fence_after();
+          if (src != static_cast<int>(rank) && i + CS < T) {
+            if (elect_one()) mbar_arrive_expect_tx(pfull0 + src * 8, xbytes);
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int c = 0; c < kBN / kBK; ++c) {
+#pragma unroll 1
+            for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
+              const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
+              mbar_wait(full0 + stage * 8, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t b_desc = umma_desc_k128(slot0 + src * kHalf + c * 8192);            // P^T rows 64c..
+                for (int u = 0; u < nblk; ++u) {
+                  const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage + u * kSub);       // Vt box, K-major
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)       // A: +32 B per 16 keys; B: +16 key rows = +2048 B
+                    if (!(p.dbg & 32))
+                      umma_ss2(tmem_o + (mb0 + u) * 128, a_desc + 2 * k, b_desc + 128 * k, idesc2,
+                               (i | c | k) != 0 ? 1u : 0u);
+                }
+                umma_commit2_mcast(empty0 + stage * 8, pair_mask);
+                if (c == kBN / kBK - 1 && mb0 + CPS >= n_mb)      // this pair is done with source src's tile
+                  umma_commit2_mcast(pempty, static_cast<uint16_t>(1u << src));
+              }
+              __syncwarp();
+              if (++stage == NS) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      };
+      int own = 0;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        if (r * CS + pair_first < T) {
+          const int sb = own & 1;
+          mbar_wait(smem_u32(&bars->s_empty[sb]), ((own >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_s = tmem_base + sb * 128;
+#pragma unroll 1
+          for (int d = 0; d < nd; d += CPS) {
+            const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
+            mbar_wait(full0 + stage * 8, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int u = 0; u < nsub; ++u) {
+                const uint32_t a_addr = ring0 + stage * kStage + u * kSub;
+                const uint64_t a_desc = umma_desc_k128(a_addr);              // K chunk (my 128 keys)
+                const uint64_t b_desc = umma_desc_k128(a_addr + 16384);      // Q half (64 queries)
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  if (!(p.dbg & 16))
+                    umma_ss2(tmem_s, a_desc + 2 * k, b_desc + 2 * k, idesc1, (d | u | k) != 0 ? 1u : 0u);
+              }
+              umma_commit2_mcast(empty0 + stage * 8, pair_mask);
+              if (d + CPS >= nd) umma_commit2_mcast(smem_u32(&bars->s_full[sb]), pair_mask);
+            }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
+          ++own;
+        }
+        if (r > 0) gemm2_round(r - 1);
+      }
+      if (R > 0) gemm2_round(R - 1);
+      if (elect_one()) umma_commit2_mcast(smem_u32(&bars->o_full), pair_mask);
+      __syncwarp();
+    } else {
+      // ===================================================== relay (odd CTA): half-slot full -> tell the leader
+#pragma unroll 1
+      for (int rr = 0; rr < R; ++rr) {
+#pragma unroll 1
+        for (int src = 0; src < CS; ++src) {
+          const int i = rr * CS + src;
+          if (i >= T) break;
+          mbar_wait(pfull0 + src * 8, rr & 1);
+          if (elect_one()) {
+            if (src != static_cast<int>(rank) && i + CS < T) mbar_arrive_expect_tx(pfull0 + src * 8, xbytes);
+            mbar_arrive_cluster(ppeer0 + src * 8, leader);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================================================== exp warps (+ epilogue), both CTAs
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                 // TMEM lane = key within my tile (exp) / class (epilogue)
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float c1 = p.c1;
+    const float cadd = p.c0;
+    const float o_scale = p.o_scale;
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const uint32_t my_slot = slot0 + rank * kHalf;    // half h of my tile (for my own pair)
+    int own = 0, sent = 0;
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+      if (r * CS + pair_first >= T) break;
+      const bool has_tile = (r * CS + static_cast<int>(rank) < T);
+      const int b = own & 1;
+      mbar_wait(smem_u32(&bars->s_full[b]), (own >> 1) & 1);
+      tc_fence_after();
+      if (has_tile) {
+        mbar_wait(smem_u32(&bars->p_empty), (sent & 1) ^ 1u);     // both pairs retired my previous tile
+#pragma unroll
+        for (int cc = 0; cc < ((p.dbg & 8) ? 0 : kBQ / 32); ++cc) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + lane_addr + b * 128 + cc * 32, rg);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(rg[2 * j]), c1, cadd));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(rg[2 * j + 1]), c1, cadd));
+            pk[j] = pack_16x2<kF16>(e0, e1);
+          }
+          // queries cc*32 .. +31 of key `row`: half (cc>>1) of P^T, 16-byte chunks (cc&1)*4 .. +3 of its row
+          const uint32_t base = (((cc >> 1) == h) ? my_slot : stag0) + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + j);
+            const uint32_t addr = base + ((chunk ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]),
+                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+        else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), leader);
+      }
+      if (has_tile) {
+        fence_proxy_async_smem();
+        named_bar_sync(1, kExpThreads);
+        if (threadIdx.x == 64) {
+          const uint32_t pf = smem_u32(&bars->p_full[rank]);
+          mbar_arrive(pf);                                                   // my own half-slot
+          bulk_copy_to_peer(mapa(my_slot, rank ^ 1u), stag0, xbytes, mapa(pf, rank ^ 1u));          // partner: other half
+          if (CS == 4) {
+            bulk_copy_to_peer(mapa(my_slot, rank ^ 2u), my_slot, xbytes, mapa(pf, rank ^ 2u));      // same half, other pair
+            bulk_copy_to_peer(mapa(my_slot, rank ^ 3u), stag0, xbytes, mapa(pf, rank ^ 3u));        // other half, other pair
+          }
+        }
+        ++sent;
+      }
+      ++own;
+    }
+    // ---- epilogue: O^T blocks (lane = class, column = query) -> O[q, class]
+    mbar_wait(smem_u32(&bars->o_full), 0);
+    tc_fence_after();
+    const int c_end = min(c0 + p.slice, p.n_cols);
+#pragma unroll 1
+    for (int mb = 0; mb < n_mb; ++mb) {
+      const int cls = c0 + mb * 128 + row;
+#pragma unroll 1
+      for (int cc = 0; cc < kBQ / 16; ++cc) {
+        uint32_t rg[16];
+        tmem_ld_32x16(tmem_base + lane_addr + kColO + mb * 128 + cc * 16, rg);
+        tmem_ld_wait();
+        if (cls < c_end) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int q = q0 + cc * 16 + j;
+            if (q < p.Nq)
+              p.O[(static_cast<long long>(split) * p.Nq + q) * p.ldo + cls] =
+                  (T > 0) ? __uint_as_float(rg[j]) * o_scale : 0.0f;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+// 16-bit row-major [rows, cols]; box = [box_rows x 64 cols], SW128 (own copy: box shapes differ per kernel)
+template <bool kF16, int NPAIR, int CPS>
+int launch_t(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+             const TParams& p) {
+  auto kernel = sc_attn_t_kernel<kF16, NPAIR, CPS>;
+  SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * NPAIR;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmQ, tmK, tmV, p));
+  return SC_OK;
+}
+
+}  // namespace
+
+namespace sc {
+
+// Called by sc_attn_fwd (sc_attn.cu) after argument validation; needs n_slices == 2 or a multiple of 4.
+int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                  const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk, int64_t D_pad,
+                  int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices, float beta,
+                  int splits, float* O, int64_t ldo, cudaStream_t st) {
+  SC_REQUIRE(n_slices == 2 || n_slices % 4 == 0, SC_EUNSUPPORTED, "transposed kernel needs 2 or 4k class slices");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, 64, f16)) != SC_OK) return rc;        // 64 queries x 64 d
+  if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, 128, f16)) != SC_OK) return rc;       // 128 keys x 64 d
+  if ((rc = make_tmap(&tmV, Vt, C_pad, Nk_pad, Nk_pad, 128, f16)) != SC_OK) return rc;  // 128 classes x 64 keys
+  TParams p;
+  p.Nq = static_cast<int>(Nq);
+  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.n_cols = static_cast<int>(n_cols);
+  p.slice = slice;
+  p.n_mb = (slice + 127) / 128;
+  p.tiles_total = static_cast<int>(ceil_div(Nk, kBN));
+  p.splits = splits;
+  p.c1 = beta * 1.4426950408889634f;
+  p.c0 = -p.c1 + (f16 ? kPShift : 0.0f);
+  p.o_scale = f16 ? exp2f(-kPShift) : 1.0f;
+  p.O = O;
+  p.ldo = ldo;
+  p.dbg = 0;
+#ifdef SC_ATTN_TIMING_EXPERIMENTS   // never in the shipped library: skipping work gives wrong results
+  if (const char* env = std::getenv("SC_ATTN_DEBUG_SKIP")) p.dbg = std::atoi(env);
+#endif
+  dim3 grid(static_cast<unsigned>(n_slices), static_cast<unsigned>(ceil_div(Nq, kBQ)), static_cast<unsigned>(splits));
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: too many query tiles; chunk the queries");
+  int cps = 1;
+  if (const char* env = std::getenv("SC_ATTN_T_CHUNKS")) {        // tuning knob: K chunks per ring stage
+    if (std::atoi(env) == 2) cps = 2;
+  }
+#define SC_T_LAUNCH(F, NPV)                                                                       \
+  (cps == 2 ? launch_t<F, NPV, 2>(grid, st, tmQ, tmK, tmV, p) : launch_t<F, NPV, 1>(grid, st, tmQ, tmK, tmV, p))
+  if (n_slices == 2) {
+    rc = f16 ? SC_T_LAUNCH(true, 1) : SC_T_LAUNCH(false, 1);
+  } else {
+    rc = f16 ? SC_T_LAUNCH(true, 2) : SC_T_LAUNCH(false, 2);
+  }
+#undef SC_T_LAUNCH
+  return rc;
+}
+
+}  // namespace sc

@@ -410,3 +410,27 @@ def test_full_size_key_bank_properties(ops, nq):
     torch.testing.assert_close(O[rows][:, :c], ref, rtol=2e-3, atol=1e-2)
     O0 = ops.attn_fwd(Qn[:128].contiguous(), Kn, Vt, nk, c + 1, 0.0)
     assert torch.all(O0[:, c] == nk)
+
+
+# ----------------------------------------------------------------------------- the three attention kernels agree
+@pytest.mark.parametrize("shape", [(300, 2000, 512, 1000), (257, 900, 1024, 397), (129, 300, 128, 100)])
+def test_attention_kernel_variants_agree(ops, shape, monkeypatch):
+    """SC_ATTN_IMPL selects the transposed pair kernel (default), the pair kernel or the single-CTA-MMA
+    cluster kernel; SC_ATTN_T_CHUNKS the ring-stage granularity.  Same operands -> same result up to the
+    fp32 summation order."""
+    nq, nk, dim, c = shape
+    g = torch.Generator().manual_seed(71)
+    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
+    Vt = ops.values_prepare(torch.randn(nk, c, generator=g).cuda(), c, softmax_scale=2.0)
+    outs = {}
+    for name, env in (("t", {"SC_ATTN_IMPL": "t"}), ("t2", {"SC_ATTN_IMPL": "t", "SC_ATTN_T_CHUNKS": "2"}),
+                      ("pair", {"SC_ATTN_IMPL": "pair"}), ("cluster", {"SC_ATTN_IMPL": "cluster"}),
+                      ("cluster1", {"SC_ATTN_IMPL": "cluster", "SC_ATTN_CLUSTER": "1"})):
+        for k in ("SC_ATTN_IMPL", "SC_ATTN_T_CHUNKS", "SC_ATTN_CLUSTER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs[name] = ops.attn_fwd(Qn, Kn, Vt, nk, c, 5.5, splits=2)
+    for name, o in outs.items():
+        torch.testing.assert_close(o, outs["cluster1"], rtol=2e-4, atol=1e-5, msg=lambda m: f"{name}: {m}")
