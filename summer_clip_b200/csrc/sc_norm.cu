@@ -36,6 +36,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
   if (normalize) {
     float ss = 0.f;
     if (my_off >= 0) {
+#pragma unroll 8
       for (int64_t d = ty; d < D; d += 8) {
         const float v = sc::to_f32<T>(src[d * stride_d + my_off]);
         ss = fmaf(v, v, ss);

@@ -1,0 +1,160 @@
+"""Secondary measurements on one B200 (the headline line comes from bench.py): the other BASELINE.json
+configs and the HBM-bound kernels against the measured copy bandwidth.  One JSON object per line.
+
+    python tools/bench_configs.py [--quick] > gpurun_out/configs.jsonl
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from bench import make_banks, read_peaks  # noqa: E402
+from summer_clip_b200 import build as _build, ops  # noqa: E402
+from summer_clip_b200.searcher import ClipSearcher  # noqa: E402
+
+
+def timed(fn, warmup=2, iters=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def attention_config(name, nq, nk, dim, c, peaks, beta=5.5):
+    dev = torch.device("cuda")
+    q_bank, k_bank, outs, text, labels = make_banks(torch, nq, 0, nk, dim, c, seed=3, device=dev)
+    s = ClipSearcher(dev)
+    s.set_text(text)
+    s.set_cache(k_bank, outs)
+    del k_bank, outs
+    qn, z = s.prepare_queries(q_bank)
+    med, best = timed(lambda: s.cache_logits(qn, beta), warmup=2, iters=3)
+    flops = 2.0 * nq * nk * (dim + c)
+    emit(config=name, kind="attention", n_queries=nq, n_keys=nk, dim=dim, n_classes=c, ms=med,
+         queries_per_s=nq / (med * 1e-3), tflops=flops / (med * 1e-3) / 1e12,
+         frac_of_bf16_peak=flops / (med * 1e-3) / 1e12 / peaks["bf16_tflops"], dtype=str(ops.OP_DTYPE))
+    return s, q_bank, labels, z, qn
+
+
+def main():
+    quick = "--quick" in sys.argv
+    _build.build_library()
+    peaks = read_peaks()
+    dev = torch.device("cuda")
+    hbm = peaks["hbm_gbs"]
+
+    # ---- cfg1: SUN397-shaped image attention
+    attention_config("cfg1_sun397", 19850, 19850, 1024, 397, peaks)
+    torch.cuda.empty_cache()
+
+    # ---- cfg2: Tip-Adapter ImageNet 16-shot head + search_hp sweep (200 beta x 20 alpha)
+    from summer_clip_b200.tip_adapter import utils as tip_utils
+    nq, nk, dim, c = 50000, 16000, 1024, 1000
+    g = torch.Generator(device=dev).manual_seed(2)
+    protos = torch.nn.functional.normalize(torch.randn(c, dim, generator=g, device=dev), dim=1)
+    yk = torch.arange(nk, device=dev) % c
+    keys = torch.nn.functional.normalize(protos[yk] + torch.randn(nk, dim, generator=g, device=dev) / dim ** 0.5, dim=1).half().t()
+    vals = torch.nn.functional.one_hot(yk, c).half()
+    yq = torch.randint(0, c, (nq,), generator=g, device=dev)
+    feats = torch.nn.functional.normalize(protos[yq] + torch.randn(nq, dim, generator=g, device=dev) / dim ** 0.5, dim=1).half()
+    clip_w = torch.nn.functional.normalize(protos + 2.0 / dim ** 0.5 * torch.randn(c, dim, generator=g, device=dev), dim=1).t().contiguous().half()
+    head = tip_utils.TipAdapterHead(keys, vals, feats, clip_w)
+    med, _ = timed(lambda: head.cache_logits(5.5), iters=5)
+    flops = 2.0 * nq * nk * (dim + c)
+    emit(config="cfg2_tip_imagenet_16shot", kind="attention_per_beta", ms=med, queries_per_s=nq / (med * 1e-3),
+         tflops=flops / (med * 1e-3) / 1e12, frac_of_bf16_peak=flops / (med * 1e-3) / 1e12 / peaks["bf16_tflops"])
+    cfg = {"search_hp": True, "search_scale": [7, 3], "search_step": [20, 20] if quick else [200, 20]}
+    import contextlib
+    import io
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        bb, ba = tip_utils.search_hp(cfg, keys, vals, feats, yq.int(), clip_w)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    emit(config="cfg2_tip_imagenet_16shot", kind="search_hp_sweep", grid=cfg["search_step"], seconds=dt,
+         best_beta=bb, best_alpha=ba,
+         note="reference recomputes both GEMMs and the zero-shot GEMM for each of the beta x alpha points")
+    del head, keys, vals, feats
+    torch.cuda.empty_cache()
+
+    # ---- cfg4: ViT-L/14 (768-d) attention + UPL per-class top-16 selection on the 1.28M x 1000 logits bank
+    n, c = 1281167, 1000
+    nq4 = 8192 if quick else 50000
+    s, q_bank, labels, z, qn = attention_config("cfg4_imagenet_vitl14", nq4, n, 768, c, peaks)
+    del s, qn
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(4)
+    for dt_name, dtype in (("fp16", torch.float16), ("fp32", torch.float32)):
+        L = (0.25 + 0.02 * torch.randn(n, c, generator=g, device=dev)).to(dtype)
+        bytes_alg = n * c * L.element_size() + 8 * n
+        for prob in (False, True):
+            med, best = timed(lambda: ops.rowconf(L, scale=100.00000762939453 if prob else 1.0, prob=prob), iters=5)
+            emit(config="cfg4_selection", kind="rowconf", logits_dtype=dt_name, prob=prob, ms=med, gbs=bytes_alg / (med * 1e-3) / 1e9,
+                 frac_of_hbm=bytes_alg / (med * 1e-3) / 1e9 / hbm, algorithmic_bytes=bytes_alg)
+        conf, label = ops.rowconf(L, scale=100.00000762939453, prob=True)
+        med, best = timed(lambda: ops.topk_per_class(conf, label, c, 16), iters=5)
+        emit(config="cfg4_selection", kind="topk_per_class_k16", logits_dtype=dt_name, ms=med,
+             note="histogram + scan + scatter + radix select; 32 N bytes of traffic", gbs=32.0 * n / (med * 1e-3) / 1e9)
+        medv, _ = timed(lambda: ops.values_prepare(L, c), iters=3)
+        bytes_v = n * c * L.element_size() + ops.pad_classes(c) * ops.pad_keys(n) * 2 * 2
+        emit(config="cfg4_selection", kind="values_hard_all_logits", logits_dtype=dt_name, ms=medv,
+             gbs=bytes_v / (medv * 1e-3) / 1e9, frac_of_hbm=bytes_v / (medv * 1e-3) / 1e9 / hbm)
+        del L, conf, label
+        torch.cuda.empty_cache()
+
+    # ---- K-norm: column-normalise + transpose + cast of the 1.28M x 1024 fp16 bank
+    dim = 1024
+    bank = torch.randn(dim, n, device=dev, dtype=torch.float16)
+    out = torch.empty((n, dim), dtype=ops.OP_DTYPE, device=dev)
+    med, _ = timed(lambda: ops.normalize_cast(bank, True, out=out), iters=5)
+    b = n * dim * 4
+    emit(config="k_norm", kind="normalize_cast_feature_major", ms=med, gbs=b / (med * 1e-3) / 1e9,
+         frac_of_hbm=b / (med * 1e-3) / 1e9 / hbm, algorithmic_bytes=b)
+    idx = torch.randperm(n, device=dev)[:16000]
+    med, _ = timed(lambda: ops.normalize_cast(bank, True, idx=idx), iters=5)
+    emit(config="k_norm", kind="gather_normalize_cast_16k_columns", ms=med)
+    del bank, out
+    torch.cuda.empty_cache()
+
+    # ---- cfg5: latency sweep, query batch 1..4096 against the 1.28M-key RN50 bank (1 GPU)
+    q_bank, k_bank, outs, text, labels = make_banks(torch, 4096, 0, n, 1024, c, seed=5, device=dev)
+    s = ClipSearcher(dev)
+    s.set_text(text)
+    s.set_cache(k_bank, outs)
+    del k_bank, outs
+    bank_bytes = 2.0 * n * (1024 + ops.pad_classes(c))
+    for b in ([1, 64, 1024, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]):
+        qb = q_bank[:, :b].contiguous()
+        lab = labels[:b].contiguous()
+        lat = []
+        for it in range(12):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = s.search(qb, [5.5], [1.0], labels=lab)[0]
+            pred = res["pred"].cpu()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[2:])
+        emit(config="cfg5_latency", batch=b, p50_ms=lat[len(lat) // 2], p99_ms=lat[-1], queries_per_s=b / (lat[len(lat) // 2] * 1e-3),
+             bank_gbs=bank_bytes / (lat[len(lat) // 2] * 1e-3) / 1e9)
+
+
+if __name__ == "__main__":
+    main()
