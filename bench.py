@@ -50,7 +50,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -75,21 +75,23 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
                 for name, bit in names.items():
                     if mask & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
         s = sorted(self.samples)
+        pw = sorted(self.power)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "power_w": round(pw[len(pw) // 2], 1) if pw else None}
 
 
 def make_banks(torch, nq, nk_lo, nk_hi, dim, n_classes, seed, device):
@@ -158,10 +160,17 @@ def run_ours(args):
     bank_build_ms = (time.perf_counter() - t0) * 1e3
     n_local = hi - lo
     del k_bank, outs
-    c_pad = searcher.vt.shape[0]
+    c_pad = ops.pad_classes(n_classes)
     splits = ops.attn_splits(nq, n_local, c_pad, device)
     if os.environ.get("SC_BENCH_SPLITS"):                  # tuning knob for A/B runs
         splits = int(os.environ["SC_BENCH_SPLITS"])
+
+    def attn(qn, merge):
+        """Fused attention against the resident bank: one-hot values go through the hard-label kernel (GEMM-2
+        operand = static on-chip one-hot zone, label-sorted bank), dense values through the Vt-streaming kernel."""
+        if searcher.hard_bank is not None:
+            return ops.attn_fwd_hard(qn, searcher.hard_bank, BETA, splits=splits, merge=merge)
+        return ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits, merge=merge)
 
     q_host = q_bank.cpu().pin_memory()
     labels_host = labels.cpu().pin_memory()
@@ -175,7 +184,7 @@ def run_ours(args):
         z = ops.zero_shot_logits(q_bank, True, searcher.text)
         if time_attn is not None:
             time_attn[0].record(stream)
-        part = ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits, merge=False)
+        part = attn(qn, False)
         if time_attn is not None:
             time_attn[1].record(stream)
         o = ops.merge_partials(part) if splits > 1 else part[0]
@@ -195,7 +204,7 @@ def run_ours(args):
         lab = labels_host.to(device, non_blocking=True)
         qn = ops.normalize_cast(q_dev, True)
         z = ops.zero_shot_logits(q_dev, True, searcher.text)
-        o = ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits)
+        o = attn(qn, True)
         if world > 1:
             gathered = torch.empty((world, nq, n_classes), dtype=torch.float32, device=device)
             dist.all_gather_into_tensor(gathered, o.contiguous(), group=group)
@@ -233,6 +242,15 @@ def run_ours(args):
     ev1.record(stream)
     sync_all()
     clocks = sampler.stop()
+    if os.environ.get("SC_ATTN_CLKPROBE"):                 # experiments builds: clock seen by the attention CTAs
+        try:
+            import ctypes
+            from summer_clip_b200 import _lib
+            fn = getattr(_lib.load(), "sc_debug_attn_hard_clock_mhz" if searcher.hard_bank is not None else "sc_debug_attn_clock_mhz")
+            fn.restype = ctypes.c_double
+            clocks["attn_cta_mhz"] = round(float(fn()), 1)
+        except Exception as exc:  # noqa: BLE001
+            clocks["attn_cta_mhz"] = str(exc)
     total_ms = max_over_ranks(ev0.elapsed_time(ev1))
     attn_ms = sum(a.elapsed_time(b) for a, b in attn_events) / args.steps
     gpu_launches = launches["n"]
@@ -256,7 +274,14 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
     flops = 2.0 * nq * n_local * (dim + n_classes)                  # 2*Nq*Nk*(D + C) per launch
-    achieved = flops / (attn_ms * 1e-3) / 1e12
+    if searcher.hard_bank is not None:
+        # label-sorted one-hot bank: GEMM-1 on every (padded) key, GEMM-2 as ONE pair UMMA (M=256 class rows x 16
+        # keys x 128 queries) per 16-key group — the all-zero class tiles are skipped
+        executed = 2.0 * nq * searcher.hard_bank.n_sorted * (dim + 256)
+    else:
+        executed = 2.0 * nq * n_local * (dim + c_pad)
+    achieved = executed / (attn_ms * 1e-3) / 1e12                   # tensor-core work actually issued
+    dense_equiv = flops / (attn_ms * 1e-3) / 1e12
     traffic = None
     try:
         with open(os.path.join(REPO, "profiles", "attn_traffic.json")) as f:
@@ -272,11 +297,16 @@ def run_ours(args):
                    "n_classes": n_classes, "beta": BETA, "alpha": ALPHA, "values": "hard (one-hot of argmax L)",
                    "sharding": f"key-sharded x{world}, all-gather + sum merge" if world > 1 else "single GPU",
                    "key_splits_per_gpu": splits, "accumulate": "fp32",
-                   "l2": "inputs larger than L2: key bank + values = %.2f GB per GPU" % (2 * n_local * (dim + c_pad) / 1e9),
+                   "l2": "inputs larger than L2: key bank = %.2f GB per GPU (+ %s)" % (
+                       2 * n_local * dim / 1e9, "sorted by label" if searcher.hard_bank is not None else "%.2f GB dense values" % (2 * n_local * c_pad / 1e9)),
+                   "values_operand": "one-hot, label-sorted bank (static on-chip operand, zero tiles skipped)" if searcher.hard_bank is not None else "dense Vt",
                    "bank_build_ms": bank_build_ms, "top1_count": top1},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                     "kernel": "sc_attn_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
+                     "kernel": "sc_attn_ts_kernel" if searcher.hard_bank is not None else "sc_attn_t_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
+                     "executed_flops_per_launch": executed, "dense_equivalent_tflops": dense_equiv,
+                     "note": "achieved/frac count the tensor-core FLOPs actually issued; dense_equivalent_tflops = "
+                             "2*Nq*Nk*(D+C)/time, the rate a dense-V kernel would need for the same queries/s",
                      "peak_source": peaks["source"] + " burst (cuBLAS bf16 8192^3)",
                      "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None},
         "e2e": {"value": nq / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",

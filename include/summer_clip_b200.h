@@ -110,6 +110,34 @@ int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, in
                 int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
                 int splits, float* O, int64_t ldo, void* stream);
 
+/* Hard-label cache values for sc_attn_fwd_hard: labels16[k] = argmax_c L[idx[k]] (or labels_override[k]) as
+ * int16 for k < n_out, and -1 for n_out <= k < n_pad and for labels outside [0, C) — i.e. the one-hot cache
+ * values of HardCacheStrategy (cache_value_strategy.py:14-17), of cache.replace_outs_with_golds
+ * (image_attention.py:65-66) and of Tip-Adapter's cache_values (tip_adapter/utils.py:62) in 2 bytes per key.
+ * n_pad = sc_pad_labels(n_out) (a multiple of the kernel's 128-key tile). */
+int64_t sc_pad_labels(int64_t Nk);
+int sc_hard_labels(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, const int64_t* idx,
+                   const int32_t* labels_override, int64_t n_out, int16_t* labels16, int64_t n_pad,
+                   void* stream);
+
+/* sc_attn_fwd for one-hot cache values on a LABEL-SORTED key bank (same result as sc_attn_fwd on
+ * Vt = one_hot(label)^T; the sum over keys does not depend on their order):
+ *     O[s, q, c] = sum_{k in split s, class(k) == c} exp(beta * (Qn[q].Ks[k] - 1)),   c < n_classes.
+ * The caller permutes the normalised bank once so that keys of one class are adjacent and every class
+ * segment starts on a 16-key boundary (padding rows: anything finite, e.g. zeros):
+ *   Ks          [Nks, D_pad]                 the permuted, padded bank (op_dtype);
+ *   group_class int16 [ceil(Nks/128) * 8]    class of every 16-key group, -1 = no real key in it;
+ *   key_valid   uint8 [ceil(Nks/128) * 128]  1 = real key, 0 = padding (its weight is forced to 0).
+ * GEMM-2 still runs as dense tensor-core tiles, but every 16-key step has a single non-zero class row, read
+ * from a static shared-memory zone (nothing is streamed for the values: 40 % fewer operand bytes per pass),
+ * and the all-zero tiles of the other class slices are skipped (exact).  Needs
+ * sc_attn_hard_supported(n_classes) != 0 (more than 256 classes, <= 32767); otherwise build Vt with
+ * sc_values_prepare and call sc_attn_fwd. */
+int sc_attn_hard_supported(int64_t n_classes);
+int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint8_t* key_valid,
+                     int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta,
+                     int splits, float* O, int64_t ldo, void* stream);
+
 /* out[r, c] = sum_p parts[p, r, c]  (key splits and key-sharded ranks; with the Tip weights
  * exp(beta(A-1)) <= 1 the running maximum of an LSE merge is the constant 0, so the merge of
  * partial (m, l, O) triples is a plain sum).  parts: fp32 [n_parts, rows, ld]. `out` may alias

@@ -15,21 +15,45 @@ from .. import ops
 
 
 class CacheValues:
-    def __init__(self, vt: torch.Tensor, n_keys: int, n_classes: int) -> None:
-        self._vt, self.n_keys, self.n_classes = vt, int(n_keys), int(n_classes)
+    """Cache values in kernel layout: the dense transposed matrix `vt` and/or — for one-hot values — the int16
+    label vector `labels16` the hard-label kernel synthesises its GEMM-2 operand from (2 bytes per key instead
+    of 2*C_pad).  Whichever of the two is missing is built on first use."""
+
+    def __init__(self, vt: tp.Optional[torch.Tensor], n_keys: int, n_classes: int,
+                 labels16: tp.Optional[torch.Tensor] = None) -> None:
+        assert vt is not None or labels16 is not None
+        self._vt, self.n_keys, self.n_classes, self.labels16 = vt, int(n_keys), int(n_classes), labels16
+        self._bank: tp.Optional[ops.HardBank] = None
+        self._bank_key: tp.Optional[tuple] = None
 
     @property
     def shape(self) -> tp.Tuple[int, int]:
         return (self.n_keys, self.n_classes)
 
+    @property
+    def is_hard(self) -> bool:
+        return self.labels16 is not None
+
+    def hard_bank(self, k_norm: torch.Tensor) -> "ops.HardBank":
+        """The label-sorted copy of the normalised key bank `k_norm` for these one-hot values (built once per
+        (values, bank) pair; the reference loop reuses both across betas, image_attention.py:106-109)."""
+        key = (k_norm.data_ptr(), tuple(k_norm.shape), k_norm.dtype, k_norm._version)
+        if self._bank is None or self._bank_key != key:
+            layout = self._bank if self._bank is not None else ops.hard_bank_layout(self.labels16[: self.n_keys], self.n_classes)
+            self._bank, self._bank_key = layout.gather(k_norm), key
+        return self._bank
+
     def vt(self, op_dtype: torch.dtype) -> torch.Tensor:
+        if self._vt is None:        # one-hot values from the labels (-1 pads select no class)
+            self._vt = ops.values_prepare(None, self.n_classes, labels=self.labels16[: self.n_keys].to(torch.int32),
+                                          op_dtype=op_dtype)
         if self._vt.dtype != op_dtype:
             self._vt = self._vt.to(op_dtype)
         return self._vt
 
     def dense(self) -> torch.Tensor:
         """[Nk, C] float tensor, what the reference's strategy would have returned."""
-        return self._vt[: self.n_classes, : self.n_keys].t().float()
+        return self.vt(ops.OP_DTYPE)[: self.n_classes, : self.n_keys].t().float()
 
     @staticmethod
     def from_dense(values: torch.Tensor, op_dtype: tp.Optional[torch.dtype] = None) -> "CacheValues":
@@ -37,6 +61,12 @@ class CacheValues:
         pad with the cast-only mode of the normalise kernel."""
         n_keys, n_classes = values.shape
         op_dtype = ops._op(op_dtype)
+        if ops.hard_supported(n_classes) and n_keys > 0:
+            # one-hot rows (Tip-Adapter cache_values, tip_adapter/utils.py:62) -> labels for the hard-label kernel
+            rows = values if values.stride(1) == 1 else values.contiguous()
+            conf, label = ops.rowconf(rows)
+            if bool(((conf == 1) & (rows.float().abs().sum(1) == 1)).all()):
+                return CacheValues(None, n_keys, n_classes, labels16=ops.hard_labels(None, n_classes, labels=label))
         c_pad, nk_pad = ops.pad_classes(n_classes), ops.pad_dim(n_keys)   # pad_dim: multiple of 64 (and of 8)
         vt = torch.zeros((c_pad, nk_pad), dtype=op_dtype, device=values.device)
         ops.normalize_cast(values, feature_major=True, normalize=False, out=vt)
@@ -53,8 +83,10 @@ class HardCacheStrategy(CacheValueStrategy):
     """cache_value_strategy.py:13-17 — one_hot(argmax_c cache_outs)."""
 
     def transform(self, cache_outs: torch.Tensor, idx: tp.Optional[torch.Tensor] = None) -> CacheValues:
-        vt = ops.values_prepare(cache_outs, cache_outs.shape[1], idx=idx)
-        return CacheValues(vt, cache_outs.shape[0] if idx is None else idx.numel(), cache_outs.shape[1])
+        n_keys, n_classes = cache_outs.shape[0] if idx is None else idx.numel(), cache_outs.shape[1]
+        if ops.hard_supported(n_classes):
+            return CacheValues(None, n_keys, n_classes, labels16=ops.hard_labels(cache_outs, n_classes, idx=idx))
+        return CacheValues(ops.values_prepare(cache_outs, n_classes, idx=idx), n_keys, n_classes)
 
 
 class SoftmaxCacheStrategy(CacheValueStrategy):
@@ -78,5 +110,7 @@ class GoldCacheValues(CacheValueStrategy):
         self.n_classes = n_classes
 
     def transform(self, labels: torch.Tensor) -> CacheValues:
-        vt = ops.values_prepare(None, self.n_classes, labels=labels)
-        return CacheValues(vt, labels.numel(), self.n_classes)
+        if ops.hard_supported(self.n_classes):
+            return CacheValues(None, labels.numel(), self.n_classes,
+                               labels16=ops.hard_labels(None, self.n_classes, labels=labels))
+        return CacheValues(ops.values_prepare(None, self.n_classes, labels=labels), labels.numel(), self.n_classes)

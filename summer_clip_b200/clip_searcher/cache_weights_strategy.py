@@ -67,6 +67,8 @@ class FusedWeights:
             values = CacheValues.from_dense(values, op_dtype=self.q_norm.dtype)
         if values.n_keys != self.n_keys:
             raise ValueError(f"weights have {self.n_keys} keys but values have {values.n_keys}")
+        if values.is_hard:     # one-hot values: GEMM-2 operand synthesised on chip from the labels
+            return ops.attn_fwd_hard(self.q_norm, values.hard_bank(self.k_norm), self.beta)
         vt = values.vt(self.q_norm.dtype)
         return ops.attn_fwd(self.q_norm, self.k_norm, vt, self.n_keys, values.n_classes, self.beta)
 

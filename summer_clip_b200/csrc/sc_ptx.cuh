@@ -80,6 +80,24 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return ok != 0;
 }
 
+// Non-blocking probe (never suspends the thread): issued BEFORE a batch of TMA / UMMA instructions for the
+// current stage so that its ~150-cycle latency hides under their issue cost; a blocking wait follows only
+// when the probe failed.  (try_wait on an already-complete barrier costs ~117 cycles of a single-thread
+// issue loop whose whole budget is the 256 cycles four N=128 UMMAs execute in.)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+
 // Bounded wait: a pipeline bug must trap, never hang the GPU.
 #ifndef SC_MBAR_TIMEOUT_CYCLES
 #define SC_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 2 GHz
@@ -191,6 +209,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// store 32 consecutive fp32 columns of this thread's lane (base_lane + i); pair with tmem_st_wait()
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -299,5 +332,79 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtenso
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c_inner), "r"(c_outer)
       : "memory");
+}
+}  // namespace scptx
+
+// ---------------------------------------------------------------- fused issue + probe (single-thread issue loops)
+// The TMA-producer and MMA-issuer loops each have the time four N=128 UMMAs execute in (256 cycles) per ring
+// stage.  Measured on B200: try_wait on a completed mbarrier 117 cycles, one UMMA issue ~36, one TMA issue
+// ~70 — a naive wait-then-issue loop does not fit.  These helpers put the non-blocking probe of the NEXT
+// ring slot, the elected issue of this stage's instructions and the read-back of the probe into ONE asm
+// block, so that ptxas cannot place the probe's consumer before the issues and the probe latency is hidden.
+// Call them warp-uniformly (all 32 lanes); they return 1 when the probed phase had completed.
+namespace scptx {
+
+// probe + 4 pair UMMAs (one 64-element K chunk) + commit to bar1 (and to bar2 iff flag2)
+__device__ __forceinline__ uint32_t umma4_cg2_probe(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2,
+                                                    uint64_t a3, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                                    uint32_t idesc, uint32_t acc0, uint32_t enable, uint32_t bar1,
+                                                    uint16_t mask1, uint32_t bar2, uint16_t mask2, uint32_t flag2,
+                                                    uint32_t probe_bar, uint32_t probe_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pp, pe, pm, pa, pt, p2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pp, [%18], %19;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.and.b32 pm, %12, 0, pe;\n\t"
+      "setp.ne.b32 pa, %11, 0;\n\t"
+      "setp.eq.b32 pt, %11, %11;\n\t"
+      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %6, %10, pa;\n\t"
+      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %3, %7, %10, pt;\n\t"
+      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %4, %8, %10, pt;\n\t"
+      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %5, %9, %10, pt;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%13], %14;\n\t"
+      "setp.ne.and.b32 p2, %17, 0, pe;\n\t"
+      "@p2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%15], %16;\n\t"
+      "selp.u32 %0, 1, 0, pp;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(acc0),
+        "r"(enable), "r"(bar1), "h"(mask1), "r"(bar2), "h"(mask2), "r"(flag2), "r"(probe_bar), "r"(probe_parity)
+      : "memory");
+  return ok;
+}
+
+// probe + (expect_tx of tx_bytes on full_local iff tx_bytes != 0, plain arrive iff plain != 0) + up to two
+// pair TMA loads whose bytes are credited to bar_cluster
+__device__ __forceinline__ uint32_t tma2_cg2_probe(uint32_t dst0, const CUtensorMap* m0, int32_t x0, int32_t y0,
+                                                   uint32_t on0, uint32_t dst1, const CUtensorMap* m1, int32_t x1,
+                                                   int32_t y1, uint32_t on1, uint32_t bar_cluster, uint32_t full_local,
+                                                   uint32_t tx_bytes, uint32_t plain, uint32_t probe_bar,
+                                                   uint32_t probe_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pp, pe, px, pa, p0, p1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pp, [%15], %16;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.and.b32 px, %13, 0, pe;\n\t"
+      "@px mbarrier.arrive.expect_tx.shared::cta.b64 _, [%12], %13;\n\t"
+      "setp.ne.and.b32 pa, %14, 0, pe;\n\t"
+      "@pa mbarrier.arrive.shared::cta.b64 _, [%12];\n\t"
+      "setp.ne.and.b32 p0, %5, 0, pe;\n\t"
+      "@p0 cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%1], [%2, {%3, %4}], [%11];\n\t"
+      "setp.ne.and.b32 p1, %10, 0, pe;\n\t"
+      "@p1 cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%6], [%7, {%8, %9}], [%11];\n\t"
+      "selp.u32 %0, 1, 0, pp;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(dst0), "l"(reinterpret_cast<uint64_t>(m0)), "r"(x0), "r"(y0), "r"(on0), "r"(dst1),
+        "l"(reinterpret_cast<uint64_t>(m1)), "r"(x1), "r"(y1), "r"(on1), "r"(bar_cluster), "r"(full_local),
+        "r"(tx_bytes), "r"(plain), "r"(probe_bar), "r"(probe_parity)
+      : "memory");
+  return ok;
 }
 }  // namespace scptx

@@ -71,6 +71,30 @@ values_softmax_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld,
   }
 }
 
+// Hard labels as the attention kernel's synthesised-values operand: int16 argmax (or override) per selected
+// key, -1 for padding keys and for labels outside [0, C).
+template <typename T>
+__global__ void __launch_bounds__(256)
+hard_labels_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, const int64_t* __restrict__ idx,
+                   const int32_t* __restrict__ labels_override, int64_t n_out, int16_t* __restrict__ out,
+                   int64_t n_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t o = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); o < n_pad;
+       o += warps_per_grid) {
+    int lab = -1;
+    if (o < n_out) {
+      if (labels_override) {
+        lab = labels_override[o];
+      } else {
+        const int64_t r = idx ? idx[o] : o;
+        if (r >= 0 && r < N) lab = sc::row_argmax<T, false>(L + r * ld, C, lane).i;
+      }
+    }
+    if (lane == 0) out[o] = (lab >= 0 && lab < C) ? static_cast<int16_t>(lab) : static_cast<int16_t>(-1);
+  }
+}
+
 template <typename TO>
 __global__ void ones_row_kernel(TO* __restrict__ row, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -119,6 +143,27 @@ extern "C" int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C,
             vt + ones_row * Nk_pad, n_out);
       }
     });
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+extern "C" int sc_hard_labels(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, const int64_t* idx,
+                              const int32_t* labels_override, int64_t n_out, int16_t* labels16, int64_t n_pad,
+                              void* stream) {
+  SC_REQUIRE(labels16, SC_EINVAL, "sc_hard_labels: null output");
+  SC_REQUIRE(L || labels_override, SC_EINVAL, "sc_hard_labels: null L");
+  SC_REQUIRE(C > 0 && C <= 32767 && n_out >= 0 && n_pad >= n_out, SC_ESHAPE, "sc_hard_labels: bad shape");
+  SC_REQUIRE(idx || labels_override || n_out == N, SC_ESHAPE, "sc_hard_labels: n_out must equal N without idx");
+  SC_REQUIRE(L == nullptr || ld >= C, SC_ESHAPE, "sc_hard_labels: ld < C");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_pad > 0) {
+    if (L == nullptr) dtype = SC_F32;
+    const int64_t want = sc::ceil_div(n_pad, 8);
+    const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+    SC_DISPATCH_DTYPE(dtype, T,
+                      (hard_labels_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, idx,
+                                                                     labels_override, n_out, labels16, n_pad)));
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;

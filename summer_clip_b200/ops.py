@@ -169,6 +169,115 @@ def values_prepare(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torc
     return Vt
 
 
+def hard_supported(n_classes: int) -> bool:
+    """True when the hard-label attention kernel (values synthesised on chip from labels) covers n_classes."""
+    if os.environ.get("SUMMER_CLIP_B200_DENSE_VALUES"):      # A/B knob: stream dense one-hot values instead
+        return False
+    return bool(_lib.load().sc_attn_hard_supported(int(n_classes)))
+
+
+def hard_labels(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int16 [sc_pad_labels(n_out)] labels of one-hot cache values: argmax_c L[idx] (HardCacheStrategy,
+    cache_value_strategy.py:14-17) or the given gold labels; -1 pads the last 128-key tile."""
+    dev = (L if L is not None else labels).device
+    if L is not None:
+        _cuda(L, "L")
+        assert L.dim() == 2 and L.stride(1) == 1 and L.shape[1] == n_classes
+        N, C = L.shape
+        ld = L.stride(0) if N > 1 else C
+    else:
+        N, C, ld = 0, n_classes, n_classes
+    if labels is not None:
+        labels = _cuda(labels, "labels").to(torch.int32).contiguous()
+        n_out = labels.numel()
+    elif idx is not None:
+        idx = _cuda(idx, "idx").to(torch.int64).contiguous()
+        n_out = idx.numel()
+    else:
+        n_out = N
+    lib = _lib.load()
+    n_pad = int(lib.sc_pad_labels(n_out))
+    out = torch.empty(n_pad, dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sc_hard_labels(_ptr(L), _code(L) if L is not None else SC_F32, N, C, ld, _ptr(idx), _ptr(labels),
+                                 n_out, _ptr(out), n_pad, _stream()), "sc_hard_labels")
+    return out
+
+
+class HardBank:
+    """Label-sorted key bank for sc_attn_fwd_hard: keys of one class adjacent, every class segment padded to
+    whole 16-key groups.  `perm[j]` = original index of sorted key j (-1 = padding), `gcls` int16 class per
+    16-key group, `kvalid` uint8 per key; `rows` (set by `gather`) = the permuted normalised bank."""
+
+    def __init__(self, perm: torch.Tensor, gcls: torch.Tensor, kvalid: torch.Tensor, n_sorted: int, n_keys: int,
+                 n_classes: int) -> None:
+        self.perm, self.gcls, self.kvalid = perm, gcls, kvalid
+        self.n_sorted, self.n_keys, self.n_classes = int(n_sorted), int(n_keys), int(n_classes)
+        self.rows: Optional[torch.Tensor] = None
+
+    def gather(self, k_norm: torch.Tensor) -> "HardBank":
+        """Permute a normalised bank [>= n_keys, D_pad] (original key order) into sorted order."""
+        src = self.perm.clamp_min(0)
+        rows = k_norm.index_select(0, src)
+        rows[self.perm < 0] = 0
+        self.rows = rows
+        return self
+
+
+def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
+    """Index plumbing of the sorted bank (once per cache): stable sort of the keys by label, class segments
+    padded to multiples of 16, the whole bank padded to whole 128-key tiles.  Labels outside [0, n_classes)
+    select no class and are dropped (their one-hot row is zero)."""
+    _cuda(labels, "labels")
+    dev = labels.device
+    lab = labels.reshape(-1).to(torch.int64)
+    n_keys = lab.numel()
+    valid = (lab >= 0) & (lab < n_classes)
+    lab_v = torch.where(valid, lab, torch.full_like(lab, n_classes))
+    order = torch.argsort(lab_v, stable=True)
+    counts = torch.bincount(lab_v, minlength=n_classes + 1)[:n_classes]
+    padded = (counts + 15) // 16 * 16
+    seg_start = torch.cumsum(padded, 0) - padded
+    cls_start = torch.cumsum(counts, 0) - counts
+    n_valid, n_sorted = (int(v) for v in torch.stack([counts.sum(), padded.sum()]).tolist())
+    order_v = order[:n_valid]
+    lab_sorted = lab_v[order_v]
+    dest = seg_start[lab_sorted] + (torch.arange(n_valid, device=dev) - cls_start[lab_sorted])
+    tiles = max(1, -(-n_sorted // 128))
+    perm = torch.full((tiles * 128,), -1, dtype=torch.int64, device=dev)
+    perm[dest] = order_v
+    gcls = torch.full((tiles * 8,), -1, dtype=torch.int16, device=dev)
+    gcls[dest // 16] = lab_sorted.to(torch.int16)
+    kvalid = (perm >= 0).to(torch.uint8)
+    return HardBank(perm, gcls, kvalid, n_sorted, n_keys, n_classes)
+
+
+def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0, merge: bool = True) -> torch.Tensor:
+    """attn_fwd for one-hot values on a label-sorted bank (hard_bank_layout + HardBank.gather):
+    fp32 [Nq, n_classes] = sum over the keys of each class of exp(beta (q.k - 1))."""
+    _cuda(Qn, "Qn")
+    Ks = bank.rows
+    assert Ks is not None, "HardBank.gather(k_norm) must be called first"
+    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16) and Ks.is_contiguous() and Qn.is_contiguous()
+    Nq, D_pad = Qn.shape
+    assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
+    n_classes = bank.n_classes
+    n_sorted = max(bank.n_sorted, 1)
+    if splits <= 0:
+        splits = attn_splits(Nq, n_sorted, pad_classes(n_classes), Qn.device)
+    O = torch.empty((splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)
+    with torch.cuda.device(Qn.device):
+        check(_lib.load().sc_attn_fwd_hard(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kvalid), _code(Qn), Nq,
+                                           n_sorted, D_pad, n_classes, float(beta), splits, _ptr(O), n_classes,
+                                           _stream()), "sc_attn_fwd_hard")
+    if not merge:
+        return O
+    if splits == 1:
+        return O[0]
+    return merge_partials(O)
+
+
 def attn_splits(Nq: int, Nk: int, C_pad: int, device=None) -> int:
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
     return int(_lib.load().sc_attn_splits(Nq, Nk, C_pad, sms))

@@ -44,7 +44,8 @@ class ClipSearcher:
             self.world, self.rank = 1, 0
         self.text: tp.Optional[torch.Tensor] = None          # [D, C] fp32
         self.k_norm: tp.Optional[torch.Tensor] = None        # [Nk_local, D_pad]
-        self.vt: tp.Optional[torch.Tensor] = None            # [C_pad, Nk_pad]
+        self.vt: tp.Optional[torch.Tensor] = None            # [C_pad, Nk_pad] (dense values)
+        self.hard_bank: tp.Optional[ops.HardBank] = None     # one-hot values: label-sorted key bank (replaces k_norm / vt)
         self.n_keys = 0                                      # local keys
         self.n_keys_global = 0
         self.n_classes = 0
@@ -84,12 +85,22 @@ class ClipSearcher:
             outs = None
             assert n_classes is not None
             self.n_classes = n_classes
+        self.k_norm = self.vt = self.hard_bank = None
         if self.n_keys == 0:
-            self.k_norm = self.vt = None
             return
         self.k_norm = ops.normalize_cast(feats, feature_major=feature_major, idx=local_idx, op_dtype=self.op_dtype)
         self.gpu_launches += 1
         local_labels = labels.to(self.device)[lo:hi] if labels is not None else None
+        self.rowsum_col = None
+        if softmax_scale is None and not softmax_normalize and ops.hard_supported(self.n_classes):
+            # one-hot values: sort the keys by label once; GEMM-2 then reads its operand from a static on-chip
+            # zone and skips the all-zero class tiles (sc_attn_fwd_hard)
+            labels16 = ops.hard_labels(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
+                                       labels=local_labels)
+            self.hard_bank = ops.hard_bank_layout(labels16[: self.n_keys], self.n_classes).gather(self.k_norm)
+            self.k_norm = None
+            self.gpu_launches += 1
+            return
         self.vt = ops.values_prepare(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
                                      labels=local_labels, softmax_scale=softmax_scale, ones_row=softmax_normalize,
                                      op_dtype=self.op_dtype)
@@ -114,10 +125,13 @@ class ClipSearcher:
         n_cols = self.n_classes + (1 if self.rowsum_col is not None else 0)
         nq = qn.shape[0]
         if self.n_keys > 0:
-            c_pad = self.vt.shape[0]
+            c_pad = self.vt.shape[0] if self.vt is not None else ops.pad_classes(self.n_classes)
             if splits <= 0:
                 splits = ops.attn_splits(nq, self.n_keys, c_pad, self.device)
-            part = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, n_cols, beta, splits=splits, merge=True)
+            if self.hard_bank is not None:
+                part = ops.attn_fwd_hard(qn, self.hard_bank, beta, splits=splits)
+            else:
+                part = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, n_cols, beta, splits=splits, merge=True)
             self.gpu_launches += 1 + int(splits > 1)
         else:
             part = torch.zeros((nq, n_cols), dtype=torch.float32, device=self.device)

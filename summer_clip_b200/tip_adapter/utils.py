@@ -49,6 +49,8 @@ class TipAdapterHead:
 
     def cache_logits(self, beta: float) -> torch.Tensor:
         """exp(-(beta - beta * features @ cache_keys)) @ cache_values."""
+        if self.values.is_hard:
+            return ops.attn_fwd_hard(self.q, self.values.hard_bank(self.k), beta)
         return ops.attn_fwd(self.q, self.k, self.values.vt(self.q.dtype), self.n_keys, self.n_classes, beta)
 
     def logits(self, beta: float, alpha: float) -> torch.Tensor:

@@ -4,6 +4,6 @@
 specs="$1"; shift
 for spec in $specs; do
   IFS=: read G NS SP PF SK <<< "$spec"; SP=${SP:-}; PF=${PF:-}; SK=${SK:-0}
-  SC_ATTN_CLUSTER=$G SC_ATTN_STAGES=$NS SC_BENCH_SPLITS=$SP SC_ATTN_PREFETCH=$PF SC_ATTN_DEBUG_SKIP=$SK python bench.py --steps 3 --warmup 2 --no-cpu-baseline "$@" 2>&1 | tail -1 | \
-    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('G=$G NS=$NS SP=$SP PF=$PF SKIP=$SK', 'ms_step=%.1f'%d['ms_per_step'], 'qps=%.0f'%d['value'], 'attn_ms=%.1f'%d['roofline']['kernel_ms'], 'frac=%.3f'%d['roofline']['frac'], 'sm_mhz=%s'%d['clocks']['sm_mhz'], d['clocks']['reasons'], 'top1=%d'%d['config']['top1_count'])"
+  SC_ATTN_CLUSTER=$G SC_ATTN_STAGES=$NS SC_BENCH_SPLITS=$SP SC_ATTN_PREFETCH=$PF SC_ATTN_CLKPROBE=1 SC_ATTN_DEBUG_SKIP=$SK python bench.py --steps 3 --warmup 2 --no-cpu-baseline "$@" 2>&1 | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('G=$G NS=$NS SP=$SP PF=$PF SKIP=$SK', 'ms_step=%.1f'%d['ms_per_step'], 'qps=%.0f'%d['value'], 'attn_ms=%.1f'%d['roofline']['kernel_ms'], 'frac=%.3f'%d['roofline']['frac'], 'sm_mhz=%s'%d['clocks']['sm_mhz'], 'cta_mhz=%s'%d['clocks'].get('attn_cta_mhz'), 'W=%s'%d['clocks'].get('power_w'), d['clocks']['reasons'], 'top1=%d'%d['config']['top1_count'])"
 done

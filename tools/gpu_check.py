@@ -84,6 +84,44 @@ def case_attn(Nq, Nk, D, C, beta, splits, identity_v=False, dt="fp16"):
     return 1 if bad else 0
 
 
+def case_attn_hard(Nq, Nk, D, C, beta, splits, dt="fp16"):
+    """Hard-label kernel (values synthesised from int16 labels) against fp32 on the same rounded operands AND
+    against the dense-Vt kernel on one_hot(labels)."""
+    import torch
+    from summer_clip_b200 import ops
+    ops.OP_DTYPE = torch.float16 if dt == "fp16" else torch.bfloat16
+    Q, K, yq, yk, protos = _banks(Nq, Nk, D, C)
+    Qn = ops.normalize_cast(Q, feature_major=False)
+    Kn = ops.normalize_cast(K, feature_major=False)
+    L = (torch.nn.functional.normalize(K, dim=1) @ protos.t()).contiguous()
+    lab16 = ops.hard_labels(L, C)
+    ref_lab = L.argmax(1)
+    lab_ok = bool((lab16[:Nk].long() == ref_lab).all()) and bool((lab16[Nk:] == -1).all())
+    bank = ops.hard_bank_layout(lab16[:Nk], C).gather(Kn)
+    Vt = ops.values_prepare(L, C)
+    torch.cuda.synchronize()
+    W = torch.exp(beta * (Qn.float() @ Kn.float().t() - 1.0))
+    O_ref = W @ torch.nn.functional.one_hot(ref_lab, C).float()
+    t0 = time.time()
+    O = ops.attn_fwd_hard(Qn, bank, beta, splits=splits)
+    torch.cuda.synchronize()
+    el = time.time() - t0
+    O_dense = ops.attn_fwd(Qn, Kn, Vt, Nk, C, beta, splits=splits)
+    torch.cuda.synchronize()
+    denom = O_ref.abs().max().item() + 1e-30
+    e_ref = (O - O_ref).abs().max().item() / denom
+    e_dense = (O - O_dense).abs().max().item() / denom
+    bad = (not lab_ok) or e_ref > 2e-2 or e_dense > 2e-3
+    print(f"attn_hard[{dt}] Nq={Nq} Nk={Nk} D={D} C={C} beta={beta} splits={splits}: labels={lab_ok} "
+          f"rel_err_vs_fp32={e_ref:.3e} rel_diff_vs_dense_kernel={e_dense:.3e} t={el * 1e3:.1f}ms {'FAIL' if bad else 'OK'}")
+    if bad:
+        e = (O - O_ref).abs()
+        print("  worst rows", e.max(1).values.topk(min(8, Nq)).indices.tolist(), "worst cols", e.max(0).values.topk(min(8, C)).indices.tolist())
+        print("  O  [0,:8]", O[0, :8].tolist())
+        print("  ref[0,:8]", O_ref[0, :8].tolist())
+    return 1 if bad else 0
+
+
 def case_norm():
     import torch
     from summer_clip_b200 import ops
@@ -187,6 +225,16 @@ def case_misc():
     return rc
 
 
+ATTN_HARD_CASES = [
+    # Nq, Nk, D, C, beta, splits  (C > 256: the hard-label kernel needs 2 or 4k class slices)
+    (128, 128, 64, 512, 5.5, 1),
+    (128, 512, 128, 1000, 5.5, 1),
+    (200, 1000, 1024, 397, 5.5, 1),
+    (300, 5000, 512, 1000, 1.0, 3),
+    (1000, 20000, 768, 1000, 11.5, 0),
+    (130, 700, 192, 1000, 3.0, 1),
+]
+
 ATTN_CASES = [
     # Nq, Nk, D, C, beta, splits, identity_v
     (128, 128, 64, 128, 5.5, 1, True),
@@ -210,8 +258,24 @@ def main(argv):
             for dt in ("fp16", "bf16"):
                 r = subprocess.run(["timeout", "120", sys.executable, me, "attn", *map(str, c[:6]), str(int(c[6])), dt])
                 rc |= (r.returncode != 0)
+        for c in ATTN_HARD_CASES:
+            for dt in ("fp16", "bf16"):
+                r = subprocess.run(["timeout", "120", sys.executable, me, "attnh", *map(str, c), dt])
+                rc |= (r.returncode != 0)
         print("ALL", "OK" if rc == 0 else "FAIL")
         return rc
+    if argv[0] == "hard":
+        rc = 0
+        me = os.path.abspath(__file__)
+        for c in ATTN_HARD_CASES:
+            for dt in ("fp16", "bf16"):
+                r = subprocess.run(["timeout", "120", sys.executable, me, "attnh", *map(str, c), dt])
+                rc |= (r.returncode != 0)
+        print("HARD", "OK" if rc == 0 else "FAIL")
+        return rc
+    if argv[0] == "attnh":
+        Nq, Nk, D, C = map(int, argv[1:5])
+        return case_attn_hard(Nq, Nk, D, C, float(argv[5]), int(argv[6]), argv[7] if len(argv) > 7 else "fp16")
     if argv[0] == "attn":
         Nq, Nk, D, C = map(int, argv[1:5])
         return case_attn(Nq, Nk, D, C, float(argv[5]), int(argv[6]), bool(int(argv[7])) if len(argv) > 7 else False,
