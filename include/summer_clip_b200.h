@@ -123,18 +123,20 @@ int sc_hard_labels(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, c
 /* sc_attn_fwd for one-hot cache values on a LABEL-SORTED key bank (same result as sc_attn_fwd on
  * Vt = one_hot(label)^T; the sum over keys does not depend on their order):
  *     O[s, q, c] = sum_{k in split s, class(k) == c} exp(beta * (Qn[q].Ks[k] - 1)),   c < n_classes.
- * The caller permutes the normalised bank once so that keys of one class are adjacent and every class
- * segment starts on a 16-key boundary (padding rows: anything finite, e.g. zeros):
- *   Ks          [Nks, D_pad]                 the permuted, padded bank (op_dtype);
- *   group_class int16 [ceil(Nks/128) * 8]    class of every 16-key group, -1 = no real key in it;
- *   key_valid   uint8 [ceil(Nks/128) * 128]  1 = real key, 0 = padding (its weight is forced to 0).
- * GEMM-2 still runs as dense tensor-core tiles, but every 16-key step has a single non-zero class row, read
- * from a static shared-memory zone (nothing is streamed for the values: 40 % fewer operand bytes per pass),
- * and the all-zero tiles of the other class slices are skipped (exact).  Needs
- * sc_attn_hard_supported(n_classes) != 0 (more than 256 classes, <= 32767); otherwise build Vt with
- * sc_values_prepare and call sc_attn_fwd. */
+ * With one-hot values W @ V is a per-class segmented row sum of the weights.  The caller permutes the
+ * normalised bank once so that keys of one class are adjacent and every class segment starts on a 16-key
+ * boundary (padding rows: anything finite, e.g. zeros):
+ *   Ks          [Nks, D_pad]                  the permuted, padded bank (op_dtype);
+ *   group_class int16  [ceil(Nks/256) * 16]   class of every 16-key group, -1 = no real key in it;
+ *   key_bits    uint32 [ceil(Nks/256) * 8]    bit j of word w = 1 iff sorted key 32 w + j is a real key
+ *                                             (padding keys get weight 0).
+ * GEMM-1 (Q.K^T) runs as 256 x 256 CTA-pair tensor-core tiles; the exponentials are summed per class straight
+ * out of tensor memory in fp32 — the weights are never rounded, stored or exchanged.  O is fp32
+ * [splits, Nq, ldo]; the library zeroes it and writes only the classes each split meets (sum the splits with
+ * sc_merge_partials).  splits = 0: the library chooses (sc_attn_hard_splits).  Any n_classes <= 32767. */
 int sc_attn_hard_supported(int64_t n_classes);
-int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint8_t* key_valid,
+int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count);
+int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                      int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta,
                      int splits, float* O, int64_t ldo, void* stream);
 

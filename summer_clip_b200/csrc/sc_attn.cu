@@ -34,11 +34,11 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
                   const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk, int64_t D_pad,
                   int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices, float beta,
                   int splits, float* O, int64_t ldo, cudaStream_t st);
-// sc_attn_ts.cu
-int attn_ts_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
-                   const void* Qn, const void* Kn, const int16_t* gcls, const uint8_t* kvalid, bool f16, int64_t Nq, int64_t Nk,
-                   int64_t D_pad, int64_t n_cols, int slice, int64_t n_slices, float beta, int splits, float* O,
-                   int64_t ldo, cudaStream_t st);
+// sc_attn_seg.cu
+int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count);
+int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
+                    int64_t Nks, int64_t D_pad, float beta, int splits, float* O, int64_t ldo, cudaStream_t st);
 }  // namespace sc
 
 namespace {
@@ -488,41 +488,36 @@ int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count) {
 
 int64_t sc_pad_labels(int64_t Nk) { return sc::round_up(Nk > 0 ? Nk : 1, kBN); }
 
-int sc_attn_hard_supported(int64_t n_classes) {
-  if (n_classes <= 0 || n_classes > 32767) return 0;
-  const int64_t n_slices = n_class_slices(sc_pad_classes(n_classes));
-  return (n_slices == 2 || n_slices % 4 == 0) ? 1 : 0;
-}
+int sc_attn_hard_supported(int64_t n_classes) { return (n_classes > 0 && n_classes <= 32767) ? 1 : 0; }
 
-int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint8_t* key_valid,
+int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count) { return sc::attn_seg_splits(Nq, Nks, sm_count); }
+
+int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                      int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta, int splits,
                      float* O, int64_t ldo, void* stream) {
-  SC_REQUIRE(Qn && Ks && group_class && key_valid && O, SC_EINVAL, "sc_attn_fwd_hard: null pointer");
+  SC_REQUIRE(Qn && Ks && group_class && key_bits && O, SC_EINVAL, "sc_attn_fwd_hard: null pointer");
   SC_REQUIRE(op_dtype == SC_F16 || op_dtype == SC_BF16, SC_EINVAL, "sc_attn_fwd_hard: op_dtype must be SC_F16 or SC_BF16");
   SC_REQUIRE(Nq > 0 && Nks > 0 && n_classes > 0, SC_ESHAPE, "sc_attn_fwd_hard: empty problem");
-  SC_REQUIRE(sc_attn_hard_supported(n_classes), SC_EUNSUPPORTED,
-             "sc_attn_fwd_hard: %lld classes do not fill 2 or 4k class slices (use sc_attn_fwd)", (long long)n_classes);
+  SC_REQUIRE(sc_attn_hard_supported(n_classes), SC_EUNSUPPORTED, "sc_attn_fwd_hard: n_classes=%lld exceeds int16 labels",
+             (long long)n_classes);
   SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_attn_fwd_hard: D_pad=%lld must be a multiple of 64",
              (long long)D_pad);
   SC_REQUIRE(ldo >= n_classes, SC_ESHAPE, "sc_attn_fwd_hard: ldo < n_classes");
-  SC_REQUIRE((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(Ks)) % 16 == 0 &&
-                 reinterpret_cast<uintptr_t>(group_class) % 2 == 0,
-             SC_EALIGN, "sc_attn_fwd_hard: Qn/Ks must be 16-byte aligned");
-  SC_REQUIRE(Nq < (1ll << 31) && Nks < (1ll << 31) - 256, SC_ESHAPE, "sc_attn_fwd_hard: Nq/Nks exceed int32 coordinates");
-  const int64_t C_pad = sc_pad_classes(n_classes);
-  const int slice = class_slice(C_pad);
-  const int64_t n_slices = n_class_slices(C_pad);
-  const int64_t tiles_total = sc::ceil_div(Nks, kBN);
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(Ks) |
+              reinterpret_cast<uintptr_t>(group_class) | reinterpret_cast<uintptr_t>(key_bits)) % 32 == 0,
+             SC_EALIGN, "sc_attn_fwd_hard: Qn, Ks, group_class and key_bits must be 32-byte aligned");
+  SC_REQUIRE(Nq < (1ll << 31) && Nks < (1ll << 31) - 512, SC_ESHAPE, "sc_attn_fwd_hard: Nq/Nks exceed int32 coordinates");
+  const int64_t steps_total = sc::ceil_div(Nks, 256);
   if (splits <= 0) {
     int dev = 0, sms = 148;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    splits = sc_attn_splits(Nq, Nks, C_pad, sms);
+    splits = sc::attn_seg_splits(Nq, Nks, sms);
   }
-  SC_REQUIRE(splits <= tiles_total && splits <= 65535, SC_ESHAPE,
-             "sc_attn_fwd_hard: splits=%d exceeds the %lld key tiles", splits, (long long)tiles_total);
-  int rc = sc::attn_ts_launch(&make_tmap, Qn, Ks, group_class, key_valid, op_dtype == SC_F16, Nq, Nks, D_pad,
-                              n_classes, slice, n_slices, beta, splits, O, ldo, static_cast<cudaStream_t>(stream));
+  SC_REQUIRE(splits <= steps_total && splits <= 65535, SC_ESHAPE,
+             "sc_attn_fwd_hard: splits=%d exceeds the %lld key steps", splits, (long long)steps_total);
+  int rc = sc::attn_seg_launch(&make_tmap, Qn, Ks, group_class, key_bits, op_dtype == SC_F16, Nq, Nks, D_pad, beta,
+                               splits, O, ldo, static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());
   return SC_OK;

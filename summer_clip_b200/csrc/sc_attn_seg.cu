@@ -1,0 +1,382 @@
+// Segmented hard-label attention kernel ("SEG") on a LABEL-SORTED key bank.
+//
+// Reference lines: cache_weights_strategy.py:33-36 (A = Q^T K, W = exp(-beta (1 - A))) + image_attention.py:109
+// (O = W @ V) for the one-hot cache values of HardCacheStrategy (cache_value_strategy.py:14-17), of
+// cache.replace_outs_with_golds (image_attention.py:65-66) and of Tip-Adapter (tip_adapter/utils.py:62,114-116).
+// With V = one_hot(label),  O[q, c] = sum_{k: label(k) = c} exp(beta (q.k - 1))  — a per-class SEGMENTED ROW SUM
+// of the weight matrix.  The sum over keys is order-free, so the host sorts the bank by label once (class
+// segments padded to whole 16-key groups, sc_attn_fwd_hard's contract) and the kernel becomes:
+//   GEMM-1  S[256 q x 256 keys] = Qn_tile . Ks_tile^T   one CTA pair, tcgen05.mma cta_group::2, M = 256 (128
+//           queries per CTA), N = 256 (128 keys per CTA: the pair shares B), K = 16 x (D / 16); operands
+//           TMA-staged through a 7-stage x 32 KB ring (Q chunk 16 KB + K chunk 16 KB per CTA), accumulators in
+//           TMEM: two [128 lanes x 256 columns] fp32 buffers = all 512 columns, double buffered against
+//   exp+sum four warps: thread = query (TMEM lane); tcgen05.ld 32 columns at a time, P = exp2(c1 S + c0) in
+//           fp32, running sum per class in a register; when the (warp-uniform) class of a 16-key group changes
+//           the finished sum is stored to O[q, class].  Padding keys are masked by a per-key bit.
+// Nothing else touches memory: the weights are never rounded to 16 bits, never written to shared memory, never
+// exchanged between CTAs, and there is no O accumulator in TMEM — which is what frees TMEM for N = 256 tiles
+// (64 B/cycle/SM of operand traffic instead of 96 for N = 128) and shared memory for a ring deep enough to
+// cover the ~2500-cycle release -> TMA -> full turnaround measured on B200 (tools/ubench).  Clusters are CTA
+// pairs, so all 148 SMs are used (4-CTA clusters strand 16).  The dense-values kernel (sc_attn_t.cu) remains the
+// path for soft cache values.
+#include "sc_common.cuh"
+#include "sc_ptx.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
+
+namespace {
+
+using namespace scptx;
+
+constexpr int kBQ = 128;             // queries per CTA (its half of UMMA M = 256)
+constexpr int kBKeys = 128;          // keys per CTA per step (its half of UMMA N = 256)
+constexpr int kStepKeys = 256;       // keys per pair step
+constexpr int kBK = 64;              // 16-bit elements per swizzled smem row
+constexpr int kStage = 32768;        // Q chunk [128 x 64] 16 KB + K chunk [128 x 64] 16 KB
+constexpr int kNS = 7;               // ring stages: 224 KB
+constexpr int kThreads = 192;        // warps 0-3 exp+sum (TMEM lane quadrant = warp), 4 TMA producer, 5 MMA issuer
+constexpr int kProducerWarp = 4;
+constexpr int kMmaWarp = 5;
+constexpr int kTmemCols = 512;       // S0 @0, S1 @256
+constexpr int kSmemBytes = kNS * kStage + 1024 + 256;
+
+struct SParams {
+  int Nq;
+  int n_dchunks;
+  int steps_total;           // ceil(Nks / 256)
+  int splits;
+  int pf_dist;               // L2 prefetch distance in steps (0 = off)
+  int dbg;                   // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit0/2 skip Q/K loads, 3 exp, 4 MMAs
+  float c1, c0;
+  const int16_t* gcls;       // class of every 16-key group, [steps_total * 16]; -1 = no real key
+  const uint32_t* kbits;     // validity bit per key, [steps_total * 8] words (bit j of word w = key 32 w + j)
+  float* O;                  // [splits, Nq, ldo], zeroed by the launcher; only the classes met are written
+  long long ldo;
+  unsigned long long* clk;   // experiments builds: {sum of CTA cycles, sum of CTA ns, CTAs}
+};
+
+struct Bars {
+  uint64_t full[8];          // leader: TMA bytes of BOTH CTAs landed
+  uint64_t empty[8];         // both: pair MMAs reading the stage retired
+  uint64_t s_full[2];        // both: S buffer complete
+  uint64_t s_empty[2];       // leader: 8 warp arrivals (4 per CTA): S buffer drained
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool kF16>
+__global__ void __launch_bounds__(kThreads, 1)
+sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const SParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t ring0 = (raw_addr + 1023u) & ~1023u;
+  Bars* bars = reinterpret_cast<Bars*>(smem_raw + (ring0 - raw_addr) + kNS * kStage);
+
+  // warp index through a shuffle: provably warp-uniform for the compiler (role loops live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the pair UMMAs), 1 = peer
+  const bool is_leader = (rank == 0);
+  const uint16_t pair_mask = 3;
+
+  const int q0 = (blockIdx.y * 2 + static_cast<int>(rank)) * kBQ;      // my 128 queries
+  const int split = blockIdx.z;
+  const int s0 = static_cast<int>((static_cast<long long>(p.steps_total) * split) / p.splits);
+  const int s1 = static_cast<int>((static_cast<long long>(p.steps_total) * (split + 1)) / p.splits);
+  const int nsteps = s1 - s0;
+  const int nd = p.n_dchunks;
+
+#ifdef SC_ATTN_TIMING_EXPERIMENTS
+  long long clk_c0 = 0;
+  unsigned long long clk_t0 = 0;
+  if (p.clk != nullptr && threadIdx.x == 0) {
+    clk_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(clk_t0));
+  }
+#endif
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars->s_full[b]), 1);
+      mbar_init(smem_u32(&bars->s_empty[b]), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc2(smem_u32(&bars->tmem_slot), kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ===================================================== TMA producer (both CTAs; warp-uniform, elected issue)
+    int stage = 0;
+    uint32_t phase = 0, ready = 0;
+    const uint32_t full0 = smem_u32(&bars->full[0]);
+    const uint32_t full0c = mapa(full0, 0);
+    const uint32_t empty0 = smem_u32(&bars->empty[0]);
+    const uint32_t kon = (p.dbg & 4) ? 0u : 1u, qon = (p.dbg & 1) ? 0u : 1u;
+    const uint32_t tx = is_leader ? 2u * 16384u * (kon + qon) : 0u;       // both CTAs' bytes
+    const uint32_t plain = (is_leader && tx == 0u) ? 1u : 0u;
+#pragma unroll 1
+    for (int st = 0; st < nsteps; ++st) {
+      const int krow = (s0 + st) * kStepKeys + static_cast<int>(rank) * kBKeys;      // my 128 keys of the step
+      // L2 prefetch of the key stream: co-resident pairs walk the same key steps at about the same time, so a
+      // step's first touch pays the HBM latency for all of them; one pair in 32 (by query tile) pulls the
+      // chunks of step st + pf_dist into L2 ahead of the pack
+      if (p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
+        if (elect_one()) {
+          for (int d = 0; d < nd; ++d) tma_prefetch_2d(&tmK, d * kBK, krow + p.pf_dist * kStepKeys);
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int d = 0; d < nd; ++d) {
+        if (!ready) mbar_wait(empty0 + stage * 8, phase ^ 1u);
+        const bool wrap = (stage + 1 == kNS);
+        const uint32_t dst = ring0 + stage * kStage;
+        ready = __all_sync(0xffffffffu,
+                           tma2_cg2_probe(dst, &tmQ, d * kBK, q0, qon, dst + 16384, &tmK, d * kBK, krow, kon,
+                                          full0c + stage * 8, full0 + stage * 8, tx, plain,
+                                          empty0 + (wrap ? 0 : stage + 1) * 8, (wrap ? phase ^ 1u : phase) ^ 1u));
+        if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (is_leader) {
+      // ===================================================== MMA issuer for the pair
+      int stage = 0;
+      uint32_t phase = 0, ready = 0;
+      const uint32_t idesc = umma_idesc_16b(256, 256, kF16);
+      const uint32_t full0 = smem_u32(&bars->full[0]);
+      const uint32_t empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t en = (p.dbg & 16) ? 0u : 1u;
+#pragma unroll 1
+      for (int st = 0; st < nsteps; ++st) {
+        const int sb = st & 1;
+        mbar_wait(smem_u32(&bars->s_empty[sb]), ((st >> 1) & 1) ^ 1u);
+        const uint32_t tmem_s = tmem_base + sb * 256;
+        const uint32_t sfull = smem_u32(&bars->s_full[sb]);
+#pragma unroll 1
+        for (int d = 0; d < nd; ++d) {
+          if (!ready) mbar_wait(full0 + stage * 8, phase);
+          tc_fence_after();
+          const bool wrap = (stage + 1 == kNS);
+          const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage);             // Q chunk: my 128 queries
+          const uint64_t b_desc = umma_desc_k128(ring0 + stage * kStage + 16384);     // K chunk: my 128 keys
+          ready = __all_sync(0xffffffffu,
+                             umma4_cg2_probe(tmem_s, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc, b_desc + 2,
+                                             b_desc + 4, b_desc + 6, idesc, d != 0 ? 1u : 0u, en, empty0 + stage * 8,
+                                             pair_mask, sfull, pair_mask, d == nd - 1 ? 1u : 0u,
+                                             full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
+          if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+        }
+      }
+    }
+  } else {
+    // ===================================================== exp + segmented sum warps: thread = query
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const float c1 = p.c1, cadd = p.c0;
+    const int q = q0 + row;
+    float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;
+    const bool q_ok = q < p.Nq;
+    int cur = -1;          // class of the running sum (warp-uniform)
+    float acc = 0.f;
+#pragma unroll 1
+    for (int st = 0; st < nsteps; ++st) {
+      const int b = st & 1;
+      // classes of the 16 groups and validity bits of the 256 keys of this step (uniform loads, issued before the wait)
+      const uint4* gp = reinterpret_cast<const uint4*>(p.gcls + static_cast<long long>(s0 + st) * 16);
+      const uint4 ga = __ldg(gp), gb = __ldg(gp + 1);
+      const uint4* kp = reinterpret_cast<const uint4*>(p.kbits + static_cast<long long>(s0 + st) * 8);
+      const uint4 ka = __ldg(kp), kb = __ldg(kp + 1);
+      const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};      // 2 classes per word
+      const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};      // 32 keys per word
+      mbar_wait(smem_u32(&bars->s_full[b]), (st >> 1) & 1);
+      tc_fence_after();
+      // 32 columns (two 16-key groups) per TMEM load, double buffered: the load of chunk cc+1 is in flight
+      // while chunk cc is exponentiated and summed
+      auto consume = [&](const uint32_t (&rg)[32], int cc) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cls = static_cast<int>(static_cast<int16_t>((gw[cc] >> (16 * hh)) & 0xffffu));
+          const uint32_t bits = (kw[cc] >> (16 * hh)) & 0xffffu;
+          if (cls != cur) {                              // warp-uniform: the finished class sum goes out
+            if (cur >= 0 && q_ok) orow[cur] = acc;
+            cur = cls;
+            acc = 0.f;
+          }
+          float s = 0.f;
+          if (bits == 0xffffu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s += ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1, cadd));
+          } else if (bits != 0u) {                       // a class segment's last group: padding keys weigh 0
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e = ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1, cadd));
+              s += ((bits >> j) & 1u) ? e : 0.f;
+            }
+          }
+          acc += s;
+        }
+      };
+      if (!(p.dbg & 8)) {
+        const uint32_t tcol = tmem_base + lane_addr + b * 256;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tcol, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < kStepKeys / 32; cc += 2) {
+          tmem_ld_32x32(tcol + (cc + 1) * 32, rb);
+          consume(ra, cc);
+          tmem_ld_wait();
+          if (cc + 2 < kStepKeys / 32) tmem_ld_32x32(tcol + (cc + 2) * 32, ra);
+          consume(rb, cc + 1);
+          tmem_ld_wait();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+        else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), 0);
+      }
+    }
+    if (cur >= 0 && q_ok) orow[cur] = acc;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+#ifdef SC_ATTN_TIMING_EXPERIMENTS
+  if (p.clk != nullptr && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicAdd(p.clk, static_cast<unsigned long long>(clock64() - clk_c0));
+    atomicAdd(p.clk + 1, t1 - clk_t0);
+    atomicAdd(p.clk + 2, 1ull);
+  }
+#endif
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+template <bool kF16>
+int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const SParams& p) {
+  auto kernel = sc_attn_seg_kernel<kF16>;
+  SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmQ, tmK, p));
+  return SC_OK;
+}
+
+#ifdef SC_ATTN_TIMING_EXPERIMENTS
+unsigned long long* g_clk = nullptr;
+#endif
+
+}  // namespace
+
+#ifdef SC_ATTN_TIMING_EXPERIMENTS
+// experiments builds only: effective SM clock seen by the hard-label attention CTAs since the last call
+extern "C" double sc_debug_attn_hard_clock_mhz(void) {
+  if (g_clk == nullptr) return 0.0;
+  unsigned long long h[3] = {0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_clk, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaMemset(g_clk, 0, sizeof(h));
+  return h[1] ? 1e3 * static_cast<double>(h[0]) / static_cast<double>(h[1]) : 0.0;
+}
+#endif
+
+namespace sc {
+
+// key splits for the pair kernel: work items = query tiles (256 queries) x splits over sm_count / 2 pairs
+int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count) {
+  if (Nq <= 0 || Nks <= 0) return 1;
+  if (sm_count <= 0) sm_count = 148;
+  const int64_t pairs = sm_count / 2 > 0 ? sm_count / 2 : 1;
+  const int64_t base = ceil_div(Nq, 2 * kBQ);
+  const int64_t steps = ceil_div(Nks, kStepKeys);
+  int best = 1;
+  double best_cost = 1e300;
+  const int64_t smax = steps < 128 ? steps : 128;
+  for (int64_t s = 1; s <= smax; ++s) {
+    const double waves = static_cast<double>(ceil_div(base * s, pairs));
+    const double cost = waves * (static_cast<double>(ceil_div(steps, s)) + 1.5);
+    if (cost < best_cost * 0.995) { best_cost = cost; best = static_cast<int>(s); }
+  }
+  return best;
+}
+
+// Called by sc_attn_fwd_hard (sc_attn.cu) after argument validation.  O [splits, Nq, ldo] is zeroed here.
+int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
+                    int64_t Nks, int64_t D_pad, float beta, int splits, float* O, int64_t ldo, cudaStream_t st) {
+  CUtensorMap tmQ, tmK;
+  int rc;
+  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
+  if ((rc = make_tmap(&tmK, Ks, Nks, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;    // 128 keys x 64 d
+  SParams p;
+  p.Nq = static_cast<int>(Nq);
+  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.steps_total = static_cast<int>(ceil_div(Nks, kStepKeys));
+  p.splits = splits;
+  p.c1 = beta * 1.4426950408889634f;
+  p.c0 = -p.c1;
+  p.gcls = gcls;
+  p.kbits = kbits;
+  p.O = O;
+  p.ldo = ldo;
+  p.dbg = 0;
+  p.clk = nullptr;
+  p.pf_dist = 2;
+  if (const char* env = std::getenv("SC_ATTN_PREFETCH")) {      // tuning knob: L2 prefetch distance (steps)
+    const int want = std::atoi(env);
+    if (want >= 0 && want <= 64) p.pf_dist = want;
+  }
+#ifdef SC_ATTN_TIMING_EXPERIMENTS   // never in the shipped library: skipping work gives wrong results
+  if (const char* env = std::getenv("SC_ATTN_DEBUG_SKIP")) p.dbg = std::atoi(env);
+  if (std::getenv("SC_ATTN_CLKPROBE")) {
+    if (g_clk == nullptr) {
+      SC_CUDA(cudaMalloc(&g_clk, 3 * sizeof(unsigned long long)));
+      SC_CUDA(cudaMemset(g_clk, 0, 3 * sizeof(unsigned long long)));
+    }
+    p.clk = g_clk;
+  }
+#endif
+  SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(splits) * Nq * ldo * sizeof(float), st));
+  dim3 grid(2u, static_cast<unsigned>(ceil_div(Nq, 2 * kBQ)), static_cast<unsigned>(splits));
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd_hard: too many query tiles; chunk the queries");
+  return f16 ? launch_seg<true>(grid, st, tmQ, tmK, p) : launch_seg<false>(grid, st, tmQ, tmK, p);
+}
+
+}  // namespace sc

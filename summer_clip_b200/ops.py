@@ -208,11 +208,12 @@ def hard_labels(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torch.T
 class HardBank:
     """Label-sorted key bank for sc_attn_fwd_hard: keys of one class adjacent, every class segment padded to
     whole 16-key groups.  `perm[j]` = original index of sorted key j (-1 = padding), `gcls` int16 class per
-    16-key group, `kvalid` uint8 per key; `rows` (set by `gather`) = the permuted normalised bank."""
+    16-key group, `kbits` one validity bit per key (uint32 words stored as int32); `rows` (set by `gather`) =
+    the permuted normalised bank."""
 
-    def __init__(self, perm: torch.Tensor, gcls: torch.Tensor, kvalid: torch.Tensor, n_sorted: int, n_keys: int,
+    def __init__(self, perm: torch.Tensor, gcls: torch.Tensor, kbits: torch.Tensor, n_sorted: int, n_keys: int,
                  n_classes: int) -> None:
-        self.perm, self.gcls, self.kvalid = perm, gcls, kvalid
+        self.perm, self.gcls, self.kbits = perm, gcls, kbits
         self.n_sorted, self.n_keys, self.n_classes = int(n_sorted), int(n_keys), int(n_classes)
         self.rows: Optional[torch.Tensor] = None
 
@@ -227,7 +228,7 @@ class HardBank:
 
 def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
     """Index plumbing of the sorted bank (once per cache): stable sort of the keys by label, class segments
-    padded to multiples of 16, the whole bank padded to whole 128-key tiles.  Labels outside [0, n_classes)
+    padded to multiples of 16, the whole bank padded to whole 256-key steps.  Labels outside [0, n_classes)
     select no class and are dropped (their one-hot row is zero)."""
     _cuda(labels, "labels")
     dev = labels.device
@@ -244,13 +245,14 @@ def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
     order_v = order[:n_valid]
     lab_sorted = lab_v[order_v]
     dest = seg_start[lab_sorted] + (torch.arange(n_valid, device=dev) - cls_start[lab_sorted])
-    tiles = max(1, -(-n_sorted // 128))
-    perm = torch.full((tiles * 128,), -1, dtype=torch.int64, device=dev)
+    steps = max(1, -(-n_sorted // 256))
+    perm = torch.full((steps * 256,), -1, dtype=torch.int64, device=dev)
     perm[dest] = order_v
-    gcls = torch.full((tiles * 8,), -1, dtype=torch.int16, device=dev)
+    gcls = torch.full((steps * 16,), -1, dtype=torch.int16, device=dev)
     gcls[dest // 16] = lab_sorted.to(torch.int16)
-    kvalid = (perm >= 0).to(torch.uint8)
-    return HardBank(perm, gcls, kvalid, n_sorted, n_keys, n_classes)
+    words = ((perm >= 0).view(-1, 32).to(torch.int64) << torch.arange(32, device=dev)).sum(1)
+    kbits = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return HardBank(perm, gcls, kbits, n_sorted, n_keys, n_classes)
 
 
 def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0, merge: bool = True) -> torch.Tensor:
@@ -265,10 +267,10 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     n_classes = bank.n_classes
     n_sorted = max(bank.n_sorted, 1)
     if splits <= 0:
-        splits = attn_splits(Nq, n_sorted, pad_classes(n_classes), Qn.device)
-    O = torch.empty((splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)
+        splits = attn_hard_splits(Nq, n_sorted, Qn.device)
+    O = torch.empty((splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)      # zeroed by the library
     with torch.cuda.device(Qn.device):
-        check(_lib.load().sc_attn_fwd_hard(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kvalid), _code(Qn), Nq,
+        check(_lib.load().sc_attn_fwd_hard(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kbits), _code(Qn), Nq,
                                            n_sorted, D_pad, n_classes, float(beta), splits, _ptr(O), n_classes,
                                            _stream()), "sc_attn_fwd_hard")
     if not merge:
@@ -276,6 +278,11 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     if splits == 1:
         return O[0]
     return merge_partials(O)
+
+
+def attn_hard_splits(Nq: int, Nks: int, device=None) -> int:
+    sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
+    return int(_lib.load().sc_attn_hard_splits(Nq, Nks, sms))
 
 
 def attn_splits(Nq: int, Nk: int, C_pad: int, device=None) -> int:

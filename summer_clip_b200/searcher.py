@@ -93,8 +93,8 @@ class ClipSearcher:
         local_labels = labels.to(self.device)[lo:hi] if labels is not None else None
         self.rowsum_col = None
         if softmax_scale is None and not softmax_normalize and ops.hard_supported(self.n_classes):
-            # one-hot values: sort the keys by label once; GEMM-2 then reads its operand from a static on-chip
-            # zone and skips the all-zero class tiles (sc_attn_fwd_hard)
+            # one-hot values: W @ V is a per-class segmented row sum; sort the keys by label once and let the
+            # kernel sum the exponentials per class straight out of tensor memory (sc_attn_fwd_hard)
             labels16 = ops.hard_labels(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
                                        labels=local_labels)
             self.hard_bank = ops.hard_bank_layout(labels16[: self.n_keys], self.n_classes).gather(self.k_norm)
@@ -125,12 +125,13 @@ class ClipSearcher:
         n_cols = self.n_classes + (1 if self.rowsum_col is not None else 0)
         nq = qn.shape[0]
         if self.n_keys > 0:
-            c_pad = self.vt.shape[0] if self.vt is not None else ops.pad_classes(self.n_classes)
-            if splits <= 0:
-                splits = ops.attn_splits(nq, self.n_keys, c_pad, self.device)
             if self.hard_bank is not None:
+                if splits <= 0:
+                    splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device)
                 part = ops.attn_fwd_hard(qn, self.hard_bank, beta, splits=splits)
             else:
+                if splits <= 0:
+                    splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
                 part = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, n_cols, beta, splits=splits, merge=True)
             self.gpu_launches += 1 + int(splits > 1)
         else:

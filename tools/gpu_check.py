@@ -233,6 +233,9 @@ ATTN_HARD_CASES = [
     (300, 5000, 512, 1000, 1.0, 3),
     (1000, 20000, 768, 1000, 11.5, 0),
     (130, 700, 192, 1000, 3.0, 1),
+    (257, 300, 64, 37, 5.5, 1),
+    (513, 4099, 320, 100, 2.0, 0),
+    (64, 40000, 1024, 1000, 5.5, 0),
 ]
 
 ATTN_CASES = [
