@@ -229,8 +229,8 @@ class HardBank:
 def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
     """Index plumbing of the sorted bank (once per cache): stable sort of the keys by label, class segments
     padded to multiples of 16, the whole bank padded to whole 256-key steps.  Labels outside [0, n_classes)
-    select no class and are dropped (their one-hot row is zero)."""
-    _cuda(labels, "labels")
+    select no class and are dropped (their one-hot row is zero).  Pure index arithmetic: also runs on CPU
+    tensors (tests); the bank it describes is consumed by the CUDA kernel only."""
     dev = labels.device
     lab = labels.reshape(-1).to(torch.int64)
     n_keys = lab.numel()

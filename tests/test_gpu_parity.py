@@ -312,6 +312,66 @@ def test_tiny_and_degenerate_shapes(ops):
         torch.testing.assert_close(O.cpu(), ref, rtol=0, atol=2e-3 * max(1.0, ref.abs().max().item()))
 
 
+# ----------------------------------------------------------------------------- one-hot values: segmented kernel
+@pytest.mark.parametrize("shape", [(1, 1, 64, 1), (3, 2, 100, 7), (128, 256, 64, 16), (129, 257, 192, 257),
+                                   (300, 5000, 512, 1000), (513, 4099, 320, 100), (130, 700, 192, 37)])
+def test_hard_label_segmented_kernel(ops, shape):
+    """sc_attn_fwd_hard on a label-sorted bank == W @ one_hot(labels): against fp32 on the same rounded operands,
+    against the dense-values kernel, with invalid labels (dropped), absent classes (zero columns), every
+    split count, and beta = 0 counting keys exactly."""
+    nq, nk, dim, c = shape
+    g = torch.Generator().manual_seed(81)
+    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
+    labels = torch.randint(0, max(1, c - c // 4), (nk,), generator=g).int()       # top quarter of the classes is absent
+    if nk > 10:
+        labels[torch.randperm(nk, generator=g)[: nk // 10]] = -1                  # invalid labels select no class
+    labels = labels.cuda()
+    bank = ops.hard_bank_layout(labels, c).gather(Kn)
+    valid = labels >= 0
+    assert bank.n_sorted % 16 == 0 and int((bank.perm >= 0).sum()) == int(valid.sum())
+    W = torch.exp(3.0 * (Qn.float() @ Kn.float().t() - 1.0))
+    ref = torch.zeros(nq, c, device="cuda").index_add_(1, labels[valid].long(), W[:, valid])
+    steps = -(-bank.n_sorted // 256)
+    for splits in sorted({1, min(3, steps), min(7, steps), 0}):
+        O = ops.attn_fwd_hard(Qn, bank, 3.0, splits=splits)
+        assert O.shape == (nq, c)
+        torch.testing.assert_close(O, ref, rtol=2e-5, atol=1e-6 * max(1.0, ref.max().item()))
+    parts = ops.attn_fwd_hard(Qn, bank, 3.0, splits=min(3, steps), merge=False)
+    assert parts.shape[0] == min(3, steps) and float(parts[:, :, c - c // 4:].abs().sum()) == 0.0 if c >= 4 else True
+    Vt = ops.values_prepare(None, c, labels=labels)
+    dense = ops.attn_fwd(Qn, Kn, Vt, nk, c, 3.0)
+    torch.testing.assert_close(O, dense, rtol=0, atol=2e-3 * max(1.0, ref.max().item()))
+    O0 = ops.attn_fwd_hard(Qn, bank, 0.0)
+    assert torch.equal(O0, torch.bincount(labels[valid].long(), minlength=c).float().expand(nq, c))
+
+
+def test_hard_values_route_through_the_segmented_kernel(ops, monkeypatch):
+    """HardCacheStrategy / gold labels / one-hot Tip-Adapter cache values all become a label-sorted bank; the
+    dense-values route (SUMMER_CLIP_B200_DENSE_VALUES=1) gives the same logits."""
+    from summer_clip_b200.clip_searcher.cache_value_strategy import CacheValues, GoldCacheValues, HardCacheStrategy
+    from summer_clip_b200.clip_searcher.cache_weights_strategy import TipAdapterWeightsStrategy, _BANKS
+    banks = orc.synthetic_banks(300, 2000, 256, 50, seed=82, sigma=0.5, sigma_text=0.8, shared=3.0)
+    Q, K, L = (banks[n].cuda() for n in ("test_image_features", "cache_image_features", "cache_image_outs"))
+    _BANKS.clear()
+    w = TipAdapterWeightsStrategy(5.5).transform(Q, K)
+    hard = HardCacheStrategy().transform(L)
+    assert hard.is_hard and hard.shape == (2000, 50)
+    got = w @ hard
+    ref = orc.image_attention(banks["test_image_features"], banks["cache_image_features"], orc.hard_values(banks["cache_image_outs"]), 5.5)
+    assert (got.cpu() - ref).abs().max().item() / ref.abs().max().item() < 1e-3
+    gold = GoldCacheValues(50).transform(banks["cache_labels"].cuda())
+    one_hot = torch.nn.functional.one_hot(banks["cache_labels"].long(), 50).half().cuda()
+    dense_in = CacheValues.from_dense(one_hot)
+    assert gold.is_hard and dense_in.is_hard
+    torch.testing.assert_close(w @ gold, w @ dense_in, rtol=0, atol=0)
+    torch.testing.assert_close(w @ one_hot, w @ gold, rtol=0, atol=0)              # plain tensor operand, reference style
+    monkeypatch.setenv("SUMMER_CLIP_B200_DENSE_VALUES", "1")
+    dense = HardCacheStrategy().transform(L)
+    assert not dense.is_hard
+    torch.testing.assert_close(w @ dense, got, rtol=0, atol=2e-3 * got.max().item())
+
+
 def test_cpu_tensors_are_rejected(ops):
     from summer_clip_b200._lib import SummerClipError
     with pytest.raises(SummerClipError):
@@ -410,24 +470,36 @@ def test_full_size_key_bank_properties(ops, nq):
     torch.testing.assert_close(O[rows][:, :c], ref, rtol=2e-3, atol=1e-2)
     O0 = ops.attn_fwd(Qn[:128].contiguous(), Kn, Vt, nk, c + 1, 0.0)
     assert torch.all(O0[:, c] == nk)
+    # the same bank through the label-sorted segmented kernel (the bench's path for one-hot values)
+    bank = ops.hard_bank_layout(yk.int(), c).gather(Kn)
+    Oh = ops.attn_fwd_hard(Qn, bank, 5.5)
+    torch.testing.assert_close(Oh[rows], ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(Oh, O[:, :c], rtol=2e-3, atol=1e-2)
+    torch.testing.assert_close(Oh.sum(1), O[:, c], rtol=1e-3, atol=1e-3)
+    hparts = []
+    for r in range(8):
+        lo, hi = shard_range(nk, r, 8)
+        hparts.append(ops.attn_fwd_hard(Qn, ops.hard_bank_layout(yk[lo:hi].int(), c).gather(Kn[lo:hi]), 5.5))
+    torch.testing.assert_close(ops.merge_partials(torch.stack(hparts)), Oh, rtol=1e-4, atol=1e-4)
+    Oh0 = ops.attn_fwd_hard(Qn[:128].contiguous(), bank, 0.0)
+    assert torch.equal(Oh0, torch.bincount(yk, minlength=c).float().expand(128, c))
 
 
 # ----------------------------------------------------------------------------- the three attention kernels agree
 @pytest.mark.parametrize("shape", [(300, 2000, 512, 1000), (257, 900, 1024, 397), (129, 300, 128, 100)])
 def test_attention_kernel_variants_agree(ops, shape, monkeypatch):
     """SC_ATTN_IMPL selects the transposed pair kernel (default), the pair kernel or the single-CTA-MMA
-    cluster kernel; SC_ATTN_T_CHUNKS the ring-stage granularity.  Same operands -> same result up to the
-    fp32 summation order."""
+    cluster kernel.  Same operands -> same result up to the fp32 summation order."""
     nq, nk, dim, c = shape
     g = torch.Generator().manual_seed(71)
     Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
     Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
     Vt = ops.values_prepare(torch.randn(nk, c, generator=g).cuda(), c, softmax_scale=2.0)
     outs = {}
-    for name, env in (("t", {"SC_ATTN_IMPL": "t"}), ("t2", {"SC_ATTN_IMPL": "t", "SC_ATTN_T_CHUNKS": "2"}),
+    for name, env in (("t", {"SC_ATTN_IMPL": "t"}),
                       ("pair", {"SC_ATTN_IMPL": "pair"}), ("cluster", {"SC_ATTN_IMPL": "cluster"}),
                       ("cluster1", {"SC_ATTN_IMPL": "cluster", "SC_ATTN_CLUSTER": "1"})):
-        for k in ("SC_ATTN_IMPL", "SC_ATTN_T_CHUNKS", "SC_ATTN_CLUSTER"):
+        for k in ("SC_ATTN_IMPL", "SC_ATTN_CLUSTER"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -1,0 +1,36 @@
+"""Host-side index plumbing of the label-sorted key bank (ops.hard_bank_layout): runs on CPU tensors."""
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.mark.parametrize("n_keys,n_classes,seed", [(1, 1, 0), (17, 3, 1), (1000, 37, 2), (5000, 1000, 3), (300, 5, 4)])
+def test_layout_invariants(n_keys, n_classes, seed):
+    from summer_clip_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.randint(-1, n_classes + 1, (n_keys,), generator=g).int()      # -1 and n_classes are invalid
+    bank = ops.hard_bank_layout(labels, n_classes)
+    perm, gcls = bank.perm.numpy(), bank.gcls.numpy()
+    bits = bank.kbits.numpy().astype(np.int64) & 0xFFFFFFFF
+    valid = (labels >= 0) & (labels < n_classes)
+    assert perm.size % 256 == 0 and gcls.size == perm.size // 16 and bits.size == perm.size // 32
+    assert bank.n_sorted % 16 == 0 and bank.n_sorted <= perm.size and bank.n_keys == n_keys
+    real = perm[perm >= 0]
+    assert sorted(real.tolist()) == torch.nonzero(valid).flatten().tolist()       # every valid key exactly once
+    lab = labels.numpy()
+    for gi in range(gcls.size):                                                    # groups are single-class
+        members = perm[16 * gi: 16 * gi + 16]
+        members = members[members >= 0]
+        if gcls[gi] < 0:
+            assert members.size == 0
+        else:
+            assert members.size > 0 and np.all(lab[members] == gcls[gi])
+    seen = gcls[gcls >= 0]
+    assert np.all(np.diff(seen) >= 0)                                              # classes ascending: one run each
+    for c in np.unique(seen):                                                      # stable within a class
+        mem = perm[np.repeat(gcls == c, 16)]
+        mem = mem[mem >= 0]
+        assert np.all(np.diff(mem) > 0)
+    unpacked = ((bits[:, None] >> np.arange(32)[None, :]) & 1).reshape(-1).astype(bool)
+    assert np.array_equal(unpacked, perm >= 0)                                     # bit j of word w = key 32 w + j
+    assert np.all(perm[bank.n_sorted:] == -1)
