@@ -8,8 +8,9 @@ A "step" is one full pass of the hot path over the query bank: normalise/cast th
 logits, fused attention against the resident key bank, cross-split/rank merge, alpha epilogue with
 accuracy counters.  The key bank (normalised K-major keys + transposed one-hot values) is built once
 before the timed region, like the reference's loaded caches; its build time is reported separately.
-With N > 1 the KEY bank is sharded across ranks (strong scaling): NCCL all-gather of the partial O
-tiles + merge kernel.  Prints ONE JSON line on rank 0.
+With N > 1 the KEY bank is sharded across ranks (strong scaling): one NCCL reduce-scatter sums the
+partial O tiles and leaves each rank the rows of its query slice, which it finishes alone (zero-shot
+logits, epilogue); predictions are all-gathered, counters all-reduced.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -125,7 +126,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from summer_clip_b200 import build as _build, ops
-    from summer_clip_b200.searcher import ClipSearcher, shard_range
+    from summer_clip_b200.searcher import ClipSearcher, exchange_partials, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,40 +180,51 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     launches = {"n": 0}
 
+    per_q = -(-nq // world)
+
+    def finish(q_src, lab_src, o_part):
+        """Zero-shot logits + alpha epilogue.  With key-sharded ranks one reduce-scatter sums the partial tiles
+        and hands every rank ITS query slice, which it finishes alone; predictions are all-gathered and the
+        counters all-reduced (searcher.exchange_partials / ClipSearcher._search_sharded)."""
+        if world == 1:
+            z = ops.zero_shot_logits(q_src, True, searcher.text)
+            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)
+            launches["n"] += 2
+            return res["pred"], torch.stack([res["top1"], res["top5"]])
+        o_mine, lo, hi = exchange_partials(o_part, group)
+        z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text)
+        res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[lo:hi].contiguous())
+        launches["n"] += 2
+        counts = torch.stack([res["top1"], res["top5"]])
+        dist.all_reduce(counts, group=group)
+        mine = torch.zeros((1, per_q), dtype=torch.int32, device=device)
+        mine[:, : hi - lo] = res["pred"]
+        pred_all = torch.empty((world, 1, per_q), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(pred_all, mine, group=group)
+        return pred_all.permute(1, 0, 2).reshape(1, world * per_q)[:, :nq], counts
+
     def step_device(time_attn=None):
         """Inputs resident in HBM."""
         qn = ops.normalize_cast(q_bank, True)
-        z = ops.zero_shot_logits(q_bank, True, searcher.text)
         if time_attn is not None:
             time_attn[0].record(stream)
         part = attn(qn, False)
         if time_attn is not None:
             time_attn[1].record(stream)
         o = ops.merge_partials(part) if splits > 1 else part[0]
-        launches["n"] += 3 + int(splits > 1)
-        if world > 1:
-            gathered = torch.empty((world, nq, n_classes), dtype=torch.float32, device=device)
-            dist.all_gather_into_tensor(gathered, o.contiguous(), group=group)
-            o = ops.merge_partials(gathered)
-            launches["n"] += 1
-        res = ops.epilogue(z, o, [ALPHA], labels=labels_dev)
-        launches["n"] += 1
-        return res
+        launches["n"] += 2 + int(splits > 1)
+        pred, counts = finish(q_bank, labels_dev, o)
+        return {"pred": pred, "top1": counts[0], "top5": counts[1]}
 
     def step_e2e():
         """Host buffers in, host result out: H2D of the query bank, D2H of predictions + counters."""
         q_dev = q_host.to(device, non_blocking=True)
         lab = labels_host.to(device, non_blocking=True)
         qn = ops.normalize_cast(q_dev, True)
-        z = ops.zero_shot_logits(q_dev, True, searcher.text)
         o = attn(qn, True)
-        if world > 1:
-            gathered = torch.empty((world, nq, n_classes), dtype=torch.float32, device=device)
-            dist.all_gather_into_tensor(gathered, o.contiguous(), group=group)
-            o = ops.merge_partials(gathered)
-        res = ops.epilogue(z, o, [ALPHA], labels=lab)
-        pred = res["pred"].to("cpu", non_blocking=True)
-        counts = torch.stack([res["top1"], res["top5"]]).to("cpu", non_blocking=True)
+        pred, counts = finish(q_dev, lab, o)
+        pred = pred.to("cpu", non_blocking=True)
+        counts = counts.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pred, counts
 
@@ -296,7 +308,7 @@ def run_ours(args):
         "dtype": "f16" if ops.OP_DTYPE == torch.float16 else "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
                    "n_classes": n_classes, "beta": BETA, "alpha": ALPHA, "values": "hard (one-hot of argmax L)",
-                   "sharding": f"key-sharded x{world}, all-gather + sum merge" if world > 1 else "single GPU",
+                   "sharding": f"key-sharded x{world}: reduce-scatter of the partial tiles, each rank finishes its query slice" if world > 1 else "single GPU",
                    "key_splits_per_gpu": splits, "accumulate": "fp32",
                    "l2": "inputs larger than L2: key bank = %.2f GB per GPU (+ %s)" % (
                        2 * n_local * dim / 1e9, "sorted by label" if searcher.hard_bank is not None else "%.2f GB dense values" % (2 * n_local * c_pad / 1e9)),

@@ -80,6 +80,84 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
   }
 }
 
+// ---- 16-bit feature-major source with contiguous columns and no gather (the key-bank build): ONE pass over HBM.
+// Block = 32 bank columns x all D rows, 512 threads.  Phase A streams the [D x 32] strip into shared memory
+// (pitch 33 halves; 64 contiguous bytes per warp-row, 16 independent loads in flight per warp) while every
+// thread accumulates the sum of squares of its column; phase B writes the 32 output rows (one 2*D_pad-byte
+// contiguous row per column, 128 bytes per warp store) from shared memory, conflict free.  The old kernel
+// read the strip twice through a 64 x 33 tile with two block barriers per 64 rows and reached 1.5 TB/s.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(512)
+norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d, TO* __restrict__ dst,
+                  int64_t D_pad, int normalize) {
+  extern __shared__ uint16_t strip[];            // [D][33]
+  __shared__ float red[16][32];
+  __shared__ float nrm_s[32];
+  constexpr int kPitch = 33;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;             // 0..15
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const bool col_ok = n0 + lane < N;
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + n0 + lane;
+  float ss = 0.f;
+  for (int64_t d0 = warp; d0 < D; d0 += 16 * 16) {
+    uint16_t raw[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int64_t d = d0 + 16 * j;
+      raw[j] = (col_ok && d < D) ? __ldg(s16 + d * stride_d) : static_cast<uint16_t>(0);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int64_t d = d0 + 16 * j;
+      if (d < D) {
+        strip[d * kPitch + lane] = raw[j];
+        const float v = sc::to_f32<T>(*reinterpret_cast<const T*>(&raw[j]));
+        ss = fmaf(v, v, ss);
+      }
+    }
+  }
+  red[warp][lane] = ss;
+  __syncthreads();
+  if (warp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t += red[j][lane];
+    nrm_s[lane] = normalize ? sqrtf(t) : 1.0f;   // the NORM; we divide below like the reference does
+  }
+  __syncthreads();
+  // phase B: warp w writes columns w and w + 16; lane handles d = d0 + 2*lane, +1
+  for (int c = warp; c < 32; c += 16) {
+    const int64_t o = n0 + c;
+    if (o >= N) continue;
+    const float nrm = nrm_s[c];
+    TO* orow = dst + o * D_pad;
+    for (int64_t d0 = 0; d0 < D_pad; d0 += 64) {
+      const int64_t d = d0 + 2 * lane;
+      float a = 0.f, b = 0.f;
+      if (d < D) {
+        a = sc::to_f32<T>(*reinterpret_cast<const T*>(&strip[d * kPitch + c]));
+        if (normalize) a = a / nrm;
+      }
+      if (d + 1 < D) {
+        b = sc::to_f32<T>(*reinterpret_cast<const T*>(&strip[(d + 1) * kPitch + c]));
+        if (normalize) b = b / nrm;
+      }
+      *reinterpret_cast<uint32_t*>(orow + d) = sc::pack2<TO>(a, b);
+    }
+  }
+}
+
+template <typename T, typename TO>
+int launch_norm_strip(const void* src, int64_t D, int64_t N, int64_t stride_d, void* dst, int64_t D_pad, int normalize,
+                      cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(D) * 33 * 2;
+  SC_CUDA(cudaFuncSetAttribute(norm_strip_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  norm_strip_kernel<T, TO><<<static_cast<unsigned>(sc::ceil_div(N, 32)), 512, smem, st>>>(
+      static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize);
+  return SC_OK;
+}
+
 // ---- source rows are contiguous along d (stride_d == 1): one warp per output row.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
@@ -124,7 +202,15 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
   SC_REQUIRE(reinterpret_cast<uintptr_t>(dst) % 4 == 0, SC_EALIGN, "sc_normalize_cast: dst misaligned");
   if (n_out == 0) return SC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (stride_d == 1 && stride_n != 1) {
+  if (idx == nullptr && stride_n == 1 && stride_d != 1 && (src_dtype == SC_F16 || src_dtype == SC_BF16) &&
+      static_cast<size_t>(D) * 33 * 2 <= 200 * 1024) {
+    int rc = SC_OK;
+    SC_DISPATCH_OP(dst_dtype, TO, {
+      if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
+      else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
+    });
+    if (rc != SC_OK) return rc;
+  } else if (stride_d == 1 && stride_n != 1) {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 8));
     SC_DISPATCH_OP(dst_dtype, TO, {
       SC_DISPATCH_DTYPE(src_dtype, T,

@@ -27,6 +27,88 @@ __device__ __forceinline__ MaxIdx warp_argmax(MaxIdx m) {
   return m;
 }
 
+// max that PROPAGATES NaN (torch.max treats NaN as the largest value): one instruction per element, and a
+// NaN result sends the caller to the exact slow path
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
+// Register-resident row of at most 32 * NV 16-byte vectors (one warp per row).  load(): every lane issues all
+// of its 16-byte loads before the first use.  argmax(): two cheap passes over the fp32 copy in registers —
+// max.NaN for the value (1 instruction per element), then "last hit in reverse order" for the FIRST index at
+// which it occurs (2 per element) — instead of the ~20-instruction ordered compare per element of
+// sc::better(); rows that contain a NaN (the max comes back NaN) take the exact path.  Semantics are those
+// of row_argmax / torch.max(dim=1): larger value wins, NaN is largest, equal values -> smaller index.
+template <typename T, int NV>
+struct RegRow {
+  static constexpr int kN = 16 / sizeof(T);
+  uint4 v[NV];   // the raw row: kept in storage type (registers decide the occupancy that hides the HBM latency)
+  int nv;        // 16-byte vectors in the row
+  int lane;
+
+  __device__ __forceinline__ void load(const T* __restrict__ row, int nv_, int lane_) {
+    nv = nv_;
+    lane = lane_;
+    const uint4* vrow = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int j = lane + 32 * u;
+      v[u] = (j < nv) ? __ldg(vrow + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  __device__ __forceinline__ bool has(int u) const { return lane + 32 * u < nv; }
+  __device__ __forceinline__ int col(int u, int t) const { return (lane + 32 * u) * kN + t; }
+  __device__ __forceinline__ float x(int u, int t) const { return to_f32<T>(reinterpret_cast<const T*>(&v[u])[t]); }
+
+  __device__ __forceinline__ MaxIdx argmax() const {
+    float mx = __int_as_float(0xff800000);   // -inf
+#pragma unroll
+    for (int u = 0; u < NV; ++u)
+      if (has(u)) {
+#pragma unroll
+        for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (mx != mx) {                           // a NaN in the row (warp-uniform): exact ordered compare
+      MaxIdx m{0.f, -1};
+#pragma unroll
+      for (int u = 0; u < NV; ++u)
+        if (has(u)) {
+#pragma unroll
+          for (int t = 0; t < kN; ++t)
+            if (better(x(u, t), col(u, t), m)) { m.v = x(u, t); m.i = col(u, t); }
+        }
+      return warp_argmax(m);
+    }
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int u = NV - 1; u >= 0; --u)
+      if (has(u)) {
+#pragma unroll
+        for (int t = kN - 1; t >= 0; --t) idx = (x(u, t) == mx) ? col(u, t) : idx;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+    return MaxIdx{mx, idx};
+  }
+
+  // sum_c exp(scale * l_c - tmax): same terms and summation order as row_expsum (lane partials in vector
+  // order, then the xor tree)
+  __device__ __forceinline__ float expsum(float scale, float tmax) const {
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV; ++u)
+      if (has(u)) {
+#pragma unroll
+        for (int t = 0; t < kN; ++t) s += expf(__fmul_rn(x(u, t), scale) - tmax);
+      }
+    return warp_sum(s);
+  }
+};
+
 template <typename T>
 struct Vec {  // 16-byte vector of T
   static constexpr int kN = 16 / sizeof(T);

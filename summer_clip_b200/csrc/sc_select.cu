@@ -39,61 +39,39 @@ rowconf_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, float 
   }
 }
 
-// Register-resident variant for rows of at most 32 * NV 16-byte vectors (C <= 1024 fp16 / bf16 with NV = 4,
-// C <= 1024 fp32 with NV = 8) whose length is a whole number of vectors: every lane issues all of its loads
-// before the first use (NV independent 16-byte requests in flight per lane instead of one), and the PROB
-// pass sums exp() from the registers, so the row is read from memory exactly once.  Summation order of
-// the exp terms is the same as in row_expsum (lane partials in vector order, then the xor tree).
+// Register-resident variant (sc::RegRow) for rows of at most 32 * NV 16-byte vectors (C <= 1024 fp16 / bf16 with
+// NV = 4, C <= 1024 fp32 with NV = 8) whose length is a whole number of vectors: all loads of a lane are in
+// flight before the first use, the argmax costs ~4 instructions per element, and the PROB pass sums exp()
+// from the registers, so the row is read from memory exactly once.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 3)
 rowconf_reg_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, float scale, int mode,
                    float* __restrict__ conf, int32_t* __restrict__ label) {
   constexpr int kN = 16 / sizeof(T);
+  constexpr int kRows = sizeof(T) == 2 ? 2 : 1;      // 16-bit rows are 2 KB: keep two of them in flight per warp
   const int lane = threadIdx.x & 31;
   const int nv = static_cast<int>(C / kN);
   const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < N;
-       r += warps_per_grid) {
-    const uint4* vrow = reinterpret_cast<const uint4*>(L + r * ld);
-    uint4 v[NV];
+  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r0 < N;
+       r0 += warps_per_grid * kRows) {
+    sc::RegRow<T, NV> row[kRows];
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int j = lane + 32 * u;
-      v[u] = (j < nv) ? __ldg(vrow + j) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < kRows; ++i) {
+      const int64_t r = r0 + i * warps_per_grid;
+      if (r < N) row[i].load(L + r * ld, nv, lane);
     }
-    MaxIdx m{0.f, -1};
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int j = lane + 32 * u;
-      if (j < nv) {
-        const T* e = reinterpret_cast<const T*>(&v[u]);
-#pragma unroll
-        for (int t = 0; t < kN; ++t) {
-          const float x = sc::to_f32<T>(e[t]);
-          const int c = j * kN + t;
-          if (sc::better(x, c, m)) { m.v = x; m.i = c; }
+    for (int i = 0; i < kRows; ++i) {
+      const int64_t r = r0 + i * warps_per_grid;
+      if (r < N) {
+        const MaxIdx m = row[i].argmax();
+        float cf = m.v;
+        if (mode == SC_CONF_PROB) cf = 1.0f / row[i].expsum(scale, __fmul_rn(m.v, scale));
+        if (lane == 0) {
+          conf[r] = cf;
+          label[r] = m.i;
         }
       }
-    }
-    m = sc::warp_argmax(m);
-    float cf = m.v;
-    if (mode == SC_CONF_PROB) {
-      const float tmax = __fmul_rn(m.v, scale);
-      float s = 0.f;
-#pragma unroll
-      for (int u = 0; u < NV; ++u) {
-        const int j = lane + 32 * u;
-        if (j < nv) {
-          const T* e = reinterpret_cast<const T*>(&v[u]);
-#pragma unroll
-          for (int t = 0; t < kN; ++t) s += expf(__fmul_rn(sc::to_f32<T>(e[t]), scale) - tmax);
-        }
-      }
-      cf = 1.0f / sc::warp_sum(s);
-    }
-    if (lane == 0) {
-      conf[r] = cf;
-      label[r] = m.i;
     }
   }
 }

@@ -95,6 +95,30 @@ hard_labels_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, co
   }
 }
 
+// register-resident fast path of hard_labels_kernel (rows of whole 16-byte vectors, C <= 1024)
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 5 : 3)
+hard_labels_reg_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, const int64_t* __restrict__ idx,
+                       int64_t n_out, int16_t* __restrict__ out, int64_t n_pad) {
+  constexpr int kN = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int nv = static_cast<int>(C / kN);
+  const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t o = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); o < n_pad;
+       o += warps_per_grid) {
+    int lab = -1;
+    if (o < n_out) {
+      const int64_t r = idx ? idx[o] : o;
+      if (r >= 0 && r < N) {
+        sc::RegRow<T, NV> row;
+        row.load(L + r * ld, nv, lane);
+        lab = row.argmax().i;
+      }
+    }
+    if (lane == 0) out[o] = (lab >= 0 && lab < C) ? static_cast<int16_t>(lab) : static_cast<int16_t>(-1);
+  }
+}
+
 template <typename TO>
 __global__ void ones_row_kernel(TO* __restrict__ row, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -161,9 +185,18 @@ extern "C" int sc_hard_labels(const void* L, int dtype, int64_t N, int64_t C, in
     if (L == nullptr) dtype = SC_F32;
     const int64_t want = sc::ceil_div(n_pad, 8);
     const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
-    SC_DISPATCH_DTYPE(dtype, T,
-                      (hard_labels_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, idx,
-                                                                     labels_override, n_out, labels16, n_pad)));
+    SC_DISPATCH_DTYPE(dtype, T, {
+      constexpr int kN = 16 / sizeof(T);
+      constexpr int NV = (sizeof(T) == 4) ? 8 : 4;
+      const bool vec = L != nullptr && labels_override == nullptr && reinterpret_cast<uintptr_t>(L) % 16 == 0 &&
+                       ld % kN == 0 && C % kN == 0 && C / kN <= 32 * NV;
+      if (vec)
+        hard_labels_reg_kernel<T, NV><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, idx, n_out,
+                                                              labels16, n_pad);
+      else
+        hard_labels_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, idx, labels_override,
+                                                      n_out, labels16, n_pad);
+    });
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;

@@ -29,6 +29,36 @@ def shard_range(n: int, rank: int, world: int, align: int = 128) -> tp.Tuple[int
     return lo, hi
 
 
+def query_slice(n_queries: int, rank: int, world: int) -> tp.Tuple[int, int]:
+    """Rows of the merged result that `rank` finishes (zero-shot logits, epilogue) after the exchange."""
+    per = -(-n_queries // world)
+    lo = min(rank * per, n_queries)
+    return lo, min(lo + per, n_queries)
+
+
+def exchange_partials(part: torch.Tensor, group: tp.Any) -> tp.Tuple[torch.Tensor, int, int]:
+    """Key-sharded ranks each hold a partial O_r [Nq, C] over their keys.  Sum them over ranks and leave rank r
+    with the rows of ITS query slice only: one reduce-scatter moves (world-1)/world of a tile per rank (an
+    all-gather would move world-1 whole tiles) and the zero-shot logits and the epilogue then cost 1/world per
+    rank instead of being repeated on every rank.  Returns (rows [hi - lo, C], lo, hi)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nq = part.shape[0]
+    lo, hi = query_slice(nq, rank, world)
+    per = -(-nq // world)
+    if dist.get_backend(group) == "nccl":
+        src = part.contiguous()
+        if per * world != nq:                              # ragged query count: pad the tile with zero rows
+            src = torch.cat([src, src.new_zeros((per * world - nq, src.shape[1]))])
+        out = torch.empty((per, src.shape[1]), dtype=src.dtype, device=src.device)
+        dist.reduce_scatter_tensor(out, src, group=group)
+        return out[: hi - lo], lo, hi
+    # backends without reduce-scatter (gloo: the CPU tests of this host logic): all-reduce, then slice
+    full = part.clone()
+    dist.all_reduce(full, group=group)
+    return full[lo:hi], lo, hi
+
+
 class ClipSearcher:
     def __init__(self, device: tp.Union[str, torch.device] = "cuda", op_dtype: tp.Optional[torch.dtype] = None,
                  group: tp.Optional[tp.Any] = None) -> None:
@@ -119,9 +149,9 @@ class ClipSearcher:
             self.gpu_launches += 1
         return qn, z
 
-    def cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
-        """O = exp(-beta (1 - Qn Kn^T)) @ V over ALL keys (local keys, then the cross-rank merge):
-        fp32 [Nq, C (+1 if a row-sum column was requested)]."""
+    def local_cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
+        """O_r = exp(-beta (1 - Qn Kn^T)) @ V over THIS rank's keys: fp32 [Nq, C (+1 if a row-sum column was
+        requested)]."""
         n_cols = self.n_classes + (1 if self.rowsum_col is not None else 0)
         nq = qn.shape[0]
         if self.n_keys > 0:
@@ -136,14 +166,17 @@ class ClipSearcher:
             self.gpu_launches += 1 + int(splits > 1)
         else:
             part = torch.zeros((nq, n_cols), dtype=torch.float32, device=self.device)
+        return part
+
+    def cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
+        """O over ALL keys for every query, on every rank (all-reduce of the per-rank partials).  `search` uses
+        the cheaper reduce-scatter (`exchange_partials`) instead."""
+        part = self.local_cache_logits(qn, beta, splits)
         if self.world == 1:
             return part
         import torch.distributed as dist
-        gathered = torch.empty((self.world, nq, n_cols), dtype=torch.float32, device=self.device)
-        dist.all_gather_into_tensor(gathered, part.contiguous(), group=self.group)
-        out = ops.merge_partials(gathered)
-        self.gpu_launches += 1
-        return out
+        dist.all_reduce(part, group=self.group)
+        return part
 
     def search(self, test_image_features: torch.Tensor, betas: tp.Sequence[float], alphas: tp.Sequence[float],
                labels: tp.Optional[torch.Tensor] = None, feature_major: bool = True, want_logits: bool = False,
@@ -151,6 +184,8 @@ class ClipSearcher:
         """One pass of the hot path for a query bank: for every beta one fused attention launch, then one
         epilogue launch covering every alpha.  Returns one dict per beta with device tensors
         pred [na, Nq], top1/top5 [na] (if labels), logits [na, Nq, C] (if requested), cache_logits."""
+        if self.world > 1:
+            return self._search_sharded(test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred)
         qn, z = self.prepare_queries(test_image_features, feature_major)
         if labels is not None:
             labels = labels.to(self.device, non_blocking=True)
@@ -164,6 +199,55 @@ class ClipSearcher:
                                labels=labels, rowsum=rowsum, want_logits=want_logits, want_pred=want_pred)
             self.gpu_launches += 1
             res["beta"] = float(beta)
+            res["cache_logits"] = o
+            res["clip_logits"] = z
+            results.append(res)
+        return results
+
+    def _search_sharded(self, test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred):
+        """Key-sharded `search`: every rank scores ALL queries against its key shard, one reduce-scatter sums
+        the partial tiles and hands each rank its query slice, which it finishes alone (zero-shot logits,
+        alpha epilogue); predictions are all-gathered and the accuracy counters all-reduced, so every rank
+        returns the same pred / top1 / top5.  `logits`, `cache_logits`, `clip_logits` cover the rank's own
+        query slice [`lo`, `hi`)."""
+        import torch.distributed as dist
+        q = test_image_features.to(self.device, non_blocking=True)
+        qn = ops.normalize_cast(q, feature_major=feature_major, op_dtype=self.op_dtype)
+        self.gpu_launches += 1
+        nq = qn.shape[0]
+        lo, hi = query_slice(nq, self.rank, self.world)
+        per = -(-nq // self.world)
+        z = None
+        if self.text is not None and hi > lo:
+            q_mine = q[:, lo:hi] if feature_major else q[lo:hi]
+            z = ops.zero_shot_logits(q_mine, feature_major, self.text, scale=100.0, normalize=True)
+            self.gpu_launches += 1
+        lab_mine = labels.to(self.device, non_blocking=True)[lo:hi].contiguous() if labels is not None else None
+        results = []
+        for beta in betas:
+            o, lo, hi = exchange_partials(self.local_cache_logits(qn, float(beta)), self.group)
+            res = {"beta": float(beta), "lo": lo, "hi": hi, "pred": None, "top1": None, "top5": None, "logits": None}
+            na = len(alphas)
+            pred_all = torch.zeros((self.world, na, per), dtype=torch.int32, device=self.device)
+            if hi > lo:
+                rowsum = o[:, self.rowsum_col].contiguous() if self.rowsum_col is not None else None
+                r = ops.epilogue(z, o[:, : self.n_classes] if self.rowsum_col is not None else o, alphas,
+                                 labels=lab_mine, rowsum=rowsum, want_logits=want_logits, want_pred=want_pred)
+                self.gpu_launches += 1
+                res.update(logits=r["logits"], top1=r["top1"], top5=r["top5"])
+                mine = torch.zeros((na, per), dtype=torch.int32, device=self.device)
+                if want_pred:
+                    mine[:, : hi - lo] = r["pred"]
+            else:
+                mine = torch.zeros((na, per), dtype=torch.int32, device=self.device)
+            if labels is not None:
+                counts = torch.stack([res["top1"], res["top5"]]) if res["top1"] is not None else \
+                    torch.zeros((2, na), dtype=torch.int32, device=self.device)
+                dist.all_reduce(counts, group=self.group)
+                res["top1"], res["top5"] = counts[0], counts[1]
+            if want_pred:
+                dist.all_gather_into_tensor(pred_all, mine, group=self.group)
+                res["pred"] = pred_all.permute(1, 0, 2).reshape(na, self.world * per)[:, :nq].contiguous()
             res["cache_logits"] = o
             res["clip_logits"] = z
             results.append(res)

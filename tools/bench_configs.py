@@ -47,9 +47,11 @@ def attention_config(name, nq, nk, dim, c, peaks, beta=5.5):
     qn, z = s.prepare_queries(q_bank)
     med, best = timed(lambda: s.cache_logits(qn, beta), warmup=2, iters=3)
     flops = 2.0 * nq * nk * (dim + c)
-    emit(config=name, kind="attention", n_queries=nq, n_keys=nk, dim=dim, n_classes=c, ms=med,
-         queries_per_s=nq / (med * 1e-3), tflops=flops / (med * 1e-3) / 1e12,
-         frac_of_bf16_peak=flops / (med * 1e-3) / 1e12 / peaks["bf16_tflops"], dtype=str(ops.OP_DTYPE))
+    executed = 2.0 * nq * s.hard_bank.n_sorted * dim if s.hard_bank is not None else 2.0 * nq * nk * (dim + ops.pad_classes(c))
+    emit(config=name, kind="attention", values="one-hot (segmented kernel)" if s.hard_bank is not None else "dense",
+         n_queries=nq, n_keys=nk, dim=dim, n_classes=c, ms=med, queries_per_s=nq / (med * 1e-3),
+         executed_tflops=executed / (med * 1e-3) / 1e12, frac_of_bf16_peak=executed / (med * 1e-3) / 1e12 / peaks["bf16_tflops"],
+         dense_equivalent_tflops=flops / (med * 1e-3) / 1e12, dtype=str(ops.OP_DTYPE))
     return s, q_bank, labels, z, qn
 
 
@@ -78,8 +80,10 @@ def main():
     head = tip_utils.TipAdapterHead(keys, vals, feats, clip_w)
     med, _ = timed(lambda: head.cache_logits(5.5), iters=5)
     flops = 2.0 * nq * nk * (dim + c)
-    emit(config="cfg2_tip_imagenet_16shot", kind="attention_per_beta", ms=med, queries_per_s=nq / (med * 1e-3),
-         tflops=flops / (med * 1e-3) / 1e12, frac_of_bf16_peak=flops / (med * 1e-3) / 1e12 / peaks["bf16_tflops"])
+    executed = 2.0 * nq * head.values.hard_bank(head.k).n_sorted * dim if head.values.is_hard else flops
+    emit(config="cfg2_tip_imagenet_16shot", kind="attention_per_beta", values="one-hot (segmented kernel)" if head.values.is_hard else "dense",
+         ms=med, queries_per_s=nq / (med * 1e-3), executed_tflops=executed / (med * 1e-3) / 1e12,
+         frac_of_bf16_peak=executed / (med * 1e-3) / 1e12 / peaks["bf16_tflops"], dense_equivalent_tflops=flops / (med * 1e-3) / 1e12)
     cfg = {"search_hp": True, "search_scale": [7, 3], "search_step": [20, 20] if quick else [200, 20]}
     import contextlib
     import io
@@ -113,6 +117,10 @@ def main():
         med, best = timed(lambda: ops.topk_per_class(conf, label, c, 16), iters=5)
         emit(config="cfg4_selection", kind="topk_per_class_k16", logits_dtype=dt_name, ms=med,
              note="histogram + scan + scatter + radix select; 32 N bytes of traffic", gbs=32.0 * n / (med * 1e-3) / 1e9)
+        medh, _ = timed(lambda: ops.hard_labels(L, c), iters=5)
+        bytes_h = n * c * L.element_size() + 2 * n
+        emit(config="cfg4_selection", kind="hard_labels", logits_dtype=dt_name, ms=medh, gbs=bytes_h / (medh * 1e-3) / 1e9,
+             frac_of_hbm=bytes_h / (medh * 1e-3) / 1e9 / hbm, algorithmic_bytes=bytes_h)
         medv, _ = timed(lambda: ops.values_prepare(L, c), iters=3)
         bytes_v = n * c * L.element_size() + ops.pad_classes(c) * ops.pad_keys(n) * 2 * 2
         emit(config="cfg4_selection", kind="values_hard_all_logits", logits_dtype=dt_name, ms=medv,
@@ -140,7 +148,7 @@ def main():
     s.set_text(text)
     s.set_cache(k_bank, outs)
     del k_bank, outs
-    bank_bytes = 2.0 * n * (1024 + ops.pad_classes(c))
+    bank_bytes = 2.0 * s.hard_bank.n_sorted * 1024 if s.hard_bank is not None else 2.0 * n * (1024 + ops.pad_classes(c))
     for b in ([1, 64, 1024, 4096] if quick else [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]):
         qb = q_bank[:, :b].contiguous()
         lab = labels[:b].contiguous()

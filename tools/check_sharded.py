@@ -1,0 +1,40 @@
+"""2-rank NCCL check of the key-sharded ClipSearcher.search against the single-rank result (run under torchrun)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from oracle import clip_search_oracle as orc
+from summer_clip_b200.searcher import ClipSearcher
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for nq, hard in ((1001, True), (512, True), (777, False)):
+    banks = orc.synthetic_banks(nq, 5000, 256, 300, seed=5, sigma=0.5, sigma_text=0.8, shared=3.0)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"]
+    kw = {} if hard else {"softmax_scale": orc.CLIP_SCALE * 0.1}
+    single = ClipSearcher(dev)
+    single.set_text(T)
+    single.set_cache(K, L, **kw)
+    ref = single.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
+    sharded = ClipSearcher(dev, group=dist.group.WORLD)
+    sharded.set_text(T)
+    sharded.set_cache(K, L, **kw)
+    got = sharded.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
+    lo, hi = got["lo"], got["hi"]
+    e = (got["logits"] - ref["logits"][:, lo:hi]).abs().max().item() / ref["logits"].abs().max().item()
+    same_pred = bool((got["pred"] == ref["pred"]).float().mean() > 0.999)
+    same_cnt = bool((got["top1"] - ref["top1"]).abs().max() <= 1) and bool((got["top5"] - ref["top5"]).abs().max() <= 1)
+    good = e < 1e-4 and same_pred and same_cnt and got["pred"].shape == ref["pred"].shape
+    ok &= good
+    print(f"rank {rank} nq={nq} hard={hard}: slice=[{lo},{hi}) rel_err={e:.2e} pred={same_pred} counts={same_cnt} {'OK' if good else 'FAIL'}", flush=True)
+dist.barrier()
+print(f"rank {rank} SHARDED {'OK' if ok else 'FAIL'}", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
