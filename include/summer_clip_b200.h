@@ -154,6 +154,19 @@ int sc_zero_shot_logits(const void* X, int x_dtype, int64_t D, int64_t N, int64_
                         int64_t stride_n, const void* T, int t_dtype, int64_t C, int64_t ldt,
                         float scale, int normalize, float* Z, int64_t ldz, void* stream);
 
+/* Tensor-core route of the same product (image_attention.py:80-83; the logits-bank producer
+ * save_image_outs.py:25): fp32-accurate although it runs on fp16 tensor cores.
+ *   sc_normalize_split: (optionally column-normalised) src, any layout / dtype as in sc_normalize_cast, written
+ *     as an fp16 PAIR hi = fp16(v), lo = fp16(v - hi), both [N, D_pad] K-major (22 significant bits);
+ *   sc_gemm_split_nt:   Z[m, n] = scale * sum_d (Ah[m,d] Bh[n,d] + Ah[m,d] Bl[n,d] + Al[m,d] Bh[n,d])
+ *     — 256 x 256 CTA-pair tcgen05 tiles, three operand passes into one TMEM accumulator; the dropped lo.lo
+ *     term is below 2^-22 |a||b|.  Z is fp32 [M, ldz]; A is [M, D_pad], B is [N, D_pad].
+ * Zero-shot logits: A = split(normalised queries), B = split(T^T), scale = 100. */
+int sc_normalize_split(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
+                       int64_t stride_n, void* hi, void* lo, int64_t D_pad, int normalize, void* stream);
+int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                     int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream);
+
 /* Epilogue (image_attention.py:111-112, clip_searcher/utils.py:15-21, tip_adapter/utils.py:10-15):
  * for every alpha a: out = Z + O * alpha  (O optionally divided by rowsum[q] first), prediction =
  * first argmax, and — if labels are given — the number of rows whose label is the top-1 / within

@@ -46,6 +46,10 @@ SIGNATURES = {
     "sc_merge_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "sc_zero_shot_logits": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,
                                     c_int64, c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_normalize_split": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                   c_int, c_void_p]),
+    "sc_gemm_split_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                 c_void_p, c_int64, c_void_p]),
     "sc_epilogue": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, POINTER(c_float),
                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

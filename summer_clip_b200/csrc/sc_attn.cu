@@ -39,6 +39,9 @@ int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count);
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                     const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
                     int64_t Nks, int64_t D_pad, float beta, int splits, float* O, int64_t ldo, cudaStream_t st);
+int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                      const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                      int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st);
 }  // namespace sc
 
 namespace {
@@ -518,6 +521,22 @@ int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class,
              "sc_attn_fwd_hard: splits=%d exceeds the %lld key steps", splits, (long long)steps_total);
   int rc = sc::attn_seg_launch(&make_tmap, Qn, Ks, group_class, key_bits, op_dtype == SC_F16, Nq, Nks, D_pad, beta,
                                splits, O, ldo, static_cast<cudaStream_t>(stream));
+  if (rc != SC_OK) return rc;
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                     int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream) {
+  SC_REQUIRE(Ah && Al && Bh && Bl && Z, SC_EINVAL, "sc_gemm_split_nt: null pointer");
+  SC_REQUIRE(M > 0 && N > 0 && ldz >= N, SC_ESHAPE, "sc_gemm_split_nt: bad shape");
+  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_gemm_split_nt: D_pad=%lld must be a multiple of 64",
+             (long long)D_pad);
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(Ah) | reinterpret_cast<uintptr_t>(Al) | reinterpret_cast<uintptr_t>(Bh) |
+              reinterpret_cast<uintptr_t>(Bl)) % 16 == 0,
+             SC_EALIGN, "sc_gemm_split_nt: operands must be 16-byte aligned");
+  SC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) - 512, SC_ESHAPE, "sc_gemm_split_nt: M/N exceed int32 coordinates");
+  int rc = sc::gemm_split_launch(&make_tmap, Ah, Al, Bh, Bl, M, N, D_pad, scale, Z, ldz, static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());
   return SC_OK;

@@ -54,6 +54,11 @@ struct SParams {
   float* O;                  // [splits, Nq, ldo], zeroed by the launcher; only the classes met are written
   long long ldo;
   unsigned long long* clk;   // experiments builds: {sum of CTA cycles, sum of CTA ns, CTAs}
+  // kGemm mode (sc_gemm_split_nt): Z[m, n] = scale * S[m, n], S accumulated over 3 operand passes
+  float* Z;
+  long long ldz;
+  int n_cols;                // valid columns of Z (rows of B)
+  float scale;
 };
 
 struct Bars {
@@ -70,9 +75,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <bool kF16>
+// kGemm = false: the attention kernel described above.  kGemm = true: the same TMA ring / pair-UMMA / TMEM
+// pipeline used as a plain "NT" GEMM with split-fp16 operands (sc_gemm_split_nt): three operand passes
+// (Ah.Bh, Ah.Bl, Al.Bh) accumulate into one S tile, and the four "exp" warps store scale * S instead.
+template <bool kF16, bool kGemm>
 __global__ void __launch_bounds__(kThreads, 1)
-sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const SParams p) {
+sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmK2, const SParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t ring0 = (raw_addr + 1023u) & ~1023u;
@@ -91,6 +100,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int s1 = static_cast<int>((static_cast<long long>(p.steps_total) * (split + 1)) / p.splits);
   const int nsteps = s1 - s0;
   const int nd = p.n_dchunks;
+  constexpr int kPasses = kGemm ? 3 : 1;      // operand passes accumulated into one S tile
 
 #ifdef SC_ATTN_TIMING_EXPERIMENTS
   long long clk_c0 = 0;
@@ -103,6 +113,10 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
+    if (kGemm) {
+      prefetch_tmap(&tmQ2);
+      prefetch_tmap(&tmK2);
+    }
     for (int s = 0; s < kNS; ++s) {
       mbar_init(smem_u32(&bars->full[s]), 1);
       mbar_init(smem_u32(&bars->empty[s]), 1);
@@ -139,22 +153,28 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // L2 prefetch of the key stream: co-resident pairs walk the same key steps at about the same time, so a
       // step's first touch pays the HBM latency for all of them; one pair in 32 (by query tile) pulls the
       // chunks of step st + pf_dist into L2 ahead of the pack
-      if (p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
+      if (!kGemm && p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
         if (elect_one()) {
           for (int d = 0; d < nd; ++d) tma_prefetch_2d(&tmK, d * kBK, krow + p.pf_dist * kStepKeys);
         }
         __syncwarp();
       }
 #pragma unroll 1
-      for (int d = 0; d < nd; ++d) {
-        if (!ready) mbar_wait(empty0 + stage * 8, phase ^ 1u);
-        const bool wrap = (stage + 1 == kNS);
-        const uint32_t dst = ring0 + stage * kStage;
-        ready = __all_sync(0xffffffffu,
-                           tma2_cg2_probe(dst, &tmQ, d * kBK, q0, qon, dst + 16384, &tmK, d * kBK, krow, kon,
-                                          full0c + stage * 8, full0 + stage * 8, tx, plain,
-                                          empty0 + (wrap ? 0 : stage + 1) * 8, (wrap ? phase ^ 1u : phase) ^ 1u));
-        if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+      for (int ps = 0; ps < kPasses; ++ps) {
+        // kGemm passes: (A hi, B hi), (A hi, B lo), (A lo, B hi)
+        const CUtensorMap* mq = (kGemm && ps == 2) ? &tmQ2 : &tmQ;
+        const CUtensorMap* mk = (kGemm && ps == 1) ? &tmK2 : &tmK;
+#pragma unroll 1
+        for (int d = 0; d < nd; ++d) {
+          if (!ready) mbar_wait(empty0 + stage * 8, phase ^ 1u);
+          const bool wrap = (stage + 1 == kNS);
+          const uint32_t dst = ring0 + stage * kStage;
+          ready = __all_sync(0xffffffffu,
+                             tma2_cg2_probe(dst, mq, d * kBK, q0, qon, dst + 16384, mk, d * kBK, krow, kon,
+                                            full0c + stage * 8, full0 + stage * 8, tx, plain,
+                                            empty0 + (wrap ? 0 : stage + 1) * 8, (wrap ? phase ^ 1u : phase) ^ 1u));
+          if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -173,7 +193,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t tmem_s = tmem_base + sb * 256;
         const uint32_t sfull = smem_u32(&bars->s_full[sb]);
 #pragma unroll 1
-        for (int d = 0; d < nd; ++d) {
+        for (int dd = 0; dd < nd * kPasses; ++dd) {
           if (!ready) mbar_wait(full0 + stage * 8, phase);
           tc_fence_after();
           const bool wrap = (stage + 1 == kNS);
@@ -181,8 +201,8 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t b_desc = umma_desc_k128(ring0 + stage * kStage + 16384);     // K chunk: my 128 keys
           ready = __all_sync(0xffffffffu,
                              umma4_cg2_probe(tmem_s, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc, b_desc + 2,
-                                             b_desc + 4, b_desc + 6, idesc, d != 0 ? 1u : 0u, en, empty0 + stage * 8,
-                                             pair_mask, sfull, pair_mask, d == nd - 1 ? 1u : 0u,
+                                             b_desc + 4, b_desc + 6, idesc, dd != 0 ? 1u : 0u, en, empty0 + stage * 8,
+                                             pair_mask, sfull, pair_mask, dd == nd * kPasses - 1 ? 1u : 0u,
                                              full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
           if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
         }
@@ -192,6 +212,45 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ===================================================== exp + segmented sum warps: thread = query
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    if constexpr (kGemm) {
+      // ---- GEMM mode: Z[q, n] = scale * S[q, n]; thread = output row, 32 consecutive columns per TMEM load
+      const int qg = q0 + row;
+      float* zrow = p.Z + static_cast<long long>(qg) * p.ldz;
+      const bool vec4 = (p.ldz % 4 == 0) && (reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
+#pragma unroll 1
+      for (int st = 0; st < nsteps; ++st) {
+        const int b = st & 1;
+        mbar_wait(smem_u32(&bars->s_full[b]), (st >> 1) & 1);
+        tc_fence_after();
+        const int n0 = (s0 + st) * kStepKeys;
+#pragma unroll 1
+        for (int cc = 0; cc < kStepKeys / 32; ++cc) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + lane_addr + b * 256 + cc * 32, rg);
+          tmem_ld_wait();
+          const int nb = n0 + cc * 32;
+          if (qg < p.Nq && nb < p.n_cols) {
+            if (vec4 && nb + 32 <= p.n_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(zrow + nb + j) =
+                    make_float4(__uint_as_float(rg[j]) * p.scale, __uint_as_float(rg[j + 1]) * p.scale,
+                                __uint_as_float(rg[j + 2]) * p.scale, __uint_as_float(rg[j + 3]) * p.scale);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.n_cols) zrow[nb + j] = __uint_as_float(rg[j]) * p.scale;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+          else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), 0);
+        }
+      }
+    } else {
     const float c1 = p.c1, cadd = p.c0;
     const int q = q0 + row;
     float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;
@@ -259,6 +318,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     if (cur >= 0 && q_ok) orow[cur] = acc;
+    }
   }
 
   tc_fence_before();
@@ -279,9 +339,10 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <bool kF16>
-int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const SParams& p) {
-  auto kernel = sc_attn_seg_kernel<kF16>;
+template <bool kF16, bool kGemm>
+int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmQ2,
+               const CUtensorMap& tmK2, const SParams& p) {
+  auto kernel = sc_attn_seg_kernel<kF16, kGemm>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -295,7 +356,7 @@ int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SC_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmQ, tmK, p));
+  SC_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmQ, tmK, tmQ2, tmK2, p));
   return SC_OK;
 }
 
@@ -376,7 +437,44 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(splits) * Nq * ldo * sizeof(float), st));
   dim3 grid(2u, static_cast<unsigned>(ceil_div(Nq, 2 * kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd_hard: too many query tiles; chunk the queries");
-  return f16 ? launch_seg<true>(grid, st, tmQ, tmK, p) : launch_seg<false>(grid, st, tmQ, tmK, p);
+  p.Z = nullptr;
+  p.ldz = 0;
+  p.n_cols = 0;
+  p.scale = 1.0f;
+  return f16 ? launch_seg<true, false>(grid, st, tmQ, tmK, tmQ, tmK, p) : launch_seg<false, false>(grid, st, tmQ, tmK, tmQ, tmK, p);
+}
+
+// Z[m, n] = scale * sum_d (Ah[m,d] Bh[n,d] + Ah[m,d] Bl[n,d] + Al[m,d] Bh[n,d]): fp32-accurate "NT" GEMM of
+// operands given as fp16 (hi, lo) pairs, on the attention kernel's pipeline (one 256-row step of B per work item).
+int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                      const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                      int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st) {
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  int rc;
+  if ((rc = make_tmap(&tmA, Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmA2, Al, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmB, Bh, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmB2, Bl, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
+  SParams p;
+  p.Nq = static_cast<int>(M);
+  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.steps_total = static_cast<int>(ceil_div(N, kStepKeys));
+  p.splits = p.steps_total;                 // one step of 256 B-rows per work item
+  p.c1 = p.c0 = 0.f;
+  p.gcls = nullptr;
+  p.kbits = nullptr;
+  p.O = nullptr;
+  p.ldo = 0;
+  p.dbg = 0;
+  p.clk = nullptr;
+  p.pf_dist = 0;
+  p.Z = Z;
+  p.ldz = ldz;
+  p.n_cols = static_cast<int>(N);
+  p.scale = scale;
+  dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
+  SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
+  return launch_seg<true, true>(grid, st, tmA, tmB, tmA2, tmB2, p);
 }
 
 }  // namespace sc

@@ -188,7 +188,130 @@ norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride
   }
 }
 
+// ---- split variants: every (optionally normalised) fp32 value v is written as an fp16 PAIR hi = fp16(v),
+// lo = fp16(v - hi), 22 significant bits in all, so that a tensor-core GEMM over (hi, lo) operands
+// (sc_gemm_split_nt) reproduces the fp32 product.  Any layout / dtype; the banks these run on are small
+// (queries, text classifier), so they keep the simple tile / warp-per-row structure.
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
+                       __half* __restrict__ hi, __half* __restrict__ lo, int64_t D_pad, int normalize) {
+  __shared__ float tile[64][33];
+  __shared__ float red[8][32];
+  __shared__ float nrm_s[32];
+  const int tx = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 5;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int64_t n = n0 + tx;
+  const bool ok = n < N;
+  float ss = 0.f;
+  if (normalize && ok)
+    for (int64_t d = ty; d < D; d += 8) {
+      const float v = sc::to_f32<T>(src[d * stride_d + n * stride_n]);
+      ss = fmaf(v, v, ss);
+    }
+  red[ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    nrm_s[tx] = normalize ? sqrtf(t) : 1.0f;
+  }
+  __syncthreads();
+  const float nrm = nrm_s[tx];
+  for (int64_t d0 = 0; d0 < D_pad; d0 += 64) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t d = d0 + ty + 8 * j;
+      float v = 0.f;
+      if (d < D && ok) {
+        v = sc::to_f32<T>(src[d * stride_d + n * stride_n]);
+        if (normalize) v = v / nrm;
+      }
+      tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = ty + 8 * j;
+      const int64_t o = n0 + r;
+      if (o < N) {
+        const int d = 2 * tx;
+        __half h0, l0, h1, l1;
+        split_f16(tile[d][r], h0, l0);
+        split_f16(tile[d + 1][r], h1, l1);
+        *reinterpret_cast<__half2*>(hi + o * D_pad + d0 + d) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(lo + o * D_pad + d0 + d) = __halves2half2(l0, l1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_n, __half* __restrict__ hi,
+                  __half* __restrict__ lo, int64_t D_pad, int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (o >= N) return;
+  const T* row = src + o * stride_n;
+  float nrm = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int64_t d = lane; d < D; d += 32) {
+      const float v = sc::to_f32<T>(row[d]);
+      ss = fmaf(v, v, ss);
+    }
+    nrm = sqrtf(sc::warp_sum(ss));
+  }
+  for (int64_t d = 2 * lane; d < D_pad; d += 64) {
+    float a = 0.f, b = 0.f;
+    if (d < D) a = sc::to_f32<T>(row[d]) / nrm;
+    if (d + 1 < D) b = sc::to_f32<T>(row[d + 1]) / nrm;
+    __half h0, l0, h1, l1;
+    split_f16(a, h0, l0);
+    split_f16(b, h1, l1);
+    *reinterpret_cast<__half2*>(hi + o * D_pad + d) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(lo + o * D_pad + d) = __halves2half2(l0, l1);
+  }
+}
+
 }  // namespace
+
+extern "C" int sc_normalize_split(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
+                                  int64_t stride_n, void* hi, void* lo, int64_t D_pad, int normalize,
+                                  void* stream) {
+  SC_REQUIRE(src && hi && lo, SC_EINVAL, "sc_normalize_split: null pointer");
+  SC_REQUIRE(D > 0 && N >= 0, SC_ESHAPE, "sc_normalize_split: bad shape");
+  SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE, "sc_normalize_split: D_pad=%lld must be >= D and a multiple of 64",
+             (long long)D_pad);
+  SC_REQUIRE((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) % 4 == 0, SC_EALIGN,
+             "sc_normalize_split: outputs misaligned");
+  if (N == 0) return SC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride_d == 1 && stride_n != 1) {
+    const unsigned blocks = static_cast<unsigned>(sc::ceil_div(N, 8));
+    SC_DISPATCH_DTYPE(src_dtype, T,
+                      (split_rows_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), D, N, stride_n,
+                                                                    static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                                    D_pad, normalize)));
+  } else {
+    const unsigned blocks = static_cast<unsigned>(sc::ceil_div(N, 32));
+    SC_DISPATCH_DTYPE(src_dtype, T,
+                      (split_transpose_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), D, N, stride_d,
+                                                                         stride_n, static_cast<__half*>(hi),
+                                                                         static_cast<__half*>(lo), D_pad, normalize)));
+  }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
 
 extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N,
                                  int64_t stride_d, int64_t stride_n, const int64_t* idx,

@@ -327,9 +327,64 @@ def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, 
     return merge_partials(O)
 
 
+def normalize_split(x: torch.Tensor, feature_major: bool, normalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(hi, lo) fp16 [N, D_pad]: the (column-normalised) bank as split-fp16 rows, hi + lo = the fp32 value to 22
+    bits — the operands of `gemm_split_nt`."""
+    _cuda(x, "x")
+    assert x.dim() == 2
+    if feature_major:
+        D, N = x.shape
+        stride_d, stride_n = x.stride()
+    else:
+        N, D = x.shape
+        stride_n, stride_d = x.stride()
+    D_pad = pad_dim(D)
+    hi = torch.empty((N, D_pad), dtype=torch.float16, device=x.device)
+    lo = torch.empty((N, D_pad), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sc_normalize_split(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(hi), _ptr(lo), D_pad,
+                                             int(normalize), _stream()), "sc_normalize_split")
+    return hi, lo
+
+
+def gemm_split_nt(a: Tuple[torch.Tensor, torch.Tensor], b: Tuple[torch.Tensor, torch.Tensor], scale: float = 1.0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Z [M, N] fp32 = scale * A @ B^T for split-fp16 operands A = (hi, lo) [M, D_pad], B = (hi, lo) [N, D_pad]
+    on the tcgen05 pipeline (fp32-accurate: three passes hi.hi + hi.lo + lo.hi into one TMEM accumulator)."""
+    ah, al = a
+    bh, bl = b
+    M, D_pad = ah.shape
+    N = bh.shape[0]
+    assert bh.shape[1] == D_pad and all(t.dtype == torch.float16 and t.is_contiguous() and t.is_cuda for t in (ah, al, bh, bl))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=ah.device)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (M, N)
+    with torch.cuda.device(ah.device):
+        check(_lib.load().sc_gemm_split_nt(_ptr(ah), _ptr(al), _ptr(bh), _ptr(bl), M, N, D_pad, float(scale), _ptr(out),
+                                           out.stride(0), _stream()), "sc_gemm_split_nt")
+    return out
+
+
+_TEXT_SPLITS: list = []      # (key, (hi, lo)) of recently used classifiers T^T (a run has one or two)
+
+
+def _text_split(T: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    key = (T.data_ptr(), tuple(T.shape), tuple(T.stride()), T.dtype, T._version, T.device)
+    for k, v in _TEXT_SPLITS:
+        if k == key:
+            return v
+    v = normalize_split(T, feature_major=True, normalize=False)      # T is [D, C]: rows of T^T, as given
+    _TEXT_SPLITS.append((key, v))
+    if len(_TEXT_SPLITS) > 4:
+        _TEXT_SPLITS.pop(0)
+    return v
+
+
 def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scale: float = 100.0,
-                     normalize: bool = True) -> torch.Tensor:
-    """Z = scale * normalise(X)^T @ T in fp32 (image_attention.py:80-83).  T is [D, C]."""
+                     normalize: bool = True, tensor_cores: Optional[bool] = None) -> torch.Tensor:
+    """Z = scale * normalise(X)^T @ T in fp32 (image_attention.py:80-83).  T is [D, C].  Default route: split-fp16
+    operands on the tensor cores (`normalize_split` + `gemm_split_nt`); `tensor_cores=False` (or
+    SUMMER_CLIP_B200_ZS_SIMT=1) selects the fp32 SIMT kernel (A/B runs, cross-check in the tests)."""
     _cuda(X, "X"), _cuda(T, "T")
     if feature_major:
         D, N = X.shape
@@ -338,6 +393,10 @@ def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scal
         N, D = X.shape
         stride_n, stride_d = X.stride()
     assert T.dim() == 2 and T.shape[0] == D
+    if tensor_cores is None:
+        tensor_cores = not os.environ.get("SUMMER_CLIP_B200_ZS_SIMT")
+    if tensor_cores and N > 0:
+        return gemm_split_nt(normalize_split(X, feature_major, normalize), _text_split(T), scale)
     if T.stride(1) != 1:
         T = T.contiguous()
     C = T.shape[1]

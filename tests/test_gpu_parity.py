@@ -372,6 +372,33 @@ def test_hard_values_route_through_the_segmented_kernel(ops, monkeypatch):
     torch.testing.assert_close(w @ dense, got, rtol=0, atol=2e-3 * got.max().item())
 
 
+@pytest.mark.parametrize("shape", [(512, 333, 101, True, torch.float32), (1024, 1000, 1000, True, torch.float16),
+                                   (768, 257, 397, False, torch.float32), (100, 5, 3, True, torch.float32),
+                                   (64, 700, 513, False, torch.float16)])
+def test_zero_shot_logits_tensor_core_route(ops, shape):
+    """Z = 100 * normalise(X)^T T through split-fp16 operands on the tcgen05 pipeline (sc_normalize_split +
+    sc_gemm_split_nt) against float64 torch and against the fp32 SIMT kernel: fp32-accurate."""
+    D, N, C, fm, dtype = shape
+    g = torch.Generator().manual_seed(83)
+    X = torch.randn((D, N) if fm else (N, D), generator=g).to(dtype).cuda()
+    T = torch.nn.functional.normalize(torch.randn(D, C, generator=g), dim=0).cuda()
+    Z = ops.zero_shot_logits(X, fm, T)
+    Zs = ops.zero_shot_logits(X, fm, T, tensor_cores=False)
+    Xd = X.double() if not fm else X.double().t()
+    ref = 100.0 * torch.nn.functional.normalize(Xd, dim=1) @ T.double()
+    assert Z.shape == (N, C) and Z.dtype == torch.float32
+    # |Z| <= 100; fp32 accumulation over D terms is what limits both routes (the golden check uses atol 2e-4)
+    assert (Z.double() - ref).abs().max().item() < 3e-4
+    assert (Zs.double() - ref).abs().max().item() < 3e-4
+    assert (Z - Zs).abs().max().item() < 3e-4
+    hi, lo = ops.normalize_split(X, fm)
+    assert hi.shape == (N, ops.pad_dim(D)) and float(hi[:, D:].abs().sum() + lo[:, D:].abs().sum()) == 0.0
+    rec = hi.double() + lo.double()
+    assert (rec[:, :D] - torch.nn.functional.normalize(Xd, dim=1)).abs().max().item() < 3e-7      # 22 bits of each value
+    raw = ops.zero_shot_logits(X, fm, T, scale=1.0, normalize=False)                              # the L producer
+    assert (raw.double() - Xd @ T.double()).abs().max().item() < 1e-4 * max(1.0, float(Xd.abs().max()) * D ** 0.5)
+
+
 def test_cpu_tensors_are_rejected(ops):
     from summer_clip_b200._lib import SummerClipError
     with pytest.raises(SummerClipError):
