@@ -120,6 +120,24 @@ int sc_hard_labels(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, c
                    const int32_t* labels_override, int64_t n_out, int16_t* labels16, int64_t n_pad,
                    void* stream);
 
+/* Layout of the label-sorted key bank sc_attn_fwd_hard consumes, from the int16 labels of sc_hard_labels:
+ * a STABLE counting sort of the keys by class (original order inside a class, so results are reproducible bit
+ * for bit) with every class segment padded to whole 16-key groups.  Outputs, all sized by
+ * capacity = sc_hard_bank_capacity(n_keys, n_classes) (a multiple of 256, >= n_keys + 15 n_classes):
+ *   perm        int64  [capacity]       original index of sorted key j, -1 = padding;
+ *   group_class int16  [capacity / 16]  class of every 16-key group, -1 = none;
+ *   key_bits    uint32 [capacity / 32]  bit j of word w = 1 iff sorted key 32 w + j is real;
+ *   n_sorted    int64  [1] (device)     keys in the padded bank (a multiple of 16): Nks of sc_attn_fwd_hard.
+ * Labels outside [0, n_classes) select no class and are dropped.  sc_gather_rows then builds the bank itself:
+ * dst[j] = src[perm[j]] for rows of row_bytes (a multiple of 16), zero rows where perm[j] < 0. */
+int64_t sc_hard_bank_capacity(int64_t n_keys, int32_t n_classes);
+size_t sc_hard_bank_workspace_bytes(int64_t n_keys, int32_t n_classes);
+int sc_hard_bank_layout(const int16_t* labels16, int64_t n_keys, int32_t n_classes, int64_t* perm,
+                        int16_t* group_class, uint32_t* key_bits, int64_t capacity, int64_t* n_sorted,
+                        void* workspace, size_t ws_bytes, void* stream);
+int sc_gather_rows(const void* src, int64_t n_src, int64_t row_bytes, const int64_t* perm, int64_t n_out,
+                   void* dst, void* stream);
+
 /* sc_attn_fwd for one-hot cache values on a LABEL-SORTED key bank (same result as sc_attn_fwd on
  * Vt = one_hot(label)^T; the sum over keys does not depend on their order):
  *     O[s, q, c] = sum_{k in split s, class(k) == c} exp(beta * (Qn[q].Ks[k] - 1)),   c < n_classes.

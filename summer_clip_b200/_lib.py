@@ -39,6 +39,11 @@ SIGNATURES = {
     "sc_pad_labels": (c_int64, [c_int64]),
     "sc_hard_labels": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                c_int64, c_void_p]),
+    "sc_hard_bank_capacity": (c_int64, [c_int64, c_int32]),
+    "sc_hard_bank_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "sc_hard_bank_layout": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_void_p, c_size_t, c_void_p]),
+    "sc_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "sc_attn_hard_supported": (c_int, [c_int64]),
     "sc_attn_hard_splits": (c_int, [c_int64, c_int64, c_int]),
     "sc_attn_fwd_hard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,

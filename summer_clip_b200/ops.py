@@ -218,19 +218,55 @@ class HardBank:
         self.rows: Optional[torch.Tensor] = None
 
     def gather(self, k_norm: torch.Tensor) -> "HardBank":
-        """Permute a normalised bank [>= n_keys, D_pad] (original key order) into sorted order."""
-        src = self.perm.clamp_min(0)
-        rows = k_norm.index_select(0, src)
-        rows[self.perm < 0] = 0
+        """Permute a normalised bank [>= n_keys, D_pad] (original key order) into sorted order (sc_gather_rows)."""
+        _cuda(k_norm, "k_norm")
+        assert k_norm.dim() == 2 and k_norm.is_contiguous() and (k_norm.shape[1] * k_norm.element_size()) % 16 == 0
+        n_out = self.perm.numel()
+        rows = torch.empty((n_out, k_norm.shape[1]), dtype=k_norm.dtype, device=k_norm.device)
+        with torch.cuda.device(k_norm.device):
+            check(_lib.load().sc_gather_rows(_ptr(k_norm), k_norm.shape[0], k_norm.shape[1] * k_norm.element_size(),
+                                             _ptr(self.perm), n_out, _ptr(rows), _stream()), "sc_gather_rows")
         self.rows = rows
         return self
 
 
 def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
-    """Index plumbing of the sorted bank (once per cache): stable sort of the keys by label, class segments
-    padded to multiples of 16, the whole bank padded to whole 256-key steps.  Labels outside [0, n_classes)
-    select no class and are dropped (their one-hot row is zero).  Pure index arithmetic: also runs on CPU
-    tensors (tests); the bank it describes is consumed by the CUDA kernel only."""
+    """Layout of the label-sorted bank (once per cache): stable sort of the keys by label, class segments padded
+    to multiples of 16, the whole bank padded to whole 256-key steps.  Labels outside [0, n_classes) select no
+    class and are dropped (their one-hot row is zero).  CUDA labels go through sc_hard_bank_layout; CPU labels
+    (the host-logic tests) through the index arithmetic below, which is also the specification the kernel is
+    tested against."""
+    if labels.is_cuda:
+        return _hard_bank_layout_cuda(labels, n_classes)
+    return _hard_bank_layout_torch(labels, n_classes)
+
+
+def _hard_bank_layout_cuda(labels: torch.Tensor, n_classes: int) -> HardBank:
+    lib = _lib.load()
+    dev = labels.device
+    lab = labels.reshape(-1)
+    n_keys = lab.numel()
+    if lab.dtype != torch.int16:                       # int32 / int64 labels -> int16, invalid -> -1 (sc_hard_labels)
+        lab = hard_labels(None, n_classes, labels=lab)[:n_keys]
+    lab = lab.contiguous()
+    cap = int(lib.sc_hard_bank_capacity(n_keys, n_classes))
+    ws_bytes = int(lib.sc_hard_bank_workspace_bytes(n_keys, n_classes))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    perm = torch.empty(cap, dtype=torch.int64, device=dev)
+    gcls = torch.empty(cap // 16, dtype=torch.int16, device=dev)
+    kbits = torch.empty(cap // 32, dtype=torch.int32, device=dev)
+    n_sorted = torch.empty(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sc_hard_bank_layout(_ptr(lab) if n_keys else None, n_keys, n_classes, _ptr(perm), _ptr(gcls), _ptr(kbits),
+                                      cap, _ptr(n_sorted), ctypes.c_void_p(ws.data_ptr() + off), ws_bytes, _stream()),
+              "sc_hard_bank_layout")
+    ns = int(n_sorted.item())                          # the one host sync of a cache build: sizes the bank
+    steps = max(1, -(-ns // 256))
+    return HardBank(perm[: steps * 256], gcls[: steps * 16], kbits[: steps * 8], ns, n_keys, n_classes)
+
+
+def _hard_bank_layout_torch(labels: torch.Tensor, n_classes: int) -> HardBank:
     dev = labels.device
     lab = labels.reshape(-1).to(torch.int64)
     n_keys = lab.numel()

@@ -346,6 +346,25 @@ def test_hard_label_segmented_kernel(ops, shape):
     assert torch.equal(O0, torch.bincount(labels[valid].long(), minlength=c).float().expand(nq, c))
 
 
+@pytest.mark.parametrize("n_keys,n_classes", [(1, 1), (17, 3), (1000, 37), (5000, 1000), (70000, 397), (2049, 5)])
+def test_sorted_bank_layout_kernel_matches_the_specification(ops, n_keys, n_classes):
+    """sc_hard_bank_layout (stable counting sort on the GPU) == the torch index arithmetic, element for element;
+    sc_gather_rows == index_select with zero padding rows."""
+    g = torch.Generator().manual_seed(84)
+    labels = torch.randint(-1, n_classes + 1, (n_keys,), generator=g).int()
+    want = ops._hard_bank_layout_torch(labels, n_classes)
+    for lab in (labels.cuda(), ops.hard_labels(None, n_classes, labels=labels.cuda())[:n_keys]):
+        got = ops.hard_bank_layout(lab, n_classes)
+        assert got.n_sorted == want.n_sorted and got.n_keys == n_keys
+        assert torch.equal(got.perm.cpu(), want.perm) and torch.equal(got.gcls.cpu(), want.gcls)
+        assert torch.equal(got.kbits.cpu(), want.kbits)
+    rows = torch.randn(n_keys, 64, generator=g).half().cuda()
+    got.gather(rows)
+    ref = rows[got.perm.clamp_min(0)]
+    ref[got.perm < 0] = 0
+    assert torch.equal(got.rows, ref)
+
+
 def test_hard_values_route_through_the_segmented_kernel(ops, monkeypatch):
     """HardCacheStrategy / gold labels / one-hot Tip-Adapter cache values all become a label-sorted bank; the
     dense-values route (SUMMER_CLIP_B200_DENSE_VALUES=1) gives the same logits."""
