@@ -82,68 +82,74 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
 
 // ---- 16-bit feature-major source with contiguous columns and no gather (the key-bank build): ONE pass over HBM.
 // Block = 32 bank columns x all D rows, 512 threads.  Phase A streams the [D x 32] strip into shared memory
-// (pitch 33 halves; 64 contiguous bytes per warp-row, 16 independent loads in flight per warp) while every
-// thread accumulates the sum of squares of its column; phase B writes the 32 output rows (one 2*D_pad-byte
-// contiguous row per column, 128 bytes per warp store) from shared memory, conflict free.  The old kernel
+// stored COLUMN-major (64 contiguous bytes per warp-row from HBM, 16 independent loads in flight per lane; the
+// odd half-pitch makes the 2-byte column stores conflict free) while every thread accumulates the sum of
+// squares of its column; phase B writes the 32 output rows (one 2*D_pad-byte contiguous row per column) with
+// one 4-byte shared load, two multiplies by the reciprocal norm and one 4-byte store per pair.  The old kernel
 // read the strip twice through a 64 x 33 tile with two block barriers per 64 rows and reached 1.5 TB/s.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(512)
 norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d, TO* __restrict__ dst,
                   int64_t D_pad, int normalize) {
-  extern __shared__ uint16_t strip[];            // [D][33]
+  extern __shared__ uint16_t strip[];            // [32 columns][pitch]: column-major, pitch = D_even + 2 halves
   __shared__ float red[16][32];
-  __shared__ float nrm_s[32];
-  constexpr int kPitch = 33;
+  __shared__ float inv_s[32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;             // 0..15
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * 32;
   const bool col_ok = n0 + lane < N;
+  const int pitch = static_cast<int>((D + 1) / 2 * 2 + 2);      // pitch / 2 is odd: lane * pitch / 2 hits 32 banks
   const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + n0 + lane;
+  uint16_t* mycol = strip + lane * pitch;
   float ss = 0.f;
+  // phase A: warp w reads rows d = w, w + 16, ...: 64 contiguous bytes per warp-row, 16 loads in flight per lane
   for (int64_t d0 = warp; d0 < D; d0 += 16 * 16) {
     uint16_t raw[16];
+    const uint16_t* p = s16 + d0 * stride_d;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int64_t d = d0 + 16 * j;
-      raw[j] = (col_ok && d < D) ? __ldg(s16 + d * stride_d) : static_cast<uint16_t>(0);
+      raw[j] = (col_ok && d0 + 16 * j < D) ? __ldg(p) : static_cast<uint16_t>(0);
+      p += 16 * stride_d;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int64_t d = d0 + 16 * j;
       if (d < D) {
-        strip[d * kPitch + lane] = raw[j];
+        mycol[d] = raw[j];
         const float v = sc::to_f32<T>(*reinterpret_cast<const T*>(&raw[j]));
         ss = fmaf(v, v, ss);
       }
     }
   }
+  if ((D & 1) && warp == 0) mycol[D] = 0;        // odd D: the pair partner of the last element
   red[warp][lane] = ss;
   __syncthreads();
   if (warp == 0) {
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) t += red[j][lane];
-    nrm_s[lane] = normalize ? sqrtf(t) : 1.0f;   // the NORM; we divide below like the reference does
+    inv_s[lane] = normalize ? 1.0f / sqrtf(t) : 1.0f;
   }
   __syncthreads();
-  // phase B: warp w writes columns w and w + 16; lane handles d = d0 + 2*lane, +1
+  // phase B: warp w writes the output rows of columns w and w + 16; lane handles the pair d = d0 + 2 lane, +1
+  // (one 4-byte shared load, one 4-byte global store: 128 contiguous bytes per warp)
   for (int c = warp; c < 32; c += 16) {
     const int64_t o = n0 + c;
     if (o >= N) continue;
-    const float nrm = nrm_s[c];
-    TO* orow = dst + o * D_pad;
-    for (int64_t d0 = 0; d0 < D_pad; d0 += 64) {
-      const int64_t d = d0 + 2 * lane;
-      float a = 0.f, b = 0.f;
-      if (d < D) {
-        a = sc::to_f32<T>(*reinterpret_cast<const T*>(&strip[d * kPitch + c]));
-        if (normalize) a = a / nrm;
+    const float inv = inv_s[c];
+    const uint32_t* col32 = reinterpret_cast<const uint32_t*>(strip + c * pitch);
+    uint32_t* orow = reinterpret_cast<uint32_t*>(dst + o * D_pad);
+    const int64_t pairs = (D + 1) / 2;
+    for (int64_t pr = lane; pr < D_pad / 2; pr += 32) {
+      uint32_t out = 0u;
+      if (pr < pairs) {
+        const uint32_t w = col32[pr];
+        const uint16_t lo16 = static_cast<uint16_t>(w & 0xffffu), hi16 = static_cast<uint16_t>(w >> 16);
+        const float a = sc::to_f32<T>(*reinterpret_cast<const T*>(&lo16)) * inv;
+        const float b = sc::to_f32<T>(*reinterpret_cast<const T*>(&hi16)) * inv;
+        out = sc::pack2<TO>(a, b);
       }
-      if (d + 1 < D) {
-        b = sc::to_f32<T>(*reinterpret_cast<const T*>(&strip[(d + 1) * kPitch + c]));
-        if (normalize) b = b / nrm;
-      }
-      *reinterpret_cast<uint32_t*>(orow + d) = sc::pack2<TO>(a, b);
+      orow[pr] = out;
     }
   }
 }
@@ -151,7 +157,7 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
 template <typename T, typename TO>
 int launch_norm_strip(const void* src, int64_t D, int64_t N, int64_t stride_d, void* dst, int64_t D_pad, int normalize,
                       cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(D) * 33 * 2;
+  const size_t smem = static_cast<size_t>(32) * ((D + 1) / 2 * 2 + 2) * 2;
   SC_CUDA(cudaFuncSetAttribute(norm_strip_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   norm_strip_kernel<T, TO><<<static_cast<unsigned>(sc::ceil_div(N, 32)), 512, smem, st>>>(
       static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize);
