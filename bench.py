@@ -193,12 +193,12 @@ def run_ours(args):
         if world == 1:
             z = ops.zero_shot_logits(q_src, True, searcher.text)
             res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)
-            launches["n"] += 2
+            launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
             return res["pred"], torch.stack([res["top1"], res["top5"]])
         o_mine, lo, hi = exchange_partials(o_part, group)
         z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text)
         res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[lo:hi].contiguous())
-        launches["n"] += 2
+        launches["n"] += 3
         counts = torch.stack([res["top1"], res["top5"]])
         dist.all_reduce(counts, group=group)
         mine = torch.zeros((1, per_q), dtype=torch.int32, device=device)
@@ -220,10 +220,28 @@ def run_ours(args):
         pred, counts = finish(q_bank, labels_dev, o)
         return {"pred": pred, "top1": counts[0], "top5": counts[1]}
 
-    def step_e2e():
+    # e2e: the query bank and labels come from pinned host memory every step and the predictions + counters go
+    # back.  The host->device copy of step i+1 is issued on a side stream while step i computes (two device
+    # buffers), as a serving loop would; the first copy of the timed region is fully exposed.
+    copy_stream = torch.cuda.Stream(device=device)
+    q_bufs = [torch.empty_like(q_bank), torch.empty_like(q_bank)]
+    lab_bufs = [torch.empty_like(labels_dev), torch.empty_like(labels_dev)]
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def start_copy(i):
+        with torch.cuda.stream(copy_stream):
+            q_bufs[i % 2].copy_(q_host, non_blocking=True)
+            lab_bufs[i % 2].copy_(labels_host, non_blocking=True)
+            copy_done[i % 2].record(copy_stream)
+
+    def step_e2e(i, n_steps):
         """Host buffers in, host result out: H2D of the query bank, D2H of predictions + counters."""
-        q_dev = q_host.to(device, non_blocking=True)
-        lab = labels_host.to(device, non_blocking=True)
+        if i == 0:
+            start_copy(0)
+        if i + 1 < n_steps:
+            start_copy(i + 1)                       # buffer (i+1) % 2 was last read by step i-1, which has completed
+        torch.cuda.current_stream().wait_event(copy_done[i % 2])
+        q_dev, lab = q_bufs[i % 2], lab_bufs[i % 2]
         qn = ops.normalize_cast(q_dev, True)
         o = attn(qn, True)
         pred, counts = finish(q_dev, lab, o)
@@ -274,12 +292,13 @@ def run_ours(args):
     top1 = int(res["top1"][0])
 
     # ---------------- end-to-end timing (host buffers)
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    n_warm = max(1, args.warmup // 2)
+    for i in range(n_warm):
+        step_e2e(i, n_warm)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        pred, counts = step_e2e()
+    for i in range(args.steps):
+        pred, counts = step_e2e(i, args.steps)
     sync_all()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
