@@ -137,6 +137,27 @@ class ClipSearcher:
         self.gpu_launches += 2 + int(softmax_normalize)
         self.rowsum_col = self.n_classes if softmax_normalize else None
 
+    def save_bank(self, directory, key: str = ""):
+        """Write the resident label-sorted bank as a sidecar directory (bank_io.save_hard_bank)."""
+        from . import bank_io
+        if self.hard_bank is None:
+            raise ops._lib.SummerClipError("save_bank: only one-hot (label-sorted) caches have a sidecar format")
+        return bank_io.save_hard_bank(self.hard_bank, directory, key)
+
+    def load_bank(self, directory, key: tp.Optional[str] = None) -> bool:
+        """Make a sidecar bank resident instead of calling set_cache.  False (nothing changed) if it is absent or
+        was built for another key."""
+        from . import bank_io
+        bank = bank_io.load_hard_bank(directory, self.device, key)
+        if bank is None:
+            return False
+        if bank.rows.dtype != self.op_dtype:
+            return False
+        self.hard_bank, self.k_norm, self.vt, self.rowsum_col = bank, None, None, None
+        self.n_keys = self.n_keys_global = bank.n_keys
+        self.n_classes = bank.n_classes
+        return True
+
     # ------------------------------------------------------------------ queries
     def prepare_queries(self, test_image_features: torch.Tensor, feature_major: bool = True):
         """H2D (if needed) + normalise/cast + zero-shot logits.  Returns (Qn, Z or None)."""

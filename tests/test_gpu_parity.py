@@ -418,6 +418,23 @@ def test_zero_shot_logits_tensor_core_route(ops, shape):
     assert (raw.double() - Xd @ T.double()).abs().max().item() < 1e-4 * max(1.0, float(Xd.abs().max()) * D ** 0.5)
 
 
+def test_sidecar_bank_gives_the_same_search(ops, tmp_path):
+    """ClipSearcher.save_bank / load_bank (bank_io sidecar): identical predictions and logits."""
+    from summer_clip_b200.searcher import ClipSearcher
+    banks = orc.synthetic_banks(300, 3000, 256, 40, seed=85, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    a = ClipSearcher("cuda")
+    a.set_text(T.float())
+    a.set_cache(K, L)
+    ra = a.search(Q, [5.5], [1.0], labels=banks["test_labels"], want_logits=True)[0]
+    a.save_bank(tmp_path / "bank", key="k1")
+    b = ClipSearcher("cuda")
+    b.set_text(T.float())
+    assert not b.load_bank(tmp_path / "bank", key="k2") and b.load_bank(tmp_path / "bank", key="k1")
+    rb = b.search(Q, [5.5], [1.0], labels=banks["test_labels"], want_logits=True)[0]
+    assert torch.equal(ra["logits"], rb["logits"]) and torch.equal(ra["pred"], rb["pred"])
+
+
 def test_cpu_tensors_are_rejected(ops):
     from summer_clip_b200._lib import SummerClipError
     with pytest.raises(SummerClipError):

@@ -34,3 +34,29 @@ def test_layout_invariants(n_keys, n_classes, seed):
     unpacked = ((bits[:, None] >> np.arange(32)[None, :]) & 1).reshape(-1).astype(bool)
     assert np.array_equal(unpacked, perm >= 0)                                     # bit j of word w = key 32 w + j
     assert np.all(perm[bank.n_sorted:] == -1)
+
+
+def test_sidecar_round_trip(tmp_path):
+    """bank_io: a gathered bank survives save -> load bit for bit; a sidecar built for another key is refused."""
+    from summer_clip_b200 import bank_io, ops
+    g = torch.Generator().manual_seed(9)
+    labels = torch.randint(0, 7, (300,), generator=g).int()
+    bank = ops.hard_bank_layout(labels, 7)
+    rows = torch.randn(300, 64, generator=g).half()
+    src = bank.perm.clamp_min(0)
+    bank.rows = rows[src]
+    bank.rows[bank.perm < 0] = 0
+    feats = tmp_path / "features.pt"
+    torch.save(rows, feats)
+    key = bank_io.bank_key([feats], 7, torch.float16, idx=torch.arange(300))
+    assert key != bank_io.bank_key([feats], 8, torch.float16, idx=torch.arange(300))
+    assert key != bank_io.bank_key([feats], 7, torch.float16, idx=torch.arange(299))
+    d = bank_io.save_hard_bank(bank, tmp_path / "bank", key)
+    back = bank_io.load_hard_bank(d, "cpu", key)
+    assert back is not None and back.n_sorted == bank.n_sorted and back.n_keys == 300 and back.n_classes == 7
+    for a, b in ((back.rows, bank.rows), (back.perm, bank.perm), (back.gcls, bank.gcls), (back.kbits, bank.kbits)):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+    assert bank_io.load_hard_bank(d, "cpu", "another-key") is None
+    assert bank_io.load_hard_bank(tmp_path / "missing", "cpu") is None
+    bank_io.save_hard_bank(bank, tmp_path / "bank", key)                      # overwrite in place
+    assert bank_io.load_hard_bank(d, "cpu", key) is not None
