@@ -225,6 +225,27 @@ class ClipSearcher:
             results.append(res)
         return results
 
+    def capture_search(self, test_image_features: torch.Tensor, betas: tp.Sequence[float], alphas: tp.Sequence[float],
+                       labels: tp.Optional[torch.Tensor] = None, feature_major: bool = True, warmup: int = 3):
+        """Capture one `search` for a FIXED query-batch shape into a CUDA graph (online serving: a small batch is a
+        dozen ~10 us kernels plus, when key-sharded, three small NCCL calls, so launch latency dominates).
+        Returns (graph, results): copy new queries / labels INTO the given tensors (they are the graph's static
+        inputs), `graph.replay()`, read the tensors in `results`.  Works on one rank and under a process group
+        (NCCL collectives are captured; every rank must replay)."""
+        q = test_image_features
+        assert q.is_cuda and (labels is None or labels.is_cuda), "static inputs must live on the device"
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                               # allocator / NCCL warm-up outside the capture
+                self.search(q, betas, alphas, labels=labels, feature_major=feature_major)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            results = self.search(q, betas, alphas, labels=labels, feature_major=feature_major)
+        return graph, results
+
     def _search_sharded(self, test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred):
         """Key-sharded `search`: every rank scores ALL queries against its key shard, one reduce-scatter sums
         the partial tiles and hands each rank its query slice, which it finishes alone (zero-shot logits,
