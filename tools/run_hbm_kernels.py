@@ -1,0 +1,28 @@
+"""One launch of every HBM-bound kernel of the path at the BASELINE sizes (1 281 167 x 1000 logits bank, 1024 x
+1 281 167 fp16 key bank) — the command profiled with ncu for profiles/*_hbm_kernels_ncu.csv."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from summer_clip_b200 import build as _build, ops
+
+_build.build_library()
+dev = torch.device("cuda")
+n, c, dim = 1281167, 1000, 1024
+g = torch.Generator(device=dev).manual_seed(4)
+for dtype in (torch.float16, torch.float32):
+    L = (0.25 + 0.02 * torch.randn(n, c, generator=g, device=dev)).to(dtype)
+    for _ in range(2):                                    # second round = warm instruction cache, same traffic
+        conf, label = ops.rowconf(L, prob=False)
+        confp, _ = ops.rowconf(L, scale=100.00000762939453, prob=True)
+        lab16 = ops.hard_labels(L, c)
+        idx = ops.select_topk_per_label(confp, label, c, 16)
+    del L
+bank = torch.randn(dim, n, device=dev, dtype=torch.float16)
+for _ in range(2):
+    kn = ops.normalize_cast(bank, True)
+    layout = ops.hard_bank_layout(lab16[:n], c).gather(kn)
+torch.cuda.synchronize()
+print("ok", idx.numel(), layout.n_sorted)
