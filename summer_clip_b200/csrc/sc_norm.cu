@@ -103,16 +103,17 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
   uint16_t* mycol = strip + lane * pitch;
   float ss = 0.f;
   // phase A: warp w reads rows d = w, w + 16, ...: 64 contiguous bytes per warp-row, 16 loads in flight per lane
-  for (int64_t d0 = warp; d0 < D; d0 += 16 * 16) {
-    uint16_t raw[16];
+  constexpr int kU = 16;                         // loads in flight per lane (32 measured the same: not latency bound)
+  for (int64_t d0 = warp; d0 < D; d0 += 16 * kU) {
+    uint16_t raw[kU];
     const uint16_t* p = s16 + d0 * stride_d;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < kU; ++j) {
       raw[j] = (col_ok && d0 + 16 * j < D) ? __ldg(p) : static_cast<uint16_t>(0);
       p += 16 * stride_d;
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < kU; ++j) {
       const int64_t d = d0 + 16 * j;
       if (d < D) {
         mycol[d] = raw[j];

@@ -435,6 +435,26 @@ def test_sidecar_bank_gives_the_same_search(ops, tmp_path):
     assert torch.equal(ra["logits"], rb["logits"]) and torch.equal(ra["pred"], rb["pred"])
 
 
+def test_cuda_graph_replay_of_a_search(ops):
+    """ClipSearcher.capture_search: new queries copied into the static inputs + graph.replay() == eager search."""
+    from summer_clip_b200.searcher import ClipSearcher
+    banks = orc.synthetic_banks(64, 3000, 256, 40, seed=86, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    s = ClipSearcher("cuda")
+    s.set_text(T.float())
+    s.set_cache(K, L)
+    q_static = Q[:, :32].contiguous().cuda()
+    lab_static = banks["test_labels"][:32].int().cuda()
+    graph, res = s.capture_search(q_static, [5.5], [1.0, 2.0], labels=lab_static)
+    for lo in (0, 32):
+        q_static.copy_(Q[:, lo:lo + 32])
+        lab_static.copy_(banks["test_labels"][lo:lo + 32])
+        graph.replay()
+        torch.cuda.synchronize()
+        eager = s.search(Q[:, lo:lo + 32].contiguous(), [5.5], [1.0, 2.0], labels=banks["test_labels"][lo:lo + 32])[0]
+        assert torch.equal(res[0]["pred"], eager["pred"]) and torch.equal(res[0]["top1"], eager["top1"])
+
+
 def test_cpu_tensors_are_rejected(ops):
     from summer_clip_b200._lib import SummerClipError
     with pytest.raises(SummerClipError):
