@@ -13,6 +13,10 @@
 // weight slots shrink to 16 KB and the operand ring grows to 6 stages.  (Measured on the non-transposed
 // pair kernel: the 32 KB x 3 exchange per tile sits on a serial chain with single-buffered slots and
 // costs ~75 ms of a 309 ms pass.)
+// The fused probe+issue loops of sc_attn_seg.cu (sc_ptx.cuh: umma4_cg2_probe / tma2_cg2_probe) were tried here too:
+// they cut the cycle count by 10 % but the kernel already sits at the board's power limit with the tensor pipe
+// half idle, so the clock fell from 1.96 to 1.55 GHz and the pass got slower (297 -> 337-342 ms, same GPU, same
+// call: profiles/r01e_ab_dense_kernels.log).  This file keeps the plain wait-then-issue loops.
 #include "sc_common.cuh"
 #include "sc_ptx.cuh"
 
@@ -27,16 +31,12 @@ constexpr int kBQ = 128;             // queries per cluster tile (UMMA N)
 constexpr int kBN = 128;             // keys per tile = TMEM lanes of S^T
 constexpr int kBK = 64;              // 16-bit elements per swizzled smem row
 constexpr int kSub = 24576;          // one 64-wide K chunk: Kn chunk 16 KB + Qn half 8 KB
-// A ring stage holds one K chunk for GEMM-1 / one Vt box (128 classes x 64 keys) for GEMM-2.  (Two chunks per
-// stage halved the barrier round trips but left only 3 stages in flight against ~1-2 us of TMA latency and
-// was slower end to end; the fused probe+issue loops below remove the round-trip cost instead.)
+// A ring stage holds CPS (1 or 2) K chunks for GEMM-1 / the Vt boxes of CPS 128-class blocks for GEMM-2.
+// CPS = 2 halves the barrier round trips (measured: on-chip time 250 -> 165 ms) but leaves only 3 stages in
+// flight against ~2 us of loaded TMA latency (full pass 296 -> 321 ms); CPS = 1 is the default.
 constexpr int kHalf = 16384;         // half of a weight tile: [128 keys x 64 queries] MN-major SW128
 constexpr int kThreads = 192;
 constexpr int kExpThreads = 128;
-// Warp roles.  The two single-thread issue loops (TMA producer, MMA issuer) take the HIGHEST warp ids: the
-// SM sub-partition arbiter favours higher warp ids, and each loop shares its sub-partition with one exp warp.
-constexpr int kProducerWarp = 4;
-constexpr int kMmaWarp = 5;
 constexpr int kTmemCols = 512;       // S^T0 @0, S^T1 @128, O^T blocks @256 (+128)
 constexpr int kColO = 256;
 constexpr int kMaxStages = 8;
@@ -58,7 +58,6 @@ struct TParams {
   float c1, c0, o_scale;
   float* O;
   long long ldo;
-  unsigned long long* clk;   // experiments builds: {sum of CTA cycles, sum of CTA ns, CTAs} -> effective SM clock
 };
 
 struct Bars {
@@ -88,12 +87,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <bool kF16, int NPAIR>
+template <bool kF16, int NPAIR, int CPS>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const TParams p) {
   constexpr int CS = 2 * NPAIR;                                            // cluster size
-  constexpr int kStage = kSub;
+  constexpr int kStage = CPS * kSub;
   constexpr int NS = (kSmemPayload - (CS + 1) * kHalf) / kStage;           // 6 (CS=4) / 7 (CS=2) stages
   static_assert(NS <= kMaxStages && NS >= 2, "ring depth");
   extern __shared__ uint8_t smem_raw[];
@@ -103,9 +102,7 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t stag0 = slot0 + CS * kHalf;                               // the other half of MY tile
   Bars* bars = reinterpret_cast<Bars*>(smem_raw + (stag0 - raw_addr) + kHalf);
 
-  // warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role loops' state
-  // (ring stage, phases, descriptors) in uniform registers instead of converting it per UMMA / TMA issue
-  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();        // == blockIdx.x % CS
   const int h = static_cast<int>(rank & 1);       // which 64-query half of P^T this CTA feeds to its pair
@@ -124,15 +121,7 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int n_mb = p.n_mb;
   const int pair_first = static_cast<int>(leader);   // round r is active for my pair iff r*CS + pair_first < T
 
-#ifdef SC_ATTN_TIMING_EXPERIMENTS
-  long long clk_c0 = 0;
-  unsigned long long clk_t0 = 0;
-  if (p.clk != nullptr && threadIdx.x == 0) {
-    clk_c0 = clock64();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(clk_t0));
-  }
-#endif
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
@@ -152,7 +141,7 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(smem_u32(&bars->o_full), 1);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == 1) {
     tmem_alloc2(smem_u32(&bars->tmem_slot), kTmemCols);
     tmem_relinquish2();
   }
@@ -163,30 +152,13 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t xbytes = (p.dbg & 64) ? 1024u : static_cast<uint32_t>(kHalf);   // exchange unit
 
-  if (warp == kProducerWarp) {
+  if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; warp-uniform, elected issue)
-    // Per ring stage: (blocking wait only if the previous probe failed) -> fused [probe next slot's empty
-    // barrier | expect_tx | TMA loads].
     int stage = 0;
-    uint32_t phase = 0, ready = 0;
+    uint32_t phase = 0;
     const uint32_t full0 = smem_u32(&bars->full[0]);
     const uint32_t full0c = mapa(full0, leader);
     const uint32_t empty0 = smem_u32(&bars->empty[0]);
-    const uint32_t kon = (p.dbg & 4) ? 0u : 1u, qon = (p.dbg & 1) ? 0u : 1u, von = (p.dbg & 2) ? 0u : 1u;
-    const uint32_t tx1 = is_leader ? 2u * (kon * 16384u + qon * 8192u) : 0u;      // both CTAs' bytes
-    const uint32_t tx2 = is_leader ? 2u * von * 16384u : 0u;
-    const uint32_t plain1 = (is_leader && tx1 == 0u) ? 1u : 0u, plain2 = (is_leader && tx2 == 0u) ? 1u : 0u;
-    auto issue = [&](const CUtensorMap* m0, int x0, int y0, uint32_t on0, const CUtensorMap* m1, int x1, int y1,
-                     uint32_t on1, uint32_t tx, uint32_t plain) {
-      if (!ready) mbar_wait(empty0 + stage * 8, phase ^ 1u);
-      const bool wrap = (stage + 1 == NS);
-      const uint32_t dst = ring0 + stage * kStage;
-      ready = __all_sync(0xffffffffu, tma2_cg2_probe(dst, m0, x0, y0, on0, dst + 16384, m1, x1, y1, on1,
-                                                     full0c + stage * 8, full0 + stage * 8, tx, plain,
-                                                     empty0 + (wrap ? 0 : stage + 1) * 8,
-                                                     (wrap ? phase ^ 1u : phase) ^ 1u));
-      if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
-    };
     auto load_v_round = [&](int rr) {
 #pragma unroll 1
       for (int src = 0; src < CS; ++src) {
@@ -195,8 +167,22 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < kBN / kBK; ++c) {
 #pragma unroll 1
-          for (int mb = 0; mb < n_mb; ++mb)     // my 128 classes x 64 keys
-            issue(&tmV, (t0 + i) * kBN + c * kBK, c0 + mb * 128, von, &tmV, 0, 0, 0u, tx2, plain2);
+          for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
+            const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
+            mbar_wait(empty0 + stage * 8, phase ^ 1u);
+            if (elect_one()) {
+              if (p.dbg & 2) {
+                if (is_leader) mbar_arrive(full0 + stage * 8);
+              } else {
+                if (is_leader) mbar_arrive_expect_tx(full0 + stage * 8, 2u * 16384u * static_cast<uint32_t>(nblk));
+                for (int u = 0; u < nblk; ++u)
+                  tma_load_2d_cg2(ring0 + stage * kStage + u * kSub, &tmV, full0c + stage * 8,
+                                  (t0 + i) * kBN + c * kBK, c0 + (mb0 + u) * 128);     // my classes x 64 keys
+              }
+            }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     };
@@ -205,13 +191,29 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (r * CS + pair_first < T) {
         const int krow = (t0 + r * CS + static_cast<int>(rank)) * kBN;   // my key tile (may be past the split: unused)
 #pragma unroll 1
-        for (int d = 0; d < nd; ++d)            // 128 keys x 64 d  +  64 queries x 64 d
-          issue(&tmK, d * kBK, krow, kon, &tmQ, d * kBK, q0 + h * 64, qon, tx1, plain1);
+        for (int d = 0; d < nd; d += CPS) {
+          const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
+          mbar_wait(empty0 + stage * 8, phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t kb = (p.dbg & 4) ? 0u : 16384u, qb = (p.dbg & 1) ? 0u : 8192u;
+            if (is_leader) {
+              if (kb + qb) mbar_arrive_expect_tx(full0 + stage * 8, 2u * (kb + qb) * static_cast<uint32_t>(nsub));
+              else mbar_arrive(full0 + stage * 8);
+            }
+            for (int u = 0; u < nsub; ++u) {
+              const uint32_t dst = ring0 + stage * kStage + u * kSub;
+              if (kb) tma_load_2d_cg2(dst, &tmK, full0c + stage * 8, (d + u) * kBK, krow);                  // 128 keys
+              if (qb) tma_load_2d_cg2(dst + 16384, &tmQ, full0c + stage * 8, (d + u) * kBK, q0 + h * 64);   // 64 queries
+            }
+          }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
       }
       if (r > 0) load_v_round(r - 1);
     }
     if (R > 0) load_v_round(R - 1);
-  } else if (warp == kMmaWarp) {
+  } else if (warp == 1) {
     const uint32_t pfull0 = smem_u32(&bars->p_full[0]);
     const uint32_t ppeer0 = smem_u32(&bars->p_peer[0]);
     if (elect_one()) {                      // arm the half-slots fed by the other CTAs for round 0
@@ -221,30 +223,14 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncwarp();
     if (is_leader) {
       // ===================================================== MMA issuer for the pair
-      // Per ring stage: (blocking wait only if the previous probe failed) -> fused [probe next slot's full
-      // barrier | 4 pair UMMAs | commit(s)].
       int stage = 0;
-      uint32_t phase = 0, ready = 0;
+      uint32_t phase = 0;
       const uint32_t idesc1 = umma_idesc_16b(256, kBQ, kF16);                 // A, B K-major
       const uint32_t idesc2 = umma_idesc_16b(256, kBQ, kF16) | (1u << 16);    // B (P^T) MN-major
       const uint32_t tmem_o = tmem_base + kColO;
       const uint32_t full0 = smem_u32(&bars->full[0]);
       const uint32_t empty0 = smem_u32(&bars->empty[0]);
       const uint32_t pempty = smem_u32(&bars->p_empty);
-      const uint32_t en1 = (p.dbg & 16) ? 0u : 1u, en2 = (p.dbg & 32) ? 0u : 1u;
-      // a_step / b_step: descriptor increment per 16-element K step
-      auto issue = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t a_step, uint64_t b_desc, uint32_t b_step,
-                       uint32_t idesc, uint32_t acc0, uint32_t enable, uint32_t bar2, uint16_t mask2, uint32_t flag2) {
-        if (!ready) mbar_wait(full0 + stage * 8, phase);
-        tc_fence_after();
-        const bool wrap = (stage + 1 == NS);
-        ready = __all_sync(0xffffffffu,
-                           umma4_cg2_probe(d_tmem, a_desc, a_desc + a_step, a_desc + 2 * a_step, a_desc + 3 * a_step,
-                                           b_desc, b_desc + b_step, b_desc + 2 * b_step, b_desc + 3 * b_step, idesc,
-                                           acc0, enable, empty0 + stage * 8, pair_mask, bar2, mask2, flag2,
-                                           full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
-        if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
-      };
       auto gemm2_round = [&](int rr) {
 #pragma unroll 1
         for (int src = 0; src < CS; ++src) {
@@ -252,19 +238,34 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (i >= T) break;
           mbar_wait(pfull0 + src * 8, rr & 1);
           mbar_wait(ppeer0 + src * 8, rr & 1);
+          tc_fence_after();
           if (src != static_cast<int>(rank) && i + CS < T) {
             if (elect_one()) mbar_arrive_expect_tx(pfull0 + src * 8, xbytes);
             __syncwarp();
           }
 #pragma unroll 1
           for (int c = 0; c < kBN / kBK; ++c) {
-            const uint64_t b_desc = umma_desc_k128(slot0 + src * kHalf + c * 8192);              // P^T rows 64c..
 #pragma unroll 1
-            for (int mb = 0; mb < n_mb; ++mb) {
-              const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage);                    // Vt box, K-major
-              // A: +32 B per 16 keys; B: +16 key rows = +2048 B.  Last chunk of this source: release its slot.
-              issue(tmem_o + mb * 128, a_desc, 2u, b_desc, 128u, idesc2, (i | c) != 0 ? 1u : 0u, en2, pempty,
-                    static_cast<uint16_t>(1u << src), (c == kBN / kBK - 1 && mb == n_mb - 1) ? 1u : 0u);
+            for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
+              const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
+              mbar_wait(full0 + stage * 8, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t b_desc = umma_desc_k128(slot0 + src * kHalf + c * 8192);            // P^T rows 64c..
+                for (int u = 0; u < nblk; ++u) {
+                  const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage + u * kSub);       // Vt box, K-major
+#pragma unroll
+                  for (int k = 0; k < kBK / 16; ++k)       // A: +32 B per 16 keys; B: +16 key rows = +2048 B
+                    if (!(p.dbg & 32))
+                      umma_ss2(tmem_o + (mb0 + u) * 128, a_desc + 2 * k, b_desc + 128 * k, idesc2,
+                               (i | c | k) != 0 ? 1u : 0u);
+                }
+                umma_commit2_mcast(empty0 + stage * 8, pair_mask);
+                if (c == kBN / kBK - 1 && mb0 + CPS >= n_mb)      // this pair is done with source src's tile
+                  umma_commit2_mcast(pempty, static_cast<uint16_t>(1u << src));
+              }
+              __syncwarp();
+              if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -275,13 +276,28 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (r * CS + pair_first < T) {
           const int sb = own & 1;
           mbar_wait(smem_u32(&bars->s_empty[sb]), ((own >> 1) & 1) ^ 1u);
+          tc_fence_after();
           const uint32_t tmem_s = tmem_base + sb * 128;
-          const uint32_t sfull = smem_u32(&bars->s_full[sb]);
 #pragma unroll 1
-          for (int d = 0; d < nd; ++d) {
-            const uint32_t a_addr = ring0 + stage * kStage;
-            issue(tmem_s, umma_desc_k128(a_addr), 2u, umma_desc_k128(a_addr + 16384), 2u, idesc1, d != 0 ? 1u : 0u, en1,
-                  sfull, pair_mask, d == nd - 1 ? 1u : 0u);
+          for (int d = 0; d < nd; d += CPS) {
+            const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
+            mbar_wait(full0 + stage * 8, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int u = 0; u < nsub; ++u) {
+                const uint32_t a_addr = ring0 + stage * kStage + u * kSub;
+                const uint64_t a_desc = umma_desc_k128(a_addr);              // K chunk (my 128 keys)
+                const uint64_t b_desc = umma_desc_k128(a_addr + 16384);      // Q half (64 queries)
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  if (!(p.dbg & 16))
+                    umma_ss2(tmem_s, a_desc + 2 * k, b_desc + 2 * k, idesc1, (d | u | k) != 0 ? 1u : 0u);
+              }
+              umma_commit2_mcast(empty0 + stage * 8, pair_mask);
+              if (d + CPS >= nd) umma_commit2_mcast(smem_u32(&bars->s_full[sb]), pair_mask);
+            }
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
           ++own;
         }
@@ -361,7 +377,7 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (has_tile) {
         fence_proxy_async_smem();
         named_bar_sync(1, kExpThreads);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 64) {
           const uint32_t pf = smem_u32(&bars->p_full[rank]);
           mbar_arrive(pf);                                                   // my own half-slot
           bulk_copy_to_peer(mapa(my_slot, rank ^ 1u), stag0, xbytes, mapa(pf, rank ^ 1u));          // partner: other half
@@ -401,27 +417,18 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-#ifdef SC_ATTN_TIMING_EXPERIMENTS
-  if (p.clk != nullptr && threadIdx.x == 0) {
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    atomicAdd(p.clk, static_cast<unsigned long long>(clock64() - clk_c0));
-    atomicAdd(p.clk + 1, t1 - clk_t0);
-    atomicAdd(p.clk + 2, 1ull);
-  }
-#endif
   cluster_sync_all();
-  if (warp == kMmaWarp) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, kTmemCols);
   }
 }
 
 // 16-bit row-major [rows, cols]; box = [box_rows x 64 cols], SW128 (own copy: box shapes differ per kernel)
-template <bool kF16, int NPAIR>
+template <bool kF16, int NPAIR, int CPS>
 int launch_t(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
              const TParams& p) {
-  auto kernel = sc_attn_t_kernel<kF16, NPAIR>;
+  auto kernel = sc_attn_t_kernel<kF16, NPAIR, CPS>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -439,23 +446,7 @@ int launch_t(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorM
   return SC_OK;
 }
 
-#ifdef SC_ATTN_TIMING_EXPERIMENTS
-unsigned long long* g_clk = nullptr;
-#endif
-
 }  // namespace
-
-#ifdef SC_ATTN_TIMING_EXPERIMENTS
-// experiments builds only: effective SM clock seen by the attention CTAs since the last call (MHz), then reset
-extern "C" double sc_debug_attn_clock_mhz(void) {
-  if (g_clk == nullptr) return 0.0;
-  unsigned long long h[3] = {0, 0, 0};
-  cudaDeviceSynchronize();
-  cudaMemcpy(h, g_clk, sizeof(h), cudaMemcpyDeviceToHost);
-  cudaMemset(g_clk, 0, sizeof(h));
-  return h[1] ? 1e3 * static_cast<double>(h[0]) / static_cast<double>(h[1]) : 0.0;
-}
-#endif
 
 namespace sc {
 
@@ -484,24 +475,23 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
   p.O = O;
   p.ldo = ldo;
   p.dbg = 0;
-  p.clk = nullptr;
 #ifdef SC_ATTN_TIMING_EXPERIMENTS   // never in the shipped library: skipping work gives wrong results
   if (const char* env = std::getenv("SC_ATTN_DEBUG_SKIP")) p.dbg = std::atoi(env);
-  if (std::getenv("SC_ATTN_CLKPROBE")) {
-    if (g_clk == nullptr) {
-      SC_CUDA(cudaMalloc(&g_clk, 3 * sizeof(unsigned long long)));
-      SC_CUDA(cudaMemset(g_clk, 0, 3 * sizeof(unsigned long long)));
-    }
-    p.clk = g_clk;
-  }
 #endif
   dim3 grid(static_cast<unsigned>(n_slices), static_cast<unsigned>(ceil_div(Nq, kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: too many query tiles; chunk the queries");
-  if (n_slices == 2) {
-    rc = f16 ? launch_t<true, 1>(grid, st, tmQ, tmK, tmV, p) : launch_t<false, 1>(grid, st, tmQ, tmK, tmV, p);
-  } else {
-    rc = f16 ? launch_t<true, 2>(grid, st, tmQ, tmK, tmV, p) : launch_t<false, 2>(grid, st, tmQ, tmK, tmV, p);
+  int cps = 1;
+  if (const char* env = std::getenv("SC_ATTN_T_CHUNKS")) {        // tuning knob: K chunks per ring stage
+    if (std::atoi(env) == 2) cps = 2;
   }
+#define SC_T_LAUNCH(F, NPV)                                                                       \
+  (cps == 2 ? launch_t<F, NPV, 2>(grid, st, tmQ, tmK, tmV, p) : launch_t<F, NPV, 1>(grid, st, tmQ, tmK, tmV, p))
+  if (n_slices == 2) {
+    rc = f16 ? SC_T_LAUNCH(true, 1) : SC_T_LAUNCH(false, 1);
+  } else {
+    rc = f16 ? SC_T_LAUNCH(true, 2) : SC_T_LAUNCH(false, 2);
+  }
+#undef SC_T_LAUNCH
   return rc;
 }
 
