@@ -191,12 +191,12 @@ def run_ours(args):
         and hands every rank ITS query slice, which it finishes alone; predictions are all-gathered and the
         counters all-reduced (searcher.exchange_partials / ClipSearcher._search_sharded)."""
         if world == 1:
-            z = ops.zero_shot_logits(q_src, True, searcher.text)
+            z = ops.zero_shot_logits(q_src, True, searcher.text, t_split=searcher.text_split)
             res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)
             launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
             return res["pred"], torch.stack([res["top1"], res["top5"]])
         o_mine, lo, hi = exchange_partials(o_part, group)
-        z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text)
+        z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text, t_split=searcher.text_split)
         res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[lo:hi].contiguous())
         launches["n"] += 3
         counts = torch.stack([res["top1"], res["top5"]])

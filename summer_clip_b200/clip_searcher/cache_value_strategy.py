@@ -7,6 +7,7 @@ tensor-core layout the attention kernel's GEMM-2 consumes) instead of a dense [N
 from __future__ import annotations
 
 import typing as tp
+import weakref
 from abc import ABC, abstractmethod
 
 import torch
@@ -37,10 +38,13 @@ class CacheValues:
     def hard_bank(self, k_norm: torch.Tensor) -> "ops.HardBank":
         """The label-sorted copy of the normalised key bank `k_norm` for these one-hot values (built once per
         (values, bank) pair; the reference loop reuses both across betas, image_attention.py:106-109)."""
-        key = (k_norm.data_ptr(), tuple(k_norm.shape), k_norm.dtype, k_norm._version)
-        if self._bank is None or self._bank_key != key:
+        # identity of the bank = the tensor OBJECT (weak reference) + its version; an address is not an identity
+        # (the allocator hands a freed bank's address to the next tensor of the same shape)
+        same = (self._bank is not None and self._bank_key is not None and self._bank_key[0]() is k_norm
+                and self._bank_key[1] == k_norm._version)
+        if not same:
             layout = self._bank if self._bank is not None else ops.hard_bank_layout(self.labels16[: self.n_keys], self.n_classes)
-            self._bank, self._bank_key = layout.gather(k_norm), key
+            self._bank, self._bank_key = layout.gather(k_norm), (weakref.ref(k_norm), k_norm._version)
         return self._bank
 
     def vt(self, op_dtype: torch.dtype) -> torch.Tensor:

@@ -9,6 +9,7 @@ runs unmodified on top of it.
 from __future__ import annotations
 
 import typing as tp
+import weakref
 from abc import ABC, abstractmethod
 
 import torch
@@ -23,7 +24,9 @@ class _BankCache:
     re-normalise them 8 times per cache."""
 
     def __init__(self, max_items: int = 4) -> None:
-        self._items: tp.List[tp.Tuple[tuple, torch.Tensor]] = []
+        # (key, weak reference to the SOURCE tensor, normalised bank): the key alone is not an identity — a freed
+        # bank's address is routinely handed to the next tensor of the same shape by the caching allocator
+        self._items: tp.List[tp.Tuple[tuple, tp.Any, torch.Tensor]] = []
         self._max = max_items
 
     @staticmethod
@@ -32,11 +35,12 @@ class _BankCache:
 
     def get(self, t: torch.Tensor, feature_major: bool, dtype: torch.dtype) -> torch.Tensor:
         key = self._key(t, feature_major, dtype)
-        for k, v in self._items:
-            if k == key:
+        self._items = [it for it in self._items if it[1]() is not None]          # drop banks whose source died
+        for k, ref, v in self._items:
+            if k == key and ref() is t:
                 return v
         out = ops.normalize_cast(t, feature_major=feature_major, op_dtype=dtype)
-        self._items.append((key, out))
+        self._items.append((key, weakref.ref(t), out))
         if len(self._items) > self._max:
             self._items.pop(0)
         return out

@@ -401,26 +401,18 @@ def gemm_split_nt(a: Tuple[torch.Tensor, torch.Tensor], b: Tuple[torch.Tensor, t
     return out
 
 
-_TEXT_SPLITS: list = []      # (key, (hi, lo)) of recently used classifiers T^T (a run has one or two)
-
-
-def _text_split(T: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    key = (T.data_ptr(), tuple(T.shape), tuple(T.stride()), T.dtype, T._version, T.device)
-    for k, v in _TEXT_SPLITS:
-        if k == key:
-            return v
-    v = normalize_split(T, feature_major=True, normalize=False)      # T is [D, C]: rows of T^T, as given
-    _TEXT_SPLITS.append((key, v))
-    if len(_TEXT_SPLITS) > 4:
-        _TEXT_SPLITS.pop(0)
-    return v
+def text_split(T: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Split-fp16 rows of T^T for a classifier T [D, C] (as given: not re-normalised)."""
+    return normalize_split(T, feature_major=True, normalize=False)
 
 
 def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scale: float = 100.0,
-                     normalize: bool = True, tensor_cores: Optional[bool] = None) -> torch.Tensor:
+                     normalize: bool = True, tensor_cores: Optional[bool] = None,
+                     t_split: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """Z = scale * normalise(X)^T @ T in fp32 (image_attention.py:80-83).  T is [D, C].  Default route: split-fp16
     operands on the tensor cores (`normalize_split` + `gemm_split_nt`); `tensor_cores=False` (or
-    SUMMER_CLIP_B200_ZS_SIMT=1) selects the fp32 SIMT kernel (A/B runs, cross-check in the tests)."""
+    SUMMER_CLIP_B200_ZS_SIMT=1) selects the fp32 SIMT kernel (A/B runs, cross-check in the tests).  `t_split` =
+    `text_split(T)` computed once by the caller (ClipSearcher does) saves two tiny launches per call."""
     _cuda(X, "X"), _cuda(T, "T")
     if feature_major:
         D, N = X.shape
@@ -432,7 +424,7 @@ def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scal
     if tensor_cores is None:
         tensor_cores = not os.environ.get("SUMMER_CLIP_B200_ZS_SIMT")
     if tensor_cores and N > 0:
-        return gemm_split_nt(normalize_split(X, feature_major, normalize), _text_split(T), scale)
+        return gemm_split_nt(normalize_split(X, feature_major, normalize), t_split if t_split is not None else text_split(T), scale)
     if T.stride(1) != 1:
         T = T.contiguous()
     C = T.shape[1]

@@ -61,7 +61,16 @@ def exchange_partials(part: torch.Tensor, group: tp.Any) -> tp.Tuple[torch.Tenso
 
 class ClipSearcher:
     def __init__(self, device: tp.Union[str, torch.device] = "cuda", op_dtype: tp.Optional[torch.dtype] = None,
-                 group: tp.Optional[tp.Any] = None) -> None:
+                 group: tp.Optional[tp.Any] = None, shard: str = "keys") -> None:
+        """`group`: a torch.distributed process group (one rank per GPU).  `shard`: what the ranks split —
+        "keys" (each rank keeps a contiguous slice of the key bank and scores every query against it; one
+        reduce-scatter per beta; the choice for large banks and small-batch latency) or "queries" (each rank keeps
+        the WHOLE bank and scores its slice of the queries; no data-path collective at all, only the predictions
+        are all-gathered and the counters all-reduced; the choice for many queries against a small cache such as
+        Tip-Adapter's 16-shot one)."""
+        if shard not in ("keys", "queries"):
+            raise ValueError("shard must be 'keys' or 'queries'")
+        self.shard = shard
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ops._lib.SummerClipError("ClipSearcher needs a CUDA device: the CLIP-search path has no CPU fallback")
@@ -73,6 +82,7 @@ class ClipSearcher:
         else:
             self.world, self.rank = 1, 0
         self.text: tp.Optional[torch.Tensor] = None          # [D, C] fp32
+        self.text_split: tp.Optional[tp.Tuple[torch.Tensor, torch.Tensor]] = None
         self.k_norm: tp.Optional[torch.Tensor] = None        # [Nk_local, D_pad]
         self.vt: tp.Optional[torch.Tensor] = None            # [C_pad, Nk_pad] (dense values)
         self.hard_bank: tp.Optional[ops.HardBank] = None     # one-hot values: label-sorted key bank (replaces k_norm / vt)
@@ -86,6 +96,7 @@ class ClipSearcher:
     def set_text(self, text_features: torch.Tensor) -> None:
         """Zero-shot classifier T [D, C] (eval_clip.zeroshot_classifier output; an input of this path)."""
         self.text = text_features.to(self.device, non_blocking=True).float().contiguous()
+        self.text_split = ops.text_split(self.text)           # split-fp16 rows of T^T for the tensor-core GEMM
 
     def set_cache(self, cache_image_features: torch.Tensor, cache_image_outs: tp.Optional[torch.Tensor],
                   idx: tp.Optional[torch.Tensor] = None, *, feature_major: bool = True,
@@ -102,8 +113,8 @@ class ClipSearcher:
             n_sel = idx.numel()
         else:
             n_sel = n_total
-        lo, hi = shard_range(n_sel, self.rank, self.world)
-        if self.world > 1 or idx is not None:
+        lo, hi = shard_range(n_sel, self.rank, self.world) if self.shard == "keys" else (0, n_sel)
+        if (self.world > 1 and self.shard == "keys") or idx is not None:
             local_idx = idx[lo:hi] if idx is not None else torch.arange(lo, hi, device=self.device)
         else:
             local_idx = None
@@ -120,7 +131,7 @@ class ClipSearcher:
             return
         self.k_norm = ops.normalize_cast(feats, feature_major=feature_major, idx=local_idx, op_dtype=self.op_dtype)
         self.gpu_launches += 1
-        local_labels = labels.to(self.device)[lo:hi] if labels is not None else None
+        local_labels = labels.to(self.device)[lo:hi].contiguous() if labels is not None else None
         self.rowsum_col = None
         if softmax_scale is None and not softmax_normalize and ops.hard_supported(self.n_classes):
             # one-hot values: W @ V is a per-class segmented row sum; sort the keys by label once and let the
@@ -166,7 +177,7 @@ class ClipSearcher:
         self.gpu_launches += 1
         z = None
         if self.text is not None:
-            z = ops.zero_shot_logits(q, feature_major, self.text, scale=100.0, normalize=True)
+            z = ops.zero_shot_logits(q, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
             self.gpu_launches += 1
         return qn, z
 
@@ -262,12 +273,17 @@ class ClipSearcher:
         z = None
         if self.text is not None and hi > lo:
             q_mine = q[:, lo:hi] if feature_major else q[lo:hi]
-            z = ops.zero_shot_logits(q_mine, feature_major, self.text, scale=100.0, normalize=True)
+            z = ops.zero_shot_logits(q_mine, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
             self.gpu_launches += 1
         lab_mine = labels.to(self.device, non_blocking=True)[lo:hi].contiguous() if labels is not None else None
         results = []
+        qn_mine = qn[lo:hi] if self.shard == "queries" else None
         for beta in betas:
-            o, lo, hi = exchange_partials(self.local_cache_logits(qn, float(beta)), self.group)
+            if self.shard == "queries":        # the whole bank is local: score my query slice, nothing to exchange
+                o = self.local_cache_logits(qn_mine, float(beta)) if hi > lo else \
+                    torch.zeros((0, self.n_classes + int(self.rowsum_col is not None)), dtype=torch.float32, device=self.device)
+            else:
+                o, lo, hi = exchange_partials(self.local_cache_logits(qn, float(beta)), self.group)
             res = {"beta": float(beta), "lo": lo, "hi": hi, "pred": None, "top1": None, "top5": None, "logits": None}
             na = len(alphas)
             pred_all = torch.zeros((self.world, na, per), dtype=torch.int32, device=self.device)

@@ -455,6 +455,31 @@ def test_cuda_graph_replay_of_a_search(ops):
         assert torch.equal(res[0]["pred"], eager["pred"]) and torch.equal(res[0]["top1"], eager["top1"])
 
 
+def test_operand_caches_are_keyed_by_identity_not_address(ops):
+    """Three problems of the SAME shapes back to back, each freeing its tensors: the caching allocator reuses the
+    addresses, so any operand cache keyed by data_ptr would serve the previous problem's text split / normalised
+    bank / sorted bank (a bug the 2-rank check caught).  Every result must match ITS oracle."""
+    from summer_clip_b200.clip_searcher.cache_value_strategy import HardCacheStrategy
+    from summer_clip_b200.clip_searcher.cache_weights_strategy import TipAdapterWeightsStrategy
+    from summer_clip_b200.searcher import ClipSearcher
+    for seed in (11, 12, 13):
+        banks = orc.synthetic_banks(200, 1500, 128, 30, seed=seed, sigma=0.5, sigma_text=0.8, shared=3.0)
+        Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+        Zref = orc.zero_shot_logits(Q, T)
+        Oref = orc.image_attention(Q, K, orc.hard_values(L), 5.5)
+        s = ClipSearcher("cuda")
+        s.set_text(T)
+        s.set_cache(K, L)
+        got = s.search(Q, [5.5], [1.0], want_logits=True)[0]
+        assert_logits_match(got["logits"][0], orc.searcher_logits(Zref, Oref, 1.0), f"searcher seed={seed}")
+        Qc, Kc, Lc = Q.cuda(), K.cuda(), L.cuda()
+        o = TipAdapterWeightsStrategy(5.5).transform(Qc, Kc) @ HardCacheStrategy().transform(Lc)
+        assert (o.cpu() - Oref).abs().max().item() / Oref.abs().max().item() < 1e-3, f"strategies seed={seed}"
+        z = ops.zero_shot_logits(Qc, True, T.cuda())
+        assert (z.cpu() - Zref).abs().max().item() < 3e-4, f"zero-shot seed={seed}"
+        del s, got, Qc, Kc, Lc, o, z
+
+
 def test_cpu_tensors_are_rejected(ops):
     from summer_clip_b200._lib import SummerClipError
     with pytest.raises(SummerClipError):

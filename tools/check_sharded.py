@@ -23,17 +23,24 @@ for nq, hard in ((1001, True), (512, True), (777, False)):
     single.set_text(T)
     single.set_cache(K, L, **kw)
     ref = single.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
-    sharded = ClipSearcher(dev, group=dist.group.WORLD)
-    sharded.set_text(T)
-    sharded.set_cache(K, L, **kw)
-    got = sharded.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
-    lo, hi = got["lo"], got["hi"]
-    e = (got["logits"] - ref["logits"][:, lo:hi]).abs().max().item() / ref["logits"].abs().max().item()
-    same_pred = bool((got["pred"] == ref["pred"]).float().mean() > 0.999)
-    same_cnt = bool((got["top1"] - ref["top1"]).abs().max() <= 1) and bool((got["top5"] - ref["top5"]).abs().max() <= 1)
-    good = e < 1e-4 and same_pred and same_cnt and got["pred"].shape == ref["pred"].shape
-    ok &= good
-    print(f"rank {rank} nq={nq} hard={hard}: slice=[{lo},{hi}) rel_err={e:.2e} pred={same_pred} counts={same_cnt} {'OK' if good else 'FAIL'}", flush=True)
+    V = orc.hard_values(L.float()) if hard else orc.softmax_values(L.float(), orc.CLIP_SCALE, 0.1)
+    want = orc.searcher_logits(orc.zero_shot_logits(Q.float(), T.float()), orc.image_attention(Q, K, V, 5.5), 0.5)
+    e0 = (ref["logits"][0].cpu() - want).abs().max().item() / want.abs().max().item()
+    print(f"rank {rank} nq={nq} hard={hard}: single-rank result vs oracle rel_err={e0:.2e}", flush=True)
+    ok &= e0 < 2e-3
+    for shard in ("keys", "queries"):
+        sharded = ClipSearcher(dev, group=dist.group.WORLD, shard=shard)
+        sharded.set_text(T)
+        sharded.set_cache(K, L, **kw)
+        got = sharded.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
+        lo, hi = got["lo"], got["hi"]
+        e = (got["logits"] - ref["logits"][:, lo:hi]).abs().max().item() / ref["logits"].abs().max().item()
+        same_pred = bool((got["pred"] == ref["pred"]).float().mean() > 0.999)
+        same_cnt = bool((got["top1"] - ref["top1"]).abs().max() <= 1) and bool((got["top5"] - ref["top5"]).abs().max() <= 1)
+        good = e < 1e-4 and same_pred and same_cnt and got["pred"].shape == ref["pred"].shape
+        ok &= good
+        print(f"rank {rank} nq={nq} hard={hard} shard={shard}: slice=[{lo},{hi}) rel_err={e:.2e} pred={same_pred} "
+              f"counts={same_cnt} {'OK' if good else 'FAIL'}", flush=True)
 dist.barrier()
 print(f"rank {rank} SHARDED {'OK' if ok else 'FAIL'}", flush=True)
 dist.destroy_process_group()
