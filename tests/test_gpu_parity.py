@@ -365,6 +365,35 @@ def test_sorted_bank_layout_kernel_matches_the_specification(ops, n_keys, n_clas
     assert torch.equal(got.rows, ref)
 
 
+def test_hard_label_segmented_kernel_random_shapes(ops):
+    """Seeded sweep of ragged shapes through sc_attn_fwd_hard (both operand types): queries / keys off every tile
+    boundary, D not a multiple of 64, more classes than keys, one huge class, splits forced high."""
+    rng = np.random.default_rng(87)
+    for case in range(14):
+        nq = int(rng.integers(1, 700))
+        nk = int(rng.integers(1, 3000))
+        dim = int(rng.choice([24, 64, 100, 192, 257, 512]))
+        c = int(rng.choice([1, 2, 17, 256, 257, 1000, 4000]))
+        beta = float(rng.choice([0.1, 1.0, 5.5, 11.5]))
+        op_dtype = torch.float16 if case % 2 == 0 else torch.bfloat16
+        g = torch.Generator().manual_seed(1000 + case)
+        Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False, op_dtype=op_dtype)
+        Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False, op_dtype=op_dtype)
+        if case % 3 == 0:
+            labels = torch.zeros(nk, dtype=torch.int32)                       # every key in one class
+        else:
+            labels = torch.randint(0, c, (nk,), generator=g).int()
+        labels = labels.cuda()
+        bank = ops.hard_bank_layout(labels, c).gather(Kn)
+        W = torch.exp(beta * (Qn.float() @ Kn.float().t() - 1.0))
+        ref = torch.zeros(nq, c, device="cuda").index_add_(1, labels.long(), W)
+        steps = max(1, -(-bank.n_sorted // 256))
+        for splits in (0, steps):
+            O = ops.attn_fwd_hard(Qn, bank, beta, splits=splits)
+            torch.testing.assert_close(O, ref, rtol=3e-5, atol=1e-6 * max(1.0, ref.max().item()),
+                                       msg=lambda m: f"case {case} nq={nq} nk={nk} D={dim} C={c} splits={splits}: {m}")
+
+
 def test_hard_values_route_through_the_segmented_kernel(ops, monkeypatch):
     """HardCacheStrategy / gold labels / one-hot Tip-Adapter cache values all become a label-sorted bank; the
     dense-values route (SUMMER_CLIP_B200_DENSE_VALUES=1) gives the same logits."""
