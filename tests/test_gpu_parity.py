@@ -92,6 +92,29 @@ def test_selection_vs_oracle_sun397_shape(ops, dtype):
                 assert k < vals.size and abs(vals[k - 1] - vals[k]) <= 4e-7 * vals[k - 1], f"class {c} differs off a tie"
 
 
+def test_remaining_strategies_vs_reference_golden(ops, golden_dir):
+    """Threshold, per-gold top-k (raw / softmax) and the per-predicted-class random sampler against outputs of the
+    reference's own classes (tests/golden/strategies.npz): indices bit-exact, same order."""
+    from summer_clip_b200.clip_searcher import cache_strategy as cs
+    st = np.load(golden_dir / "strategies.npz")
+    outs = cuda(st["image_outs"])
+    gold = cuda(st["gold_labels"])
+    feats = torch.empty(1, outs.shape[0], device="cuda")
+    for thr in (0.06, 0.07):
+        assert np.array_equal(cs.ThresholdStrategy(thr, True).select(feats, outs).cpu().numpy(), st[f"threshold_softmax_{thr}"])
+    for thr in (0.3, 0.36):
+        assert np.array_equal(cs.ThresholdStrategy(thr, False).select(feats, outs).cpu().numpy(), st[f"threshold_raw_{thr}"])
+    for k in (1, 4, 80):
+        got = cs.TopKPerGoldStrategy(k, cache_labels=gold).select(feats, outs).cpu().numpy()
+        assert np.array_equal(got, st[f"topk_per_gold_{k}"])
+        got = cs.TopKPerGoldProbStrategy(k, scale=orc.CLIP_SCALE, cache_labels=gold).select(feats, outs).cpu().numpy()
+        assert np.array_equal(got, st[f"topk_per_gold_prob_{k}"])
+    for k in (1, 3, 60):
+        np.random.seed(42)
+        got = cs.PerPredClassRandomSampleStrategy(k).select(feats, outs).cpu().numpy()
+        assert np.array_equal(got, st[f"per_pred_random_{k}"])
+
+
 def test_selection_edge_cases(ops):
     # empty classes, classes with fewer than k members, k larger than N, a single row, all rows one class
     conf = cuda(np.array([0.9, 0.1, 0.5, 0.5, 0.7], dtype=np.float32))
