@@ -157,6 +157,12 @@ int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count);
 int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                      int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta,
                      int splits, float* O, int64_t ldo, void* stream);
+/* The same for 1..4 betas in ONE pass (`betas` is a HOST array): S = Q.K^T does not depend on beta, so a beta
+ * sweep (image_attention.yaml: 8 per cache; tip_adapter/utils.py:99-129: 200) pays the tensor-core GEMM once
+ * per group of betas and only the exponentials per beta.  O is fp32 [n_betas, splits, Nq, ldo]. */
+int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
+                           int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes,
+                           const float* betas, int n_betas, int splits, float* O, int64_t ldo, void* stream);
 
 /* out[r, c] = sum_p parts[p, r, c]  (key splits and key-sharded ranks; with the Tip weights
  * exp(beta(A-1)) <= 1 the running maximum of an LSE merge is the constant 0, so the merge of
@@ -194,6 +200,15 @@ int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void*
 int sc_epilogue(const float* Z, int64_t ldz, const float* O, int64_t ldo, const float* rowsum,
                 int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
                 float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream);
+
+/* sc_epilogue on UNMERGED partial tiles: O is fp32 [n_parts, Nq, ldo] with the parts part_stride floats apart
+ * (what sc_attn_fwd_hard / _multi write for splits > 1); every element is summed over the parts in
+ * sc_merge_partials' order, so the results are bit-identical to sc_merge_partials followed by sc_epilogue —
+ * without the extra pass over HBM.  Replaces the same reference lines as sc_epilogue. */
+int sc_epilogue_parts(const float* Z, int64_t ldz, const float* O, int64_t ldo, int n_parts, int64_t part_stride,
+                      const float* rowsum, int64_t Nq, int64_t C, const float* alphas, int na,
+                      const int32_t* labels, float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,8 @@ SIGNATURES = {
     "sc_attn_hard_splits": (c_int, [c_int64, c_int64, c_int]),
     "sc_attn_fwd_hard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                  c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_attn_fwd_hard_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                       POINTER(c_float), c_int, c_int, c_void_p, c_int64, c_void_p]),
     "sc_merge_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "sc_zero_shot_logits": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,
                                     c_int64, c_float, c_int, c_void_p, c_int64, c_void_p]),
@@ -57,6 +59,8 @@ SIGNATURES = {
                                  c_void_p, c_int64, c_void_p]),
     "sc_epilogue": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, POINTER(c_float),
                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sc_epilogue_parts": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64,
+                                  POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -76,6 +76,20 @@ class FusedWeights:
         vt = values.vt(self.q_norm.dtype)
         return ops.attn_fwd(self.q_norm, self.k_norm, vt, self.n_keys, values.n_classes, self.beta)
 
+    @staticmethod
+    def matmul_many(weights: tp.Sequence["FusedWeights"], values: tp.Union["CacheValues", torch.Tensor]) -> tp.List[torch.Tensor]:
+        """[w @ values for w in weights] for weights that differ only in beta (the sweep of image_attention.py:
+        106-109, of search_hp): with one-hot values the tensor-core pass is shared by groups of 4 betas."""
+        if not weights:
+            return []
+        if isinstance(values, torch.Tensor):
+            values = CacheValues.from_dense(values, op_dtype=weights[0].q_norm.dtype)
+        w0 = weights[0]
+        same_banks = all(w.q_norm is w0.q_norm and w.k_norm is w0.k_norm and w.n_keys == w0.n_keys for w in weights)
+        if same_banks and values.is_hard and values.n_keys == w0.n_keys:
+            return ops.attn_fwd_hard_multi(w0.q_norm, values.hard_bank(w0.k_norm), [w.beta for w in weights])
+        return [w @ values for w in weights]
+
     def materialize(self, chunk: int = 4096) -> torch.Tensor:
         """Dense fp32 [Nq, Nk] (tests / debugging on small caches only): the kernel with V = I."""
         cols = []

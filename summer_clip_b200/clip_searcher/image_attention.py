@@ -28,7 +28,7 @@ from ..utils.config import Config, load_config
 from ..utils.log_utils import JsonLinesLogger
 from .cache_strategy import CacheStrategy, IndexedCacheStrategy
 from .cache_value_strategy import GoldCacheValues, HardCacheStrategy, SoftmaxCacheStrategy
-from .cache_weights_strategy import NormalizedBank
+from .cache_weights_strategy import FusedWeights, NormalizedBank
 from .utils import TensorsNumpySaver, compute_accuracy
 
 
@@ -140,17 +140,24 @@ class ImageAttention:
                     cache_strategy, self.origin_cache_image_features, self.origin_cache_image_outs)
                 self.logger.log_info(dict(**cache_info, cache_strategy=cache_strategy_params, type="cache_info"))
                 value_cache: tp.Dict[int, tp.Any] = {}
-                for weights_strategy, weights_params in hydra_utils.instantiate_all(self.cfg.cache_weights_strategy):
-                    cache_weights = weights_strategy.transform(q_bank, k_bank)
-                    for vi, (value_strategy, value_params) in enumerate(hydra_utils.instantiate_all(self.cfg.cache_value_strategy)):
-                        if vi not in value_cache:
-                            if gold is not None:
-                                value_cache[vi] = GoldCacheValues(outs.shape[1]).transform(gold)
-                            elif isinstance(value_strategy, (HardCacheStrategy, SoftmaxCacheStrategy)):
-                                value_cache[vi] = value_strategy.transform(outs, idx=idx)
-                            else:
-                                value_cache[vi] = value_strategy.transform(outs if idx is None else outs[idx])
-                        cache_logits = cache_weights @ value_cache[vi]
+                weights_grid = [(ws.transform(q_bank, k_bank), wp)
+                                for ws, wp in hydra_utils.instantiate_all(self.cfg.cache_weights_strategy)]
+                values_grid = list(hydra_utils.instantiate_all(self.cfg.cache_value_strategy))
+                for vi, (value_strategy, value_params) in enumerate(values_grid):
+                    if gold is not None:
+                        value_cache[vi] = GoldCacheValues(outs.shape[1]).transform(gold)
+                    elif isinstance(value_strategy, (HardCacheStrategy, SoftmaxCacheStrategy)):
+                        value_cache[vi] = value_strategy.transform(outs, idx=idx)
+                    else:
+                        value_cache[vi] = value_strategy.transform(outs if idx is None else outs[idx])
+                # every (weights, values) product of this cache; betas share the tensor-core pass where they can
+                logits_grid = {vi: FusedWeights.matmul_many([w for w, _ in weights_grid], value_cache[vi])
+                               if all(isinstance(w, FusedWeights) for w, _ in weights_grid)
+                               else [w @ value_cache[vi] for w, _ in weights_grid]
+                               for vi in range(len(values_grid))}
+                for wi, (_, weights_params) in enumerate(weights_grid):          # record order of the reference loop
+                    for vi, (_, value_params) in enumerate(values_grid):
+                        cache_logits = logits_grid[vi][wi]
                         res = ops.epilogue(clip_logits, cache_logits, alphas, labels=self.test_labels,
                                            want_pred=bool(self.cfg.run_saves.save_preds))
                         top1, top5 = res["top1"].cpu().tolist(), res["top5"].cpu().tolist()   # one D2H per beta

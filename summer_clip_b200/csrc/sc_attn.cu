@@ -38,7 +38,8 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
 int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count);
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                     const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
-                    int64_t Nks, int64_t D_pad, float beta, int splits, float* O, int64_t ldo, cudaStream_t st);
+                    int64_t Nks, int64_t D_pad, const float* betas, int n_betas, int splits, float* O, int64_t ldo,
+                    cudaStream_t st);
 int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                       const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
                       int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st);
@@ -495,10 +496,11 @@ int sc_attn_hard_supported(int64_t n_classes) { return (n_classes > 0 && n_class
 
 int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count) { return sc::attn_seg_splits(Nq, Nks, sm_count); }
 
-int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
-                     int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta, int splits,
-                     float* O, int64_t ldo, void* stream) {
-  SC_REQUIRE(Qn && Ks && group_class && key_bits && O, SC_EINVAL, "sc_attn_fwd_hard: null pointer");
+int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
+                           int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes,
+                           const float* betas, int n_betas, int splits, float* O, int64_t ldo, void* stream) {
+  SC_REQUIRE(Qn && Ks && group_class && key_bits && O && betas, SC_EINVAL, "sc_attn_fwd_hard: null pointer");
+  SC_REQUIRE(n_betas >= 1 && n_betas <= 4, SC_ESHAPE, "sc_attn_fwd_hard_multi: n_betas=%d must be in [1, 4]", n_betas);
   SC_REQUIRE(op_dtype == SC_F16 || op_dtype == SC_BF16, SC_EINVAL, "sc_attn_fwd_hard: op_dtype must be SC_F16 or SC_BF16");
   SC_REQUIRE(Nq > 0 && Nks > 0 && n_classes > 0, SC_ESHAPE, "sc_attn_fwd_hard: empty problem");
   SC_REQUIRE(sc_attn_hard_supported(n_classes), SC_EUNSUPPORTED, "sc_attn_fwd_hard: n_classes=%lld exceeds int16 labels",
@@ -519,11 +521,18 @@ int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class,
   }
   SC_REQUIRE(splits <= steps_total && splits <= 65535, SC_ESHAPE,
              "sc_attn_fwd_hard: splits=%d exceeds the %lld key steps", splits, (long long)steps_total);
-  int rc = sc::attn_seg_launch(&make_tmap, Qn, Ks, group_class, key_bits, op_dtype == SC_F16, Nq, Nks, D_pad, beta,
-                               splits, O, ldo, static_cast<cudaStream_t>(stream));
+  int rc = sc::attn_seg_launch(&make_tmap, Qn, Ks, group_class, key_bits, op_dtype == SC_F16, Nq, Nks, D_pad, betas,
+                               n_betas, splits, O, ldo, static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
+                     int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta, int splits,
+                     float* O, int64_t ldo, void* stream) {
+  return sc_attn_fwd_hard_multi(Qn, Ks, group_class, key_bits, op_dtype, Nq, Nks, D_pad, n_classes, &beta, 1, splits, O,
+                                ldo, stream);
 }
 
 int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,

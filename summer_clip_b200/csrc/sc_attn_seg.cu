@@ -48,7 +48,8 @@ struct SParams {
   int splits;
   int pf_dist;               // L2 prefetch distance in steps (0 = off)
   int dbg;                   // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit0/2 skip Q/K loads, 3 exp, 4 MMAs
-  float c1, c0;
+  float c1[4], c0[4];        // per beta: exponent scale beta * log2(e) and offset -c1 (kNB betas per launch)
+  long long o_beta_stride;   // elements between the O slabs of consecutive betas (= splits * Nq * ldo)
   const int16_t* gcls;       // class of every 16-key group, [steps_total * 16]; -1 = no real key
   const uint32_t* kbits;     // validity bit per key, [steps_total * 8] words (bit j of word w = key 32 w + j)
   float* O;                  // [splits, Nq, ldo], zeroed by the launcher; only the classes met are written
@@ -78,7 +79,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // kGemm = false: the attention kernel described above.  kGemm = true: the same TMA ring / pair-UMMA / TMEM
 // pipeline used as a plain "NT" GEMM with split-fp16 operands (sc_gemm_split_nt): three operand passes
 // (Ah.Bh, Ah.Bl, Al.Bh) accumulate into one S tile, and the four "exp" warps store scale * S instead.
-template <bool kF16, bool kGemm>
+// kNB (attention mode): betas per launch.  S = Q.K^T does not depend on beta, so a beta sweep (8 betas per cache
+// in image_attention.yaml, 200 in Tip-Adapter's search_hp) pays GEMM-1 once per kNB betas; the exp warps then do
+// kNB exponentials per S element — 2048 MUFU cycles per beta and step against 8192 cycles of UMMAs, so kNB = 4
+// balances the two pipes.
+template <bool kF16, bool kGemm, int kNB>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmK2, const SParams p) {
@@ -251,12 +256,22 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     } else {
-    const float c1 = p.c1, cadd = p.c0;
+    float c1[kNB], cadd[kNB];
+#pragma unroll
+    for (int bi = 0; bi < kNB; ++bi) { c1[bi] = p.c1[bi]; cadd[bi] = p.c0[bi]; }
     const int q = q0 + row;
-    float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;
+    float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;     // beta bi: + bi * o_beta_stride
     const bool q_ok = q < p.Nq;
-    int cur = -1;          // class of the running sum (warp-uniform)
-    float acc = 0.f;
+    int cur = -1;          // class of the running sums (warp-uniform)
+    float acc[kNB];
+#pragma unroll
+    for (int bi = 0; bi < kNB; ++bi) acc[bi] = 0.f;
+    auto flush = [&]() {
+      if (cur >= 0 && q_ok) {
+#pragma unroll
+        for (int bi = 0; bi < kNB; ++bi) orow[bi * p.o_beta_stride + cur] = acc[bi];
+      }
+    };
 #pragma unroll 1
     for (int st = 0; st < nsteps; ++st) {
       const int b = st & 1;
@@ -276,23 +291,32 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int hh = 0; hh < 2; ++hh) {
           const int cls = static_cast<int>(static_cast<int16_t>((gw[cc] >> (16 * hh)) & 0xffffu));
           const uint32_t bits = (kw[cc] >> (16 * hh)) & 0xffffu;
-          if (cls != cur) {                              // warp-uniform: the finished class sum goes out
-            if (cur >= 0 && q_ok) orow[cur] = acc;
+          if (cls != cur) {                              // warp-uniform: the finished class sums go out
+            flush();
             cur = cls;
-            acc = 0.f;
+#pragma unroll
+            for (int bi = 0; bi < kNB; ++bi) acc[bi] = 0.f;
           }
-          float s = 0.f;
           if (bits == 0xffffu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) s += ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1, cadd));
+            for (int bi = 0; bi < kNB; ++bi) {
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) s += ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1[bi], cadd[bi]));
+              acc[bi] += s;
+            }
           } else if (bits != 0u) {                       // a class segment's last group: padding keys weigh 0
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float e = ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1, cadd));
-              s += ((bits >> j) & 1u) ? e : 0.f;
+            for (int bi = 0; bi < kNB; ++bi) {
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float e = ex2_approx(fmaf(__uint_as_float(rg[16 * hh + j]), c1[bi], cadd[bi]));
+                s += ((bits >> j) & 1u) ? e : 0.f;
+              }
+              acc[bi] += s;
             }
           }
-          acc += s;
         }
       };
       if (!(p.dbg & 8)) {
@@ -317,7 +341,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), 0);
       }
     }
-    if (cur >= 0 && q_ok) orow[cur] = acc;
+    flush();
     }
   }
 
@@ -339,10 +363,10 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <bool kF16, bool kGemm>
+template <bool kF16, bool kGemm, int kNB>
 int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmQ2,
                const CUtensorMap& tmK2, const SParams& p) {
-  auto kernel = sc_attn_seg_kernel<kF16, kGemm>;
+  auto kernel = sc_attn_seg_kernel<kF16, kGemm, kNB>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -398,10 +422,12 @@ int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count) {
   return best;
 }
 
-// Called by sc_attn_fwd_hard (sc_attn.cu) after argument validation.  O [splits, Nq, ldo] is zeroed here.
+// Called by sc_attn_fwd_hard[_multi] (sc_attn.cu) after argument validation: 1..4 betas per launch, O is
+// [n_betas, splits, Nq, ldo] and is zeroed here.
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                     const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
-                    int64_t Nks, int64_t D_pad, float beta, int splits, float* O, int64_t ldo, cudaStream_t st) {
+                    int64_t Nks, int64_t D_pad, const float* betas, int n_betas, int splits, float* O, int64_t ldo,
+                    cudaStream_t st) {
   CUtensorMap tmQ, tmK;
   int rc;
   if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
@@ -411,8 +437,11 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   p.n_dchunks = static_cast<int>(D_pad / kBK);
   p.steps_total = static_cast<int>(ceil_div(Nks, kStepKeys));
   p.splits = splits;
-  p.c1 = beta * 1.4426950408889634f;
-  p.c0 = -p.c1;
+  for (int bi = 0; bi < 4; ++bi) {
+    p.c1[bi] = betas[bi < n_betas ? bi : n_betas - 1] * 1.4426950408889634f;
+    p.c0[bi] = -p.c1[bi];
+  }
+  p.o_beta_stride = static_cast<long long>(splits) * Nq * ldo;
   p.gcls = gcls;
   p.kbits = kbits;
   p.O = O;
@@ -434,14 +463,24 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
     p.clk = g_clk;
   }
 #endif
-  SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(splits) * Nq * ldo * sizeof(float), st));
+  SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(n_betas) * splits * Nq * ldo * sizeof(float), st));
   dim3 grid(2u, static_cast<unsigned>(ceil_div(Nq, 2 * kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd_hard: too many query tiles; chunk the queries");
   p.Z = nullptr;
   p.ldz = 0;
   p.n_cols = 0;
   p.scale = 1.0f;
-  return f16 ? launch_seg<true, false>(grid, st, tmQ, tmK, tmQ, tmK, p) : launch_seg<false, false>(grid, st, tmQ, tmK, tmQ, tmK, p);
+#define SC_SEG_LAUNCH(NB)                                                                              \
+  (f16 ? launch_seg<true, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p) : launch_seg<false, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p))
+  int rc2;
+  switch (n_betas) {
+    case 1: rc2 = SC_SEG_LAUNCH(1); break;
+    case 2: rc2 = SC_SEG_LAUNCH(2); break;
+    case 3: rc2 = SC_SEG_LAUNCH(3); break;
+    default: rc2 = SC_SEG_LAUNCH(4); break;
+  }
+#undef SC_SEG_LAUNCH
+  return rc2;
 }
 
 // Z[m, n] = scale * sum_d (Ah[m,d] Bh[n,d] + Ah[m,d] Bl[n,d] + Al[m,d] Bh[n,d]): fp32-accurate "NT" GEMM of
@@ -460,7 +499,8 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.n_dchunks = static_cast<int>(D_pad / kBK);
   p.steps_total = static_cast<int>(ceil_div(N, kStepKeys));
   p.splits = p.steps_total;                 // one step of 256 B-rows per work item
-  p.c1 = p.c0 = 0.f;
+  for (int bi = 0; bi < 4; ++bi) p.c1[bi] = p.c0[bi] = 0.f;
+  p.o_beta_stride = 0;
   p.gcls = nullptr;
   p.kbits = nullptr;
   p.O = nullptr;
@@ -474,7 +514,7 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.scale = scale;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
   SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
-  return launch_seg<true, true>(grid, st, tmA, tmB, tmA2, tmB2, p);
+  return launch_seg<true, true, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
 }
 
 }  // namespace sc

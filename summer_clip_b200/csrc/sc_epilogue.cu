@@ -5,6 +5,7 @@
 //                         clip_searcher/utils.py:15-21, clip_adapter/train_adapter.py:156-159,
 //                         tip_adapter/utils.py:10-15
 #include "sc_common.cuh"
+#include "sc_rowops.cuh"
 
 namespace {
 
@@ -85,10 +86,17 @@ zero_shot_kernel(const TX* __restrict__ X, int64_t D, int64_t N, int64_t stride_
   }
 }
 
-// one warp per query row; the row (Z and O, 8 KB at C = 1000) is re-read per alpha from L1.
+// sum of the n_parts partial tiles of one O element, in merge_kernel's order (bit-identical to a merged O)
+__device__ __forceinline__ float o_sum(const float* __restrict__ src, int n_parts, int64_t part_stride) {
+  float s = src[0];
+  for (int p = 1; p < n_parts; ++p) s += src[p * part_stride];
+  return s;
+}
+
+// Generic path (C > 1024): one warp per query row; the row is re-read per alpha from L1.
 __global__ void __launch_bounds__(256)
-epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ O, int64_t ldo,
-                const float* __restrict__ rowsum, int64_t Nq, int64_t C, AlphaList alphas, int na,
+epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ O, int64_t ldo, int n_parts,
+                int64_t part_stride, const float* __restrict__ rowsum, int64_t Nq, int64_t C, AlphaList alphas, int na,
                 const int32_t* __restrict__ labels, float* __restrict__ out_logits,
                 int32_t* __restrict__ pred, int32_t* __restrict__ top1, int32_t* __restrict__ top5) {
   __shared__ int32_t s_top1[kMaxAlphas];
@@ -107,7 +115,7 @@ epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restric
       const float alpha = alphas.a[ai];
       float vlab = 0.f;
       if (lab >= 0 && lab < C) {
-        float o = orow[lab];
+        float o = o_sum(orow + lab, n_parts, part_stride);
         if (rowsum) o *= inv;
         vlab = __fadd_rn(zrow ? zrow[lab] : 0.f, __fmul_rn(o, alpha));
       }
@@ -115,7 +123,7 @@ epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restric
       int besti = -1;
       int ahead = 0;   // classes ranked strictly before the label (value desc, index asc)
       for (int64_t c = lane; c < C; c += 32) {
-        float o = orow[c];
+        float o = o_sum(orow + c, n_parts, part_stride);
         if (rowsum) o *= inv;
         const float v = __fadd_rn(zrow ? zrow[c] : 0.f, __fmul_rn(o, alpha));
         if (out_logits) out_logits[(static_cast<int64_t>(ai) * Nq + q) * C + c] = v;
@@ -143,6 +151,147 @@ epilogue_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restric
     if (top1 && s_top1[i]) atomicAdd(&top1[i], s_top1[i]);
     if (top5 && s_top5[i]) atomicAdd(&top5[i], s_top5[i]);
   }
+}
+
+// Register-resident path (C <= 32 * NV <= 1024): one warp per query row, Z and the (summed) O row loaded ONCE
+// into registers, then every alpha is ~5 instructions per class: out = Z + O * alpha (separately rounded, as
+// torch), "classes ahead of the label" counted as (v > v_label) plus, only when a value ties with the label's
+// (warp-uniform, rare), the exact index-ordered recount.  kPred adds the running max.NaN and one pass for the
+// FIRST index of the maximum; rows whose maximum is NaN take the generic kernel's ordered compare.
+template <int NV, bool kPred>
+__global__ void __launch_bounds__(256)
+epilogue_reg_kernel(const float* __restrict__ Z, int64_t ldz, const float* __restrict__ O, int64_t ldo, int n_parts,
+                    int64_t part_stride, const float* __restrict__ rowsum, int64_t Nq, int C, AlphaList alphas, int na,
+                    const int32_t* __restrict__ labels, float* __restrict__ out_logits,
+                    int32_t* __restrict__ pred, int32_t* __restrict__ top1, int32_t* __restrict__ top5) {
+  __shared__ int32_t s_top1[kMaxAlphas];
+  __shared__ int32_t s_top5[kMaxAlphas];
+  for (int i = threadIdx.x; i < na; i += blockDim.x) { s_top1[i] = 0; s_top5[i] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const float kNegInf = __int_as_float(0xff800000);
+  const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); q < Nq;
+       q += warps_per_grid) {
+    const float* zrow = Z ? Z + q * ldz : nullptr;
+    const float* orow = O + q * ldo;
+    const float inv = rowsum ? 1.0f / rowsum[q] : 1.0f;
+    float z[NV], o[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {                       // padding classes: -inf + 0 * alpha never wins
+      const int c = j * 32 + lane;
+      z[j] = c < C ? (zrow ? zrow[c] : 0.f) : kNegInf;
+      o[j] = c < C ? orow[c] : 0.f;
+    }
+    for (int p = 1; p < n_parts; ++p) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = j * 32 + lane;
+        if (c < C) o[j] += orow[p * part_stride + c];
+      }
+    }
+    if (rowsum) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) o[j] *= inv;
+    }
+    const int lab = labels ? labels[q] : -1;
+    const bool lab_ok = lab >= 0 && lab < C;             // warp-uniform
+    float zlab = 0.f, olab = 0.f;
+    if (lab_ok) {
+      zlab = zrow ? zrow[lab] : 0.f;
+      olab = o_sum(orow + lab, n_parts, part_stride);
+      if (rowsum) olab *= inv;
+    }
+    for (int ai = 0; ai < na; ++ai) {
+      const float alpha = alphas.a[ai];
+      const float vlab = __fadd_rn(zlab, __fmul_rn(olab, alpha));
+      float m = kNegInf;
+      int cnt = 0;                                       // (v > vlab) in the low half, (v == vlab) in the high half
+      if (out_logits) {
+        float* dst = out_logits + (static_cast<int64_t>(ai) * Nq + q) * C;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c = j * 32 + lane;
+          if (c < C) dst[c] = __fadd_rn(z[j], __fmul_rn(o[j], alpha));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float v = __fadd_rn(z[j], __fmul_rn(o[j], alpha));
+        if (kPred) m = sc::max_nan(m, v);
+        cnt += (v > vlab ? 1 : 0) + (v == vlab ? 0x10000 : 0);
+      }
+      bool slow = false;
+      if (kPred) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = sc::max_nan(m, __shfl_xor_sync(0xffffffffu, m, s));
+        slow = m != m;
+      }
+      if (lab_ok) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        slow = slow || (cnt >> 16) != 1;                 // a tie with the label's value (or a NaN label value)
+      }
+      int ahead = cnt & 0xffff, besti = -1;
+      if (!slow) {
+        if (kPred) {
+          int idx = 0x7fffffff;
+#pragma unroll
+          for (int j = NV - 1; j >= 0; --j)
+            if (__fadd_rn(z[j], __fmul_rn(o[j], alpha)) == m) idx = j * 32 + lane;
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, s));
+          besti = idx < C ? idx : -1;                    // all -inf rows: the first class, as the ordered compare
+          if (idx >= C) slow = true;
+        }
+      }
+      if (slow) {                                        // the generic kernel's ordered compare, from registers
+        float best = 0.f;
+        besti = -1;
+        ahead = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c = j * 32 + lane;
+          if (c < C) {
+            const float v = __fadd_rn(z[j], __fmul_rn(o[j], alpha));
+            if (besti < 0 || v > best) { best = v; besti = c; }
+            if (lab_ok && (v > vlab || (v == vlab && c < lab))) ++ahead;
+          }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, s);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, s);
+          if (oi >= 0 && (besti < 0 || ov > best || (ov == best && oi < besti))) { best = ov; besti = oi; }
+          ahead += __shfl_xor_sync(0xffffffffu, ahead, s);
+        }
+      }
+      if (lane == 0) {
+        if (kPred && pred) pred[static_cast<int64_t>(ai) * Nq + q] = besti;
+        if (lab_ok) {
+          if (ahead == 0) atomicAdd(&s_top1[ai], 1);
+          if (ahead < 5) atomicAdd(&s_top5[ai], 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < na; i += blockDim.x) {
+    if (top1 && s_top1[i]) atomicAdd(&top1[i], s_top1[i]);
+    if (top5 && s_top5[i]) atomicAdd(&top5[i], s_top5[i]);
+  }
+}
+
+template <int NV>
+void launch_epilogue_reg(unsigned blocks, cudaStream_t st, const float* Z, int64_t ldz, const float* O, int64_t ldo,
+                         int n_parts, int64_t part_stride, const float* rowsum, int64_t Nq, int C, const AlphaList& al,
+                         int na, const int32_t* labels, float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5) {
+  if (pred)
+    epilogue_reg_kernel<NV, true><<<blocks, 256, 0, st>>>(Z, ldz, O, ldo, n_parts, part_stride, rowsum, Nq, C, al, na,
+                                                          labels, out_logits, pred, top1, top5);
+  else
+    epilogue_reg_kernel<NV, false><<<blocks, 256, 0, st>>>(Z, ldz, O, ldo, n_parts, part_stride, rowsum, Nq, C, al, na,
+                                                           labels, out_logits, pred, top1, top5);
 }
 
 }  // namespace
@@ -181,21 +330,40 @@ int sc_zero_shot_logits(const void* X, int x_dtype, int64_t D, int64_t N, int64_
   return SC_OK;
 }
 
-int sc_epilogue(const float* Z, int64_t ldz, const float* O, int64_t ldo, const float* rowsum,
-                int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
-                float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream) {
+int sc_epilogue_parts(const float* Z, int64_t ldz, const float* O, int64_t ldo, int n_parts, int64_t part_stride,
+                      const float* rowsum, int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
+                      float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream) {
   SC_REQUIRE(O && alphas, SC_EINVAL, "sc_epilogue: null pointer");
   SC_REQUIRE(na >= 1 && na <= kMaxAlphas, SC_ESHAPE, "sc_epilogue: na=%d must be in [1, %d]", na, kMaxAlphas);
   SC_REQUIRE(Nq >= 0 && C > 0 && ldo >= C && (Z == nullptr || ldz >= C), SC_ESHAPE, "sc_epilogue: bad shape");
+  SC_REQUIRE(n_parts >= 1 && (n_parts == 1 || part_stride >= Nq * ldo), SC_ESHAPE,
+             "sc_epilogue: n_parts=%d needs part_stride >= Nq * ldo", n_parts);
   if (Nq == 0) return SC_OK;
   AlphaList al;
   for (int i = 0; i < na; ++i) al.a[i] = alphas[i];   // alphas is a HOST array
   const int64_t want = sc::ceil_div(Nq, 8);
   const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
-  epilogue_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      Z, ldz, O, ldo, rowsum, Nq, C, al, na, labels, out_logits, pred, top1, top5);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int c = static_cast<int>(C);
+#define SC_EPI_REG(NV)                                                                                              \
+  launch_epilogue_reg<NV>(blocks, st, Z, ldz, O, ldo, n_parts, part_stride, rowsum, Nq, c, al, na, labels, out_logits, \
+                          pred, top1, top5)
+  if (C <= 128) SC_EPI_REG(4);
+  else if (C <= 256) SC_EPI_REG(8);
+  else if (C <= 512) SC_EPI_REG(16);
+  else if (C <= 1024) SC_EPI_REG(32);
+  else
+    epilogue_kernel<<<blocks, 256, 0, st>>>(Z, ldz, O, ldo, n_parts, part_stride, rowsum, Nq, C, al, na, labels,
+                                            out_logits, pred, top1, top5);
+#undef SC_EPI_REG
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+int sc_epilogue(const float* Z, int64_t ldz, const float* O, int64_t ldo, const float* rowsum,
+                int64_t Nq, int64_t C, const float* alphas, int na, const int32_t* labels,
+                float* out_logits, int32_t* pred, int32_t* top1, int32_t* top5, void* stream) {
+  return sc_epilogue_parts(Z, ldz, O, ldo, 1, 0, rowsum, Nq, C, alphas, na, labels, out_logits, pred, top1, top5, stream);
 }
 
 }  // extern "C"

@@ -316,6 +316,36 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     return merge_partials(O)
 
 
+def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float], splits: int = 0,
+                        merge: bool = True) -> list:
+    """`attn_fwd_hard` for a LIST of betas: one tensor-core pass per group of up to 4 betas (S = Q.K^T does not
+    depend on beta; only the exponentials are per beta).  Returns one fp32 [Nq, n_classes] tensor per beta
+    (merge=False: the unmerged [splits, Nq, n_classes] partial tiles, which `epilogue` sums on the fly)."""
+    _cuda(Qn, "Qn")
+    Ks = bank.rows
+    assert Ks is not None, "HardBank.gather(k_norm) must be called first"
+    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16) and Ks.is_contiguous() and Qn.is_contiguous()
+    Nq, D_pad = Qn.shape
+    assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
+    n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)
+    if splits <= 0:
+        splits = attn_hard_splits(Nq, n_sorted, Qn.device)
+    lib = _lib.load()
+    outs = []
+    betas = [float(b) for b in betas]
+    for g0 in range(0, len(betas), 4):
+        grp = betas[g0:g0 + 4]
+        O = torch.empty((len(grp), splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)   # zeroed by the library
+        arr = (ctypes.c_float * len(grp))(*grp)
+        with torch.cuda.device(Qn.device):
+            check(lib.sc_attn_fwd_hard_multi(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kbits), _code(Qn), Nq, n_sorted,
+                                             D_pad, n_classes, arr, len(grp), splits, _ptr(O), n_classes, _stream()),
+                  "sc_attn_fwd_hard_multi")
+        for bi in range(len(grp)):
+            outs.append(O[bi] if not merge else O[bi, 0] if splits == 1 else merge_partials(O[bi]))
+    return outs
+
+
 def attn_hard_splits(Nq: int, Nks: int, device=None) -> int:
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
     return int(_lib.load().sc_attn_hard_splits(Nq, Nks, sms))
@@ -440,9 +470,14 @@ def epilogue(Z: Optional[torch.Tensor], O: torch.Tensor, alphas: Sequence[float]
              labels: Optional[torch.Tensor] = None, rowsum: Optional[torch.Tensor] = None,
              want_logits: bool = False, want_pred: bool = True):
     """out = Z + O * alpha for each alpha; returns dict(pred int32 [na, Nq], top1/top5 int32 [na] counts,
-    logits fp32 [na, Nq, C] if requested)."""
+    logits fp32 [na, Nq, C] if requested).  O is [Nq, C], or the UNMERGED [n_parts, Nq, C] partial tiles of a
+    key-split attention launch (summed on the fly, bit-identical to merge_partials first)."""
     _cuda(O, "O")
-    assert O.dtype == torch.float32 and O.stride(1) == 1
+    assert O.dtype == torch.float32 and O.stride(-1) == 1 and O.dim() in (2, 3)
+    n_parts, part_stride = 1, 0
+    if O.dim() == 3:
+        n_parts, part_stride = O.shape[0], O.stride(0)
+        O = O[0]
     Nq, C = O.shape
     if Z is not None:
         _cuda(Z, "Z")
@@ -460,7 +495,8 @@ def epilogue(Z: Optional[torch.Tensor], O: torch.Tensor, alphas: Sequence[float]
     if rowsum is not None:
         rowsum = _cuda(rowsum, "rowsum").to(torch.float32).contiguous()
     with torch.cuda.device(dev):
-        check(_lib.load().sc_epilogue(_ptr(Z), Z.stride(0) if Z is not None else C, _ptr(O), O.stride(0),
-                                      _ptr(rowsum), Nq, C, arr, na, _ptr(labels), _ptr(logits), _ptr(pred),
-                                      _ptr(top1), _ptr(top5), _stream()), "sc_epilogue")
+        check(_lib.load().sc_epilogue_parts(_ptr(Z), Z.stride(0) if Z is not None else C, _ptr(O), O.stride(0),
+                                            n_parts, part_stride, _ptr(rowsum), Nq, C, arr, na, _ptr(labels),
+                                            _ptr(logits), _ptr(pred), _ptr(top1), _ptr(top5), _stream()),
+              "sc_epilogue")
     return {"pred": pred, "top1": top1, "top5": top5, "logits": logits}

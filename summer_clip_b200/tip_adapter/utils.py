@@ -53,6 +53,24 @@ class TipAdapterHead:
             return ops.attn_fwd_hard(self.q, self.values.hard_bank(self.k), beta)
         return ops.attn_fwd(self.q, self.k, self.values.vt(self.q.dtype), self.n_keys, self.n_classes, beta)
 
+    def cache_logits_many(self, betas: tp.Sequence[float]) -> tp.List[torch.Tensor]:
+        """cache_logits for a list of betas; one-hot values share the tensor-core pass between groups of 4."""
+        if self.values.is_hard:
+            return ops.attn_fwd_hard_multi(self.q, self.values.hard_bank(self.k), betas)
+        return [self.cache_logits(b) for b in betas]
+
+    def top1_counts_many(self, betas: tp.Sequence[float], alphas: tp.Sequence[float], labels: torch.Tensor) -> torch.Tensor:
+        """[len(betas), len(alphas)] top-1 counts, in chunks of 16 betas (bounded memory)."""
+        rows = []
+        for s in range(0, len(betas), 8):
+            if self.values.is_hard:       # unmerged key-split tiles: the epilogue sums them as it reads
+                outs = ops.attn_fwd_hard_multi(self.q, self.values.hard_bank(self.k), betas[s:s + 8], merge=False)
+            else:
+                outs = self.cache_logits_many(betas[s:s + 8])
+            for o in outs:
+                rows.append(ops.epilogue(self.clip_logits, o, alphas, labels=labels, want_pred=False)["top1"])
+        return torch.stack(rows)
+
     def logits(self, beta: float, alpha: float) -> torch.Tensor:
         """tip_logits = clip_logits + cache_logits * alpha (tip_adapter.py:68)."""
         return ops.epilogue(self.clip_logits, self.cache_logits(beta), [alpha], want_logits=True, want_pred=False)["logits"][0]
@@ -70,7 +88,7 @@ def search_hp(cfg, cache_keys, cache_values, features, labels, clip_weights, ada
 
         head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
         n = labels.shape[0]
-        counts = torch.stack([head.top1_counts(beta, alpha_list, labels) for beta in beta_list]).cpu()  # one D2H
+        counts = head.top1_counts_many(beta_list, alpha_list, labels).cpu()                             # one D2H
 
         best_acc = 0
         for bi, beta in enumerate(beta_list):

@@ -417,6 +417,76 @@ def test_hard_label_segmented_kernel_random_shapes(ops):
                                        msg=lambda m: f"case {case} nq={nq} nk={nk} D={dim} C={c} splits={splits}: {m}")
 
 
+@pytest.mark.parametrize("nq,c", [(1, 1), (37, 5), (300, 128), (257, 129), (100, 397), (64, 1000), (50, 1024), (40, 1025), (33, 3000)])
+def test_alpha_epilogue_kernel(ops, nq, c):
+    """sc_epilogue / sc_epilogue_parts == torch `Z + O * alpha` -> argmax / top-1 / top-5 (image_attention.py:111-117,
+    clip_searcher/utils.py:15-21) bit for bit, on the register path (C <= 1024) and the generic one: ties with the
+    label's value and with the maximum (first index wins), -inf rows, labels out of range (not counted), missing Z,
+    row-sum normalisation, and unmerged partial tiles (== merge_partials first)."""
+    g = torch.Generator().manual_seed(93 + c)
+    Z = (torch.randn(nq, c, generator=g) * 3).cuda()
+    O = torch.rand(3, nq, c, generator=g).cuda()
+    O[:, :, ::3] = (O[:, :, ::3] * 4).round() / 4                  # many exact ties
+    Z[:, ::3] = Z[:, ::3].round()
+    if nq > 4:
+        Z[1], O[:, 1] = 0.0, 1.0                                   # a whole row of equal values
+        Z[2] = float("-inf")
+        Z[3, c // 2] = float("inf")
+    labels = torch.randint(0, c, (nq,), generator=g).int().cuda()
+    if nq > 8:
+        labels[5], labels[6] = -1, c + 3
+    alphas = [0.0, 0.25, 1.0, 4.0, 17.5]
+    merged = ops.merge_partials(O)
+    for z, rowsum in ((Z, None), (None, None), (Z, merged.sum(1) + 1.0)):
+        res = ops.epilogue(z, merged, alphas, labels=labels, rowsum=rowsum, want_logits=True)
+        from_parts = ops.epilogue(z, O, alphas, labels=labels, rowsum=rowsum, want_logits=True)
+        counts_only = ops.epilogue(z, O, alphas, labels=labels, rowsum=rowsum, want_pred=False)
+        o = merged if rowsum is None else merged * (1.0 / rowsum)[:, None]
+        valid = (labels >= 0) & (labels < c)
+        lab = labels.long().clamp(0, c - 1)
+        for ai, alpha in enumerate(alphas):
+            want = o * alpha if z is None else z + o * alpha
+            assert torch.equal(res["logits"][ai], want)
+            assert torch.equal(res["pred"][ai].long(), want.argmax(dim=1)), (nq, c, alpha)
+            vlab = want.gather(1, lab[:, None])
+            ahead = ((want > vlab) | ((want == vlab) & (torch.arange(c, device="cuda")[None, :] < lab[:, None]))).sum(1)
+            assert int(res["top1"][ai]) == int(((ahead == 0) & valid).sum())
+            assert int(res["top5"][ai]) == int(((ahead < 5) & valid).sum())
+        for k in ("logits", "pred", "top1", "top5"):
+            assert torch.equal(res[k], from_parts[k]), k
+        assert counts_only["pred"] is None
+        assert torch.equal(counts_only["top1"], res["top1"]) and torch.equal(counts_only["top5"], res["top5"])
+
+
+def test_beta_sweep_shares_the_tensor_core_pass(ops):
+    """sc_attn_fwd_hard_multi: up to 4 betas per launch off one S = Q.K^T; every beta's slab is bit-identical to
+    its own single-beta launch (same arithmetic, same summation order), for any group size and ragged shapes; the
+    strategy-level sweep (FusedWeights.matmul_many, TipAdapterHead.cache_logits_many) goes through it."""
+    from summer_clip_b200.clip_searcher.cache_value_strategy import GoldCacheValues
+    from summer_clip_b200.clip_searcher.cache_weights_strategy import FusedWeights, TipAdapterWeightsStrategy, _BANKS
+    g = torch.Generator().manual_seed(91)
+    for nq, nk, dim, c in [(300, 3000, 192, 37), (129, 257, 64, 300), (513, 9000, 512, 1000)]:
+        Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+        Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
+        labels = torch.randint(0, c, (nk,), generator=g).int().cuda()
+        bank = ops.hard_bank_layout(labels, c).gather(Kn)
+        betas = [0.1, 1.0, 1.5, 3.5, 5.5, 7.5, 9.5, 11.5, 0.0]          # image_attention.yaml's sweep + a 1-beta tail group
+        for n in (1, 2, 3, 4, 9):
+            outs = ops.attn_fwd_hard_multi(Qn, bank, betas[:n])
+            assert len(outs) == n
+            for beta, O in zip(betas[:n], outs):
+                assert torch.equal(O, ops.attn_fwd_hard(Qn, bank, beta)), (nq, nk, dim, c, n, beta)
+        outs = ops.attn_fwd_hard_multi(Qn, bank, betas[:4], splits=3)
+        for beta, O in zip(betas[:4], outs):
+            assert torch.equal(O, ops.attn_fwd_hard(Qn, bank, beta, splits=3))
+    _BANKS.clear()
+    Q, K = torch.randn(64, 200, generator=g).cuda(), torch.randn(64, 1500, generator=g).cuda()
+    gold = GoldCacheValues(20).transform(torch.randint(0, 20, (1500,), generator=g).cuda())
+    ws = [TipAdapterWeightsStrategy(b).transform(Q, K) for b in (0.1, 1.0, 5.5, 7.5, 11.5)]
+    for w, many in zip(ws, FusedWeights.matmul_many(ws, gold)):
+        assert torch.equal(many, w @ gold)
+
+
 def test_hard_values_route_through_the_segmented_kernel(ops, monkeypatch):
     """HardCacheStrategy / gold labels / one-hot Tip-Adapter cache values all become a label-sorted bank; the
     dense-values route (SUMMER_CLIP_B200_DENSE_VALUES=1) gives the same logits."""
