@@ -183,6 +183,13 @@ def run_ours(args):
     labels_dev = labels
     stream = torch.cuda.current_stream()
     launches = {"n": 0}
+    phase_marks = None                                     # --phases: [(name, event)] of the step being decomposed
+
+    def mark(name):
+        if phase_marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            phase_marks.append((name, ev))
 
     per_q = -(-nq // world)
 
@@ -192,12 +199,21 @@ def run_ours(args):
         counters all-reduced (searcher.exchange_partials / ClipSearcher._search_sharded)."""
         if world == 1:
             z = ops.zero_shot_logits(q_src, True, searcher.text, t_split=searcher.text_split)
-            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)
+            mark("zero_shot")
+            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)   # sums the unmerged key-split tiles as it reads
+            mark("epilogue")
             launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
             return res["pred"], torch.stack([res["top1"], res["top5"]])
+        if o_part.dim() == 3:
+            o_part = ops.merge_partials(o_part)
+            launches["n"] += 1
+            mark("merge_splits")
         o_mine, lo, hi = exchange_partials(o_part, group)
+        mark("reduce_scatter")
         z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text, t_split=searcher.text_split)
+        mark("zero_shot")
         res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[lo:hi].contiguous())
+        mark("epilogue")
         launches["n"] += 3
         counts = torch.stack([res["top1"], res["top5"]])
         dist.all_reduce(counts, group=group)
@@ -205,19 +221,22 @@ def run_ours(args):
         mine[:, : hi - lo] = res["pred"]
         pred_all = torch.empty((world, 1, per_q), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(pred_all, mine, group=group)
+        mark("counters_and_predictions")
         return pred_all.permute(1, 0, 2).reshape(1, world * per_q)[:, :nq], counts
 
     def step_device(time_attn=None):
         """Inputs resident in HBM."""
+        mark("start")
         qn = ops.normalize_cast(q_bank, True)
+        mark("normalize_queries")
         if time_attn is not None:
             time_attn[0].record(stream)
         part = attn(qn, False)
         if time_attn is not None:
             time_attn[1].record(stream)
-        o = ops.merge_partials(part) if splits > 1 else part[0]
-        launches["n"] += 2 + int(splits > 1)
-        pred, counts = finish(q_bank, labels_dev, o)
+        mark("attention")
+        launches["n"] += 2
+        pred, counts = finish(q_bank, labels_dev, part if splits > 1 else part[0])
         return {"pred": pred, "top1": counts[0], "top5": counts[1]}
 
     # e2e: the query bank and labels come from pinned host memory every step and the predictions + counters go
@@ -243,8 +262,8 @@ def run_ours(args):
         torch.cuda.current_stream().wait_event(copy_done[i % 2])
         q_dev, lab = q_bufs[i % 2], lab_bufs[i % 2]
         qn = ops.normalize_cast(q_dev, True)
-        o = attn(qn, True)
-        pred, counts = finish(q_dev, lab, o)
+        part = attn(qn, False)
+        pred, counts = finish(q_dev, lab, part if splits > 1 else part[0])
         pred = pred.to("cpu", non_blocking=True)
         counts = counts.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -302,6 +321,18 @@ def run_ours(args):
     sync_all()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
+    phases = None
+    if args.phases:                                        # untimed extra steps, decomposed with events on the stream
+        acc = {}
+        for _ in range(3):
+            phase_marks = []
+            step_device()
+            sync_all()
+            for (_, e0), (name, e1) in zip(phase_marks[:-1], phase_marks[1:]):
+                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1) / 3
+        phase_marks = None
+        phases = {k: round(v, 4) for k, v in acc.items()}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -351,6 +382,8 @@ def run_ours(args):
         "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
+    if phases is not None:
+        out["phases_ms"] = phases
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(nq, nk, dim, n_classes, budget_s=args.cpu_budget)
     print(json.dumps(out), flush=True)
@@ -449,6 +482,7 @@ def main():
     ap.add_argument("--nq", type=int, default=0, help="override the number of queries (debug)")
     ap.add_argument("--op-dtype", default="", choices=["", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="add phases_ms: rank 0's per-phase device times of extra untimed steps")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,38 @@ merge_kernel(const float* __restrict__ parts, int n_parts, int64_t rows, int64_t
   }
 }
 
+// cols, ld, ld_out multiples of 4 and 16-byte aligned bases: 16-byte loads, one row segment per thread, all parts
+// of a vector in flight before the adds (same summation order as merge_kernel)
+template <int kParts>
+__global__ void __launch_bounds__(256)
+merge_vec_kernel(const float4* __restrict__ parts, int n_parts, int64_t rows, int cols4, int64_t ld4,
+                 float4* __restrict__ out, int64_t ld_out4) {
+  const int64_t part_stride = rows * ld4;
+  const int64_t total = rows * cols4;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / cols4;
+    const int c = static_cast<int>(e - r * cols4);
+    const float4* src = parts + r * ld4 + c;
+    float4 s;
+    if (kParts > 0) {
+      float4 v[kParts > 0 ? kParts : 1];
+#pragma unroll
+      for (int p = 0; p < kParts; ++p) v[p] = __ldcs(src + p * part_stride);
+      s = v[0];
+#pragma unroll
+      for (int p = 1; p < kParts; ++p) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+    } else {
+      s = __ldcs(src);
+      for (int p = 1; p < n_parts; ++p) {
+        const float4 v = __ldcs(src + p * part_stride);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    out[r * ld_out4 + c] = s;
+  }
+}
+
 // fp32 SIMT GEMM, 64 x 64 output tile per block, 4 x 4 per thread, K step 16.
 //   Z[n, c] = scale / ||X[:, n]|| * sum_d X[d, n] * T[d, c]
 template <typename TX, typename TT>
@@ -178,17 +210,25 @@ epilogue_reg_kernel(const float* __restrict__ Z, int64_t ldz, const float* __res
     const float inv = rowsum ? 1.0f / rowsum[q] : 1.0f;
     float z[NV], o[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {                       // padding classes: -inf + 0 * alpha never wins
+    for (int j = 0; j < NV; ++j) {
       const int c = j * 32 + lane;
-      z[j] = c < C ? (zrow ? zrow[c] : 0.f) : kNegInf;
-      o[j] = c < C ? orow[c] : 0.f;
+      o[j] = c < C ? __ldg(orow + c) : 0.f;
     }
-    for (int p = 1; p < n_parts; ++p) {
+    for (int p = 1; p < n_parts; ++p) {                  // a whole part row in flight before the first add
+      float t[NV];
+      const float* prow = orow + p * part_stride;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int c = j * 32 + lane;
-        if (c < C) o[j] += orow[p * part_stride + c];
+        t[j] = c < C ? __ldg(prow + c) : 0.f;
       }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) o[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {                       // padding classes: -inf + 0 * alpha never wins
+      const int c = j * 32 + lane;
+      z[j] = c < C ? (zrow ? __ldg(zrow + c) : 0.f) : kNegInf;
     }
     if (rowsum) {
 #pragma unroll
@@ -304,9 +344,27 @@ int sc_merge_partials(const float* parts, int n_parts, int64_t rows, int64_t col
   SC_REQUIRE(n_parts >= 1 && rows >= 0 && cols >= 0 && ld >= cols && ld_out >= cols, SC_ESHAPE,
              "sc_merge_partials: bad shape");
   if (rows * cols == 0) return SC_OK;
-  const int64_t want = sc::ceil_div(rows * cols, 256);
-  const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
-  merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(parts, n_parts, rows, cols, ld, out, ld_out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0 && cols / 4 <= 0x7fffffff &&
+                   (reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+  if (vec) {
+    const int64_t want = sc::ceil_div(rows * (cols / 4), 256);
+    const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+    const float4* p4 = reinterpret_cast<const float4*>(parts);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const int c4 = static_cast<int>(cols / 4);
+    switch (n_parts) {
+      case 2: merge_vec_kernel<2><<<blocks, 256, 0, st>>>(p4, n_parts, rows, c4, ld / 4, o4, ld_out / 4); break;
+      case 3: merge_vec_kernel<3><<<blocks, 256, 0, st>>>(p4, n_parts, rows, c4, ld / 4, o4, ld_out / 4); break;
+      case 4: merge_vec_kernel<4><<<blocks, 256, 0, st>>>(p4, n_parts, rows, c4, ld / 4, o4, ld_out / 4); break;
+      case 8: merge_vec_kernel<8><<<blocks, 256, 0, st>>>(p4, n_parts, rows, c4, ld / 4, o4, ld_out / 4); break;
+      default: merge_vec_kernel<0><<<blocks, 256, 0, st>>>(p4, n_parts, rows, c4, ld / 4, o4, ld_out / 4); break;
+    }
+  } else {
+    const int64_t want = sc::ceil_div(rows * cols, 256);
+    const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+    merge_kernel<<<blocks, 256, 0, st>>>(parts, n_parts, rows, cols, ld, out, ld_out);
+  }
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }

@@ -458,6 +458,19 @@ def test_alpha_epilogue_kernel(ops, nq, c):
         assert torch.equal(counts_only["top1"], res["top1"]) and torch.equal(counts_only["top5"], res["top5"])
 
 
+@pytest.mark.parametrize("n_parts,rows,cols", [(1, 5, 8), (2, 300, 1000), (3, 513, 1000), (5, 100, 400), (8, 64, 1024),
+                                               (3, 77, 397), (4, 10, 3)])
+def test_merge_partials_is_the_ordered_sum(ops, n_parts, rows, cols):
+    """sc_merge_partials (16-byte vector path when the row length allows it, scalar otherwise) == p0 + p1 + ... in that
+    order, bit for bit — the order sc_epilogue_parts and the key-sharded exchange rely on."""
+    g = torch.Generator().manual_seed(97)
+    parts = (torch.randn(n_parts, rows, cols, generator=g) * 10.0 ** torch.randint(-3, 4, (n_parts, 1, 1), generator=g)).cuda()
+    want = parts[0].clone()
+    for p in range(1, n_parts):
+        want += parts[p]
+    assert torch.equal(ops.merge_partials(parts), want)
+
+
 def test_beta_sweep_shares_the_tensor_core_pass(ops):
     """sc_attn_fwd_hard_multi: up to 4 betas per launch off one S = Q.K^T; every beta's slab is bit-identical to
     its own single-beta launch (same arithmetic, same summation order), for any group size and ragged shapes; the
