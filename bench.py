@@ -148,7 +148,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     if args.op_dtype:
-        ops.OP_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.op_dtype]
+        ops.OP_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16, "e4m3": ops.E4M3}[args.op_dtype]
 
     nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
     if args.nq:
@@ -359,7 +359,7 @@ def run_ours(args):
         "metric": "clip_search_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16" if ops.OP_DTYPE == torch.float16 else "bf16", "data": "synthetic",
+        "dtype": {torch.float16: "f16", torch.bfloat16: "bf16"}.get(ops.OP_DTYPE, "e4m3 (opt-in reduced precision; NOT the headline)"), "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
                    "n_classes": n_classes, "beta": BETA, "alpha": ALPHA, "values": "hard (one-hot of argmax L)",
                    "sharding": f"key-sharded x{world}: reduce-scatter of the partial tiles, each rank finishes its query slice" if world > 1 else "single GPU",
@@ -480,7 +480,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="imagenet_rn50", choices=sorted(WORKLOADS))
     ap.add_argument("--nq", type=int, default=0, help="override the number of queries (debug)")
-    ap.add_argument("--op-dtype", default="", choices=["", "fp16", "bf16"])
+    ap.add_argument("--op-dtype", default="", choices=["", "fp16", "bf16", "e4m3"],
+                    help="tensor-core operand type of the feature banks (default fp16; e4m3 is the opt-in 8-bit mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", action="store_true", help="add phases_ms: rank 0's per-phase device times of extra untimed steps")
     ap.add_argument("--cpu-budget", type=float, default=20.0)

@@ -33,8 +33,13 @@ extern "C" {
 
 #define SC_ABI_VERSION 1
 
-/* element types of caller buffers */
-enum { SC_F16 = 0, SC_BF16 = 1, SC_F32 = 2 };
+/* element types of caller buffers.  SC_E4M3 (8-bit float, 4 exponent / 3 mantissa bits) is an OPERAND type only:
+ * sc_normalize_cast can write it and sc_attn_fwd_hard[_multi] can read it (tcgen05 kind::f8f6f4, fp32 accumulate:
+ * half the bank bytes and twice the contraction length per instruction of the 16-bit types).  e4m3 rows hold
+ * SC_E4M3_SCALE * x, so that unit-norm feature rows (|x| <= 1, typically 1/sqrt(D)) sit in the normal range;
+ * the attention kernel divides the scale back out.  Reduced precision: opt-in, see DESIGN.md for measured error. */
+enum { SC_F16 = 0, SC_BF16 = 1, SC_F32 = 2, SC_E4M3 = 3 };
+#define SC_E4M3_SCALE 256.0f
 /* sc_rowconf modes: rank rows by the raw maximum (TopKStrategy, cache_strategy.py:67-70) or by
  * the maximum of softmax(scale * row) (TopKProbStrategy, cache_strategy.py:79-81). */
 enum { SC_CONF_RAW = 0, SC_CONF_PROB = 1 };
@@ -52,6 +57,7 @@ const char* sc_last_error(void);
  *   Vt [C_pad, Nk_pad] (same type; cache values TRANSPOSED, zero padded),
  * where D_pad = sc_pad_dim(D), Nk_pad = sc_pad_keys(Nk), C_pad = sc_pad_classes(C). */
 int64_t sc_pad_dim(int64_t D);          /* multiple of 64 */
+int64_t sc_pad_dim_op(int64_t D, int op_dtype);  /* row length for an operand type: 128-byte chunks (64 16-bit / 128 e4m3) */
 int64_t sc_pad_keys(int64_t Nk);        /* multiple of 8  */
 int64_t sc_pad_classes(int64_t C);      /* n_slices * slice width (multiple of 16, <= 256) */
 int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C classes */
@@ -61,7 +67,8 @@ int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C cla
  *   src: element (d, n) at src[d*stride_d + n*stride_n], d < D, n < N, dtype src_dtype.
  *   idx: optional int64[n_out] column indices (NULL: n_out must equal N, identity).
  *   dst: [n_out, D_pad] of dst_dtype (SC_BF16 or SC_F16 — the tensor-core operand type, see
- *        sc_attn_fwd); columns D..D_pad-1 are written as zero.
+ *        sc_attn_fwd — or SC_E4M3 with D_pad = sc_pad_dim_op(D, SC_E4M3), values scaled by SC_E4M3_SCALE,
+ *        round-to-nearest, for sc_attn_fwd_hard); columns D..D_pad-1 are written as zero.
  *   normalize: 1 = divide by the column's L2 norm (fp32), 0 = cast only. */
 int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
                       int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst, int dst_dtype,

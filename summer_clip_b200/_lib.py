@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
-SC_F16, SC_BF16, SC_F32 = 0, 1, 2
+SC_F16, SC_BF16, SC_F32, SC_E4M3 = 0, 1, 2, 3
+SC_E4M3_SCALE = 256.0
 SC_CONF_RAW, SC_CONF_PROB = 0, 1
 SC_VALUES_HARD, SC_VALUES_SOFTMAX = 0, 1
 
@@ -21,6 +22,7 @@ SIGNATURES = {
     "sc_version": (c_int, []),
     "sc_last_error": (c_char_p, []),
     "sc_pad_dim": (c_int64, [c_int64]),
+    "sc_pad_dim_op": (c_int64, [c_int64, c_int]),
     "sc_pad_keys": (c_int64, [c_int64]),
     "sc_pad_classes": (c_int64, [c_int64]),
     "sc_class_slice": (c_int64, [c_int64]),

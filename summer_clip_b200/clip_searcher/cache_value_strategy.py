@@ -64,13 +64,13 @@ class CacheValues:
         """Arbitrary dense [Nk, C] values (e.g. Tip-Adapter's one-hot fp16 cache_values): transpose + cast +
         pad with the cast-only mode of the normalise kernel."""
         n_keys, n_classes = values.shape
-        op_dtype = ops._op(op_dtype)
         if ops.hard_supported(n_classes) and n_keys > 0:
             # one-hot rows (Tip-Adapter cache_values, tip_adapter/utils.py:62) -> labels for the hard-label kernel
             rows = values if values.stride(1) == 1 else values.contiguous()
             conf, label = ops.rowconf(rows)
             if bool(((conf == 1) & (rows.float().abs().sum(1) == 1)).all()):
                 return CacheValues(None, n_keys, n_classes, labels16=ops.hard_labels(None, n_classes, labels=label))
+        op_dtype = ops._op(op_dtype)                                      # dense values: 16-bit operands only
         c_pad, nk_pad = ops.pad_classes(n_classes), ops.pad_dim(n_keys)   # pad_dim: multiple of 64 (and of 8)
         vt = torch.zeros((c_pad, nk_pad), dtype=op_dtype, device=values.device)
         ops.normalize_cast(values, feature_major=True, normalize=False, out=vt)

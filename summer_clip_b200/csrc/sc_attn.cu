@@ -37,7 +37,8 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
 // sc_attn_seg.cu
 int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count);
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
-                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
+                    int (*make_tmap_u8)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int),
+                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, int op_dtype, int64_t Nq,
                     int64_t Nks, int64_t D_pad, const float* betas, int n_betas, int splits, float* O, int64_t ldo,
                     cudaStream_t st);
 int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
@@ -427,6 +428,21 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return SC_OK;
 }
 
+// e4m3 operand rows: bytes as elements, 128-byte (128-element) boxes, same 128-byte swizzle
+int make_tmap_u8(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SC_REQUIRE(fn != nullptr, SC_EDRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_elems)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(2 * kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SC_REQUIRE(r == CUDA_SUCCESS, SC_EDRIVER, "cuTensorMapEncodeTiled (u8) failed with CUresult %d", (int)r);
+  return SC_OK;
+}
+
 // number of class slices: 1, 2 or a multiple of 4 (so the slices of one query tile fill whole clusters)
 int64_t n_class_slices(int64_t C) {
   const int64_t c16 = sc::round_up(C, 16);
@@ -466,6 +482,7 @@ int launch(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap
 extern "C" {
 
 int64_t sc_pad_dim(int64_t D) { return sc::round_up(D, 64); }
+int64_t sc_pad_dim_op(int64_t D, int op_dtype) { return sc::round_up(D, op_dtype == SC_E4M3 ? 128 : 64); }
 int64_t sc_pad_keys(int64_t Nk) { return sc::round_up(Nk, 8); }
 int64_t sc_class_slice(int64_t C) { return class_slice(C); }
 int64_t sc_pad_classes(int64_t C) {
@@ -501,12 +518,13 @@ int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_
                            const float* betas, int n_betas, int splits, float* O, int64_t ldo, void* stream) {
   SC_REQUIRE(Qn && Ks && group_class && key_bits && O && betas, SC_EINVAL, "sc_attn_fwd_hard: null pointer");
   SC_REQUIRE(n_betas >= 1 && n_betas <= 4, SC_ESHAPE, "sc_attn_fwd_hard_multi: n_betas=%d must be in [1, 4]", n_betas);
-  SC_REQUIRE(op_dtype == SC_F16 || op_dtype == SC_BF16, SC_EINVAL, "sc_attn_fwd_hard: op_dtype must be SC_F16 or SC_BF16");
+  SC_REQUIRE(op_dtype == SC_F16 || op_dtype == SC_BF16 || op_dtype == SC_E4M3, SC_EINVAL,
+             "sc_attn_fwd_hard: op_dtype must be SC_F16, SC_BF16 or SC_E4M3");
   SC_REQUIRE(Nq > 0 && Nks > 0 && n_classes > 0, SC_ESHAPE, "sc_attn_fwd_hard: empty problem");
   SC_REQUIRE(sc_attn_hard_supported(n_classes), SC_EUNSUPPORTED, "sc_attn_fwd_hard: n_classes=%lld exceeds int16 labels",
              (long long)n_classes);
-  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_attn_fwd_hard: D_pad=%lld must be a multiple of 64",
-             (long long)D_pad);
+  SC_REQUIRE(D_pad > 0 && D_pad % (op_dtype == SC_E4M3 ? 128 : 64) == 0, SC_ESHAPE,
+             "sc_attn_fwd_hard: D_pad=%lld must be a multiple of %d", (long long)D_pad, op_dtype == SC_E4M3 ? 128 : 64);
   SC_REQUIRE(ldo >= n_classes, SC_ESHAPE, "sc_attn_fwd_hard: ldo < n_classes");
   SC_REQUIRE((reinterpret_cast<uintptr_t>(Qn) | reinterpret_cast<uintptr_t>(Ks) |
               reinterpret_cast<uintptr_t>(group_class) | reinterpret_cast<uintptr_t>(key_bits)) % 32 == 0,
@@ -521,7 +539,7 @@ int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_
   }
   SC_REQUIRE(splits <= steps_total && splits <= 65535, SC_ESHAPE,
              "sc_attn_fwd_hard: splits=%d exceeds the %lld key steps", splits, (long long)steps_total);
-  int rc = sc::attn_seg_launch(&make_tmap, Qn, Ks, group_class, key_bits, op_dtype == SC_F16, Nq, Nks, D_pad, betas,
+  int rc = sc::attn_seg_launch(&make_tmap, &make_tmap_u8, Qn, Ks, group_class, key_bits, op_dtype, Nq, Nks, D_pad, betas,
                                n_betas, splits, O, ldo, static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());

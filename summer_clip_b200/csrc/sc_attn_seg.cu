@@ -83,7 +83,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // in image_attention.yaml, 200 in Tip-Adapter's search_hp) pays GEMM-1 once per kNB betas; the exp warps then do
 // kNB exponentials per S element — 2048 MUFU cycles per beta and step against 8192 cycles of UMMAs, so kNB = 4
 // balances the two pipes.
-template <bool kF16, bool kGemm, int kNB>
+template <int kOp, bool kGemm, int kNB>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmK2, const SParams p) {
@@ -105,6 +105,8 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int s1 = static_cast<int>((static_cast<long long>(p.steps_total) * (split + 1)) / p.splits);
   const int nsteps = s1 - s0;
   const int nd = p.n_dchunks;
+  constexpr bool kF8 = (kOp == SC_E4M3);
+  constexpr int kChunkElems = kF8 ? 2 * kBK : kBK;      // elements in a 128-byte operand row
   constexpr int kPasses = kGemm ? 3 : 1;      // operand passes accumulated into one S tile
 
 #ifdef SC_ATTN_TIMING_EXPERIMENTS
@@ -160,7 +162,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // chunks of step st + pf_dist into L2 ahead of the pack
       if (!kGemm && p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
         if (elect_one()) {
-          for (int d = 0; d < nd; ++d) tma_prefetch_2d(&tmK, d * kBK, krow + p.pf_dist * kStepKeys);
+          for (int d = 0; d < nd; ++d) tma_prefetch_2d(&tmK, d * kChunkElems, krow + p.pf_dist * kStepKeys);
         }
         __syncwarp();
       }
@@ -175,7 +177,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const bool wrap = (stage + 1 == kNS);
           const uint32_t dst = ring0 + stage * kStage;
           ready = __all_sync(0xffffffffu,
-                             tma2_cg2_probe(dst, mq, d * kBK, q0, qon, dst + 16384, mk, d * kBK, krow, kon,
+                             tma2_cg2_probe(dst, mq, d * kChunkElems, q0, qon, dst + 16384, mk, d * kChunkElems, krow, kon,
                                             full0c + stage * 8, full0 + stage * 8, tx, plain,
                                             empty0 + (wrap ? 0 : stage + 1) * 8, (wrap ? phase ^ 1u : phase) ^ 1u));
           if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
@@ -187,7 +189,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ===================================================== MMA issuer for the pair
       int stage = 0;
       uint32_t phase = 0, ready = 0;
-      const uint32_t idesc = umma_idesc_16b(256, 256, kF16);
+      const uint32_t idesc = umma_idesc_16b(256, 256, kOp != SC_BF16);
       const uint32_t full0 = smem_u32(&bars->full[0]);
       const uint32_t empty0 = smem_u32(&bars->empty[0]);
       const uint32_t en = (p.dbg & 16) ? 0u : 1u;
@@ -205,7 +207,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage);             // Q chunk: my 128 queries
           const uint64_t b_desc = umma_desc_k128(ring0 + stage * kStage + 16384);     // K chunk: my 128 keys
           ready = __all_sync(0xffffffffu,
-                             umma4_cg2_probe(tmem_s, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc, b_desc + 2,
+                             umma4_cg2_probe<kF8>(tmem_s, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc, b_desc + 2,
                                              b_desc + 4, b_desc + 6, idesc, dd != 0 ? 1u : 0u, en, empty0 + stage * 8,
                                              pair_mask, sfull, pair_mask, dd == nd * kPasses - 1 ? 1u : 0u,
                                              full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
@@ -252,7 +254,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) {
           if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
-          else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), 0);
+          else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
         }
       }
     } else {
@@ -263,6 +265,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;     // beta bi: + bi * o_beta_stride
     const bool q_ok = q < p.Nq;
     int cur = -1;          // class of the running sums (warp-uniform)
+    uint32_t cur_pair = 0xffffffffu;      // cur in both halves of a word (the group-class word of a chunk that continues it)
     float acc[kNB];
 #pragma unroll
     for (int bi = 0; bi < kNB; ++bi) acc[bi] = 0.f;
@@ -287,6 +290,23 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // 32 columns (two 16-key groups) per TMEM load, double buffered: the load of chunk cc+1 is in flight
       // while chunk cc is exponentiated and summed
       auto consume = [&](const uint32_t (&rg)[32], int cc) {
+        // common case (a class is ~80 groups long on ImageNet): both 16-key groups of the chunk continue the running
+        // class with every key valid -> straight-line code, the two groups' sums interleave and the MUFU pipe
+        // never drains.  Same arithmetic and summation order as the general path below (bit-identical results).
+        if (gw[cc] == cur_pair && kw[cc] == 0xffffffffu) {
+#pragma unroll
+          for (int bi = 0; bi < kNB; ++bi) {
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              sa += ex2_approx(fmaf(__uint_as_float(rg[j]), c1[bi], cadd[bi]));
+              sb += ex2_approx(fmaf(__uint_as_float(rg[16 + j]), c1[bi], cadd[bi]));
+            }
+            acc[bi] += sa;
+            acc[bi] += sb;
+          }
+          return;
+        }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int cls = static_cast<int>(static_cast<int16_t>((gw[cc] >> (16 * hh)) & 0xffffu));
@@ -294,6 +314,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (cls != cur) {                              // warp-uniform: the finished class sums go out
             flush();
             cur = cls;
+            cur_pair = (static_cast<uint32_t>(cls) & 0xffffu) * 0x10001u;
 #pragma unroll
             for (int bi = 0; bi < kNB; ++bi) acc[bi] = 0.f;
           }
@@ -338,7 +359,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
-        else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), 0);
+        else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
       }
     }
     flush();
@@ -363,10 +384,10 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <bool kF16, bool kGemm, int kNB>
+template <int kOp, bool kGemm, int kNB>
 int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmQ2,
                const CUtensorMap& tmK2, const SParams& p) {
-  auto kernel = sc_attn_seg_kernel<kF16, kGemm, kNB>;
+  auto kernel = sc_attn_seg_kernel<kOp, kGemm, kNB>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -425,21 +446,31 @@ int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count) {
 // Called by sc_attn_fwd_hard[_multi] (sc_attn.cu) after argument validation: 1..4 betas per launch, O is
 // [n_betas, splits, Nq, ldo] and is zeroed here.
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
-                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, bool f16, int64_t Nq,
+                    int (*make_tmap_u8)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int),
+                    const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, int op_dtype, int64_t Nq,
                     int64_t Nks, int64_t D_pad, const float* betas, int n_betas, int splits, float* O, int64_t ldo,
                     cudaStream_t st) {
   CUtensorMap tmQ, tmK;
   int rc;
-  if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
-  if ((rc = make_tmap(&tmK, Ks, Nks, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;    // 128 keys x 64 d
+  const bool f8 = (op_dtype == SC_E4M3), f16 = (op_dtype == SC_F16);
+  if (f8) {                                                                                 // 128 rows x 128 e4m3
+    if ((rc = make_tmap_u8(&tmQ, Qn, Nq, D_pad, D_pad, kBQ)) != SC_OK) return rc;
+    if ((rc = make_tmap_u8(&tmK, Ks, Nks, D_pad, D_pad, kBKeys)) != SC_OK) return rc;
+  } else {
+    if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
+    if ((rc = make_tmap(&tmK, Ks, Nks, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;    // 128 keys x 64 d
+  }
   SParams p;
   p.Nq = static_cast<int>(Nq);
-  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.n_dchunks = static_cast<int>(D_pad / (f8 ? 2 * kBK : kBK));
+  // e4m3 operands are stored as SC_E4M3_SCALE * x: S comes back scaled by its square
+  const float s_unscale = f8 ? 1.0f / (SC_E4M3_SCALE * SC_E4M3_SCALE) : 1.0f;
   p.steps_total = static_cast<int>(ceil_div(Nks, kStepKeys));
   p.splits = splits;
   for (int bi = 0; bi < 4; ++bi) {
-    p.c1[bi] = betas[bi < n_betas ? bi : n_betas - 1] * 1.4426950408889634f;
-    p.c0[bi] = -p.c1[bi];
+    const float c = betas[bi < n_betas ? bi : n_betas - 1] * 1.4426950408889634f;
+    p.c1[bi] = c * s_unscale;
+    p.c0[bi] = -c;
   }
   p.o_beta_stride = static_cast<long long>(splits) * Nq * ldo;
   p.gcls = gcls;
@@ -470,8 +501,10 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   p.ldz = 0;
   p.n_cols = 0;
   p.scale = 1.0f;
-#define SC_SEG_LAUNCH(NB)                                                                              \
-  (f16 ? launch_seg<true, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p) : launch_seg<false, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p))
+#define SC_SEG_LAUNCH(NB)                                                          \
+  (f8    ? launch_seg<SC_E4M3, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)         \
+   : f16 ? launch_seg<SC_F16, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)          \
+         : launch_seg<SC_BF16, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p))
   int rc2;
   switch (n_betas) {
     case 1: rc2 = SC_SEG_LAUNCH(1); break;
@@ -514,7 +547,7 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.scale = scale;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
   SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
-  return launch_seg<true, true, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
+  return launch_seg<SC_F16, true, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
 }
 
 }  // namespace sc

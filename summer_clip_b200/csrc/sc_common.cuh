@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,6 +64,29 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// store two adjacent operand elements (p 4-byte aligned for the 16-bit types, 2-byte for e4m3; e4m3 stores
+// SC_E4M3_SCALE * x, round-to-nearest-even, saturating)
+template <typename T>
+__device__ __forceinline__ void store2(T* p, float lo, float hi) {
+  *reinterpret_cast<uint32_t*>(p) = pack2<T>(lo, hi);
+}
+template <>
+__device__ __forceinline__ void store2<__nv_fp8_e4m3>(__nv_fp8_e4m3* p, float lo, float hi) {
+  *reinterpret_cast<__nv_fp8x2_storage_t*>(p) =
+      __nv_cvt_float2_to_fp8x2(make_float2(lo * SC_E4M3_SCALE, hi * SC_E4M3_SCALE), __NV_SATFINITE, __NV_E4M3);
+}
+
+// operand types a normalised bank can be written in (16-bit, or e4m3 for sc_attn_fwd_hard)
+#define SC_DISPATCH_OP8(dtype, T, ...)                                         \
+  switch (dtype) {                                                             \
+    case SC_F16: { using T = __half; __VA_ARGS__; break; }                     \
+    case SC_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }             \
+    case SC_E4M3: { using T = __nv_fp8_e4m3; __VA_ARGS__; break; }             \
+    default:                                                                   \
+      ::sc::set_error("operand dtype %d must be SC_F16, SC_BF16 or SC_E4M3", (int)(dtype)); \
+      return SC_EINVAL;                                                        \
+  }
 
 // dispatch on the tensor-core operand type (fp16 or bf16)
 #define SC_DISPATCH_OP(dtype, T, ...)                                          \

@@ -73,7 +73,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
       const int64_t o = n0 + r;
       if (o < n_out) {
         const int d = 2 * tx;
-        *reinterpret_cast<uint32_t*>(dst + o * D_pad + d0 + d) = sc::pack2<TO>(tile[d][r], tile[d + 1][r]);
+        sc::store2<TO>(dst + o * D_pad + d0 + d, tile[d][r], tile[d + 1][r]);
       }
     }
     __syncthreads();
@@ -139,18 +139,17 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
     if (o >= N) continue;
     const float inv = inv_s[c];
     const uint32_t* col32 = reinterpret_cast<const uint32_t*>(strip + c * pitch);
-    uint32_t* orow = reinterpret_cast<uint32_t*>(dst + o * D_pad);
+    TO* orow = dst + o * D_pad;
     const int64_t pairs = (D + 1) / 2;
     for (int64_t pr = lane; pr < D_pad / 2; pr += 32) {
-      uint32_t out = 0u;
+      float a = 0.f, b = 0.f;
       if (pr < pairs) {
         const uint32_t w = col32[pr];
         const uint16_t lo16 = static_cast<uint16_t>(w & 0xffffu), hi16 = static_cast<uint16_t>(w >> 16);
-        const float a = sc::to_f32<T>(*reinterpret_cast<const T*>(&lo16)) * inv;
-        const float b = sc::to_f32<T>(*reinterpret_cast<const T*>(&hi16)) * inv;
-        out = sc::pack2<TO>(a, b);
+        a = sc::to_f32<T>(*reinterpret_cast<const T*>(&lo16)) * inv;
+        b = sc::to_f32<T>(*reinterpret_cast<const T*>(&hi16)) * inv;
       }
-      orow[pr] = out;
+      sc::store2<TO>(orow + 2 * pr, a, b);
     }
   }
 }
@@ -191,7 +190,7 @@ norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride
     float a = 0.f, b = 0.f;
     if (ok && d < D) a = sc::to_f32<T>(row[d]) / nrm;
     if (ok && d + 1 < D) b = sc::to_f32<T>(row[d + 1]) / nrm;
-    *reinterpret_cast<uint32_t*>(dst + o * D_pad + d) = sc::pack2<TO>(a, b);
+    sc::store2<TO>(dst + o * D_pad + d, a, b);
   }
 }
 
@@ -328,6 +327,8 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
   SC_REQUIRE(D > 0 && N >= 0 && n_out >= 0, SC_ESHAPE, "sc_normalize_cast: bad shape");
   SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE,
              "sc_normalize_cast: D_pad=%lld must be >= D and a multiple of 64", (long long)D_pad);
+  SC_REQUIRE(dst_dtype != SC_E4M3 || D_pad % 128 == 0, SC_ESHAPE,
+             "sc_normalize_cast: D_pad=%lld must be a multiple of 128 for SC_E4M3 rows", (long long)D_pad);
   SC_REQUIRE(idx != nullptr || n_out == N, SC_ESHAPE, "sc_normalize_cast: n_out must equal N without idx");
   SC_REQUIRE(reinterpret_cast<uintptr_t>(dst) % 4 == 0, SC_EALIGN, "sc_normalize_cast: dst misaligned");
   if (n_out == 0) return SC_OK;
@@ -335,14 +336,14 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
   if (idx == nullptr && stride_n == 1 && stride_d != 1 && (src_dtype == SC_F16 || src_dtype == SC_BF16) &&
       static_cast<size_t>(D) * 33 * 2 <= 200 * 1024) {
     int rc = SC_OK;
-    SC_DISPATCH_OP(dst_dtype, TO, {
+    SC_DISPATCH_OP8(dst_dtype, TO, {
       if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
       else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
     });
     if (rc != SC_OK) return rc;
   } else if (stride_d == 1 && stride_n != 1) {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 8));
-    SC_DISPATCH_OP(dst_dtype, TO, {
+    SC_DISPATCH_OP8(dst_dtype, TO, {
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_rows_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_n, idx, n_out,
@@ -350,7 +351,7 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
     });
   } else {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
-    SC_DISPATCH_OP(dst_dtype, TO, {
+    SC_DISPATCH_OP8(dst_dtype, TO, {
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_transpose_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,

@@ -53,6 +53,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
       "r"(cta_rank)
       : "memory");
 }
+// the same without the release fence (MEMBAR.ALL.GPU + ERRBAR: ~20 % of an exp warp's step when global stores are
+// outstanding): for hand-offs that publish no memory — "my tcgen05.ld reads of this TMEM buffer are complete",
+// ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by the memory model
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "}\n" ::"r"(bar),
+      "r"(cta_rank)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -255,6 +268,8 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 // UMMA instruction descriptor, kind::f16: (bf16 | fp16)^2 -> fp32, A and B K-major, dense.
 //   c_format[4,6)=1 (F32)  a_format[7,10), b_format[10,13): 0 = F16, 1 = BF16
 //   a_major bit15=0  b_major bit16=0  n_dim[17,23)=N>>3  m_dim[24,29)=M>>4
+// kind::f8f6f4 uses the same layout with a_format / b_format 0 = E4M3, so an e4m3 x e4m3 -> fp32 descriptor has
+// the bits of the fp16 one.
 __host__ __device__ constexpr uint32_t umma_idesc_16b(uint32_t M, uint32_t N, bool is_f16) {
   const uint32_t fmt = is_f16 ? 0u : 1u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -344,36 +359,46 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtenso
 // Call them warp-uniformly (all 32 lanes); they return 1 when the probed phase had completed.
 namespace scptx {
 
-// probe + 4 pair UMMAs (one 64-element K chunk) + commit to bar1 (and to bar2 iff flag2)
+// probe + 4 pair UMMAs (one 128-byte K chunk: 64 16-bit or 128 e4m3 elements) + commit to bar1 (and to bar2 iff
+// flag2).  kF8: kind::f8f6f4 (K = 32 per instruction) instead of kind::f16 (K = 16) — the same 32-byte descriptor
+// advance and the same cycles per instruction, twice the contraction length.
+#define SC_UMMA4_CG2_PROBE_ASM(KIND)                                                                                \
+  asm volatile(                                                                                                     \
+      "{\n\t"                                                                                                       \
+      ".reg .pred pp, pe, pm, pa, pt, p2;\n\t"                                                                      \
+      "mbarrier.test_wait.parity.shared::cta.b64 pp, [%18], %19;\n\t"                                               \
+      "elect.sync _|pe, 0xffffffff;\n\t"                                                                            \
+      "setp.ne.and.b32 pm, %12, 0, pe;\n\t"                                                                         \
+      "setp.ne.b32 pa, %11, 0;\n\t"                                                                                 \
+      "setp.eq.b32 pt, %11, %11;\n\t"                                                                               \
+      "@pm tcgen05.mma.cta_group::2.kind::" KIND " [%1], %2, %6, %10, pa;\n\t"                                      \
+      "@pm tcgen05.mma.cta_group::2.kind::" KIND " [%1], %3, %7, %10, pt;\n\t"                                      \
+      "@pm tcgen05.mma.cta_group::2.kind::" KIND " [%1], %4, %8, %10, pt;\n\t"                                      \
+      "@pm tcgen05.mma.cta_group::2.kind::" KIND " [%1], %5, %9, %10, pt;\n\t"                                      \
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%13], %14;\n\t" \
+      "setp.ne.and.b32 p2, %17, 0, pe;\n\t"                                                                         \
+      "@p2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%15], %16;\n\t" \
+      "selp.u32 %0, 1, 0, pp;\n\t"                                                                                  \
+      "}\n"                                                                                                         \
+      : "=r"(ok)                                                                                                    \
+      : "r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(acc0),  \
+        "r"(enable), "r"(bar1), "h"(mask1), "r"(bar2), "h"(mask2), "r"(flag2), "r"(probe_bar), "r"(probe_parity)    \
+      : "memory")
+template <bool kF8 = false>
 __device__ __forceinline__ uint32_t umma4_cg2_probe(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2,
                                                     uint64_t a3, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
                                                     uint32_t idesc, uint32_t acc0, uint32_t enable, uint32_t bar1,
                                                     uint16_t mask1, uint32_t bar2, uint16_t mask2, uint32_t flag2,
                                                     uint32_t probe_bar, uint32_t probe_parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred pp, pe, pm, pa, pt, p2;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 pp, [%18], %19;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.and.b32 pm, %12, 0, pe;\n\t"
-      "setp.ne.b32 pa, %11, 0;\n\t"
-      "setp.eq.b32 pt, %11, %11;\n\t"
-      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %6, %10, pa;\n\t"
-      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %3, %7, %10, pt;\n\t"
-      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %4, %8, %10, pt;\n\t"
-      "@pm tcgen05.mma.cta_group::2.kind::f16 [%1], %5, %9, %10, pt;\n\t"
-      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%13], %14;\n\t"
-      "setp.ne.and.b32 p2, %17, 0, pe;\n\t"
-      "@p2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%15], %16;\n\t"
-      "selp.u32 %0, 1, 0, pp;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(acc0),
-        "r"(enable), "r"(bar1), "h"(mask1), "r"(bar2), "h"(mask2), "r"(flag2), "r"(probe_bar), "r"(probe_parity)
-      : "memory");
+  if constexpr (kF8) {
+    SC_UMMA4_CG2_PROBE_ASM("f8f6f4");
+  } else {
+    SC_UMMA4_CG2_PROBE_ASM("f16");
+  }
   return ok;
 }
+#undef SC_UMMA4_CG2_PROBE_ASM
 
 // probe + (expect_tx of tx_bytes on full_local iff tx_bytes != 0, plain arrive iff plain != 0) + up to two
 // pair TMA loads whose bytes are credited to bar_cluster

@@ -8,23 +8,30 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (SC_BF16, SC_CONF_PROB, SC_CONF_RAW, SC_F16, SC_F32, SC_VALUES_HARD, SC_VALUES_SOFTMAX, check)
+from ._lib import (SC_BF16, SC_CONF_PROB, SC_CONF_RAW, SC_E4M3, SC_F16, SC_F32, SC_VALUES_HARD, SC_VALUES_SOFTMAX, check)
 
 import os
 
-_DTYPES = {torch.float16: SC_F16, torch.bfloat16: SC_BF16, torch.float32: SC_F32}
+E4M3 = torch.float8_e4m3fn
+_DTYPES = {torch.float16: SC_F16, torch.bfloat16: SC_BF16, torch.float32: SC_F32, E4M3: SC_E4M3}
 
 # Tensor-core operand type of the attention path (Qn, Kn, Vt and the on-chip weights P); fp32
 # accumulation either way, same tcgen05 rate.  Every operand lies in [-1, 1], where fp16 has 3 more
 # mantissa bits than bf16 (DESIGN.md "Precision").  Override with SUMMER_CLIP_B200_OP_DTYPE=bf16.
+# SUMMER_CLIP_B200_OP_DTYPE=e4m3 (opt-in, reduced precision): feature banks as 8-bit floats (scaled by 256), half
+# the bank bytes and twice the contraction length per tensor-core instruction; only the segmented (one-hot values)
+# attention kernel reads them — dense values with e4m3 banks fail loudly.
 OP_DTYPE = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "f16": torch.float16, "fp16": torch.float16,
-            "float16": torch.float16}[os.environ.get("SUMMER_CLIP_B200_OP_DTYPE", "fp16").lower()]
+            "float16": torch.float16, "e4m3": E4M3, "fp8": E4M3}[os.environ.get("SUMMER_CLIP_B200_OP_DTYPE", "fp16").lower()]
 
 
-def _op(dtype: Optional[torch.dtype]) -> torch.dtype:
+def _op(dtype: Optional[torch.dtype], allow_e4m3: bool = False) -> torch.dtype:
     dtype = OP_DTYPE if dtype is None else dtype
-    if dtype not in (torch.float16, torch.bfloat16):
-        raise TypeError(f"operand dtype must be float16 or bfloat16, got {dtype}")
+    if dtype is E4M3 and not allow_e4m3:
+        raise TypeError("e4m3 feature banks are read by the one-hot (segmented) attention kernel only; dense cache "
+                        "values need float16 or bfloat16 operands")
+    if dtype not in (torch.float16, torch.bfloat16, E4M3):
+        raise TypeError(f"operand dtype must be float16, bfloat16 or float8_e4m3fn, got {dtype}")
     return dtype
 
 
@@ -49,7 +56,9 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def pad_dim(D: int) -> int:
+def pad_dim(D: int, op_dtype: Optional[torch.dtype] = None) -> int:
+    if op_dtype is E4M3:
+        return int(_lib.load().sc_pad_dim_op(D, SC_E4M3))
     return int(_lib.load().sc_pad_dim(D))
 
 
@@ -80,8 +89,8 @@ def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Ten
         n_out = idx.numel()
     else:
         n_out = N
-    D_pad = pad_dim(D)
-    op_dtype = _op(op_dtype if out is None else out.dtype)
+    op_dtype = _op(op_dtype if out is None else out.dtype, allow_e4m3=True)
+    D_pad = pad_dim(D, op_dtype)
     if out is None:
         out = torch.empty((n_out, D_pad), dtype=op_dtype, device=x.device)
     else:
@@ -297,7 +306,7 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     _cuda(Qn, "Qn")
     Ks = bank.rows
     assert Ks is not None, "HardBank.gather(k_norm) must be called first"
-    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16) and Ks.is_contiguous() and Qn.is_contiguous()
+    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16, E4M3) and Ks.is_contiguous() and Qn.is_contiguous()
     Nq, D_pad = Qn.shape
     assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
     n_classes = bank.n_classes
@@ -324,7 +333,7 @@ def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float]
     _cuda(Qn, "Qn")
     Ks = bank.rows
     assert Ks is not None, "HardBank.gather(k_norm) must be called first"
-    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16) and Ks.is_contiguous() and Qn.is_contiguous()
+    assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16, E4M3) and Ks.is_contiguous() and Qn.is_contiguous()
     Nq, D_pad = Qn.shape
     assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
     n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)

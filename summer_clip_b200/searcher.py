@@ -74,7 +74,7 @@ class ClipSearcher:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ops._lib.SummerClipError("ClipSearcher needs a CUDA device: the CLIP-search path has no CPU fallback")
-        self.op_dtype = ops._op(op_dtype)
+        self.op_dtype = ops._op(op_dtype, allow_e4m3=True)
         self.group = group
         if group is not None:
             import torch.distributed as dist

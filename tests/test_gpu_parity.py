@@ -471,6 +471,50 @@ def test_merge_partials_is_the_ordered_sum(ops, n_parts, rows, cols):
     assert torch.equal(ops.merge_partials(parts), want)
 
 
+def test_e4m3_feature_banks(ops):
+    """Opt-in 8-bit operands (north star part 1: "bf16/fp8 cast"): sc_normalize_cast writes 256 * x as e4m3
+    (round-to-nearest, within one e4m3 step of torch's own cast of the fp32 normalised value), the segmented
+    kernel (tcgen05 kind::f8f6f4, fp32 accumulate) reproduces fp32 arithmetic on THOSE operands to the same
+    tolerance as the 16-bit types, and against unquantised fp32 the class sums move by a few 1e-3 relative."""
+    e4m3 = torch.float8_e4m3fn
+    g = torch.Generator().manual_seed(101)
+    for nq, nk, dim, c, feature_major in [(300, 3000, 1024, 37, True), (129, 700, 200, 300, False), (64, 5000, 512, 1000, True)]:
+        q_src = torch.randn((dim, nq) if feature_major else (nq, dim), generator=g).cuda()
+        k_src = torch.randn((dim, nk) if feature_major else (nk, dim), generator=g).half().cuda()
+        Qn = ops.normalize_cast(q_src, feature_major, op_dtype=e4m3)
+        Kn = ops.normalize_cast(k_src, feature_major, op_dtype=e4m3)
+        d_pad = -(-dim // 128) * 128
+        assert Qn.dtype == e4m3 and Qn.shape == (nq, d_pad) and Kn.shape == (nk, d_pad)
+        for src, got in ((q_src, Qn), (k_src, Kn)):
+            x = src.float().t() if feature_major else src.float()
+            want = torch.nn.functional.normalize(x, dim=1) * 256.0
+            ref = want.to(e4m3).float()
+            gf = got.float()
+            assert float(gf[:, dim:].abs().sum()) == 0.0
+            step = torch.maximum(torch.full_like(ref, 2.0 ** -9), 2.0 ** (torch.floor(torch.log2(ref.abs().clamp_min(2.0 ** -6))) - 3))
+            assert bool(((gf[:, :dim] - ref).abs() <= step).all())
+            assert float((gf[:, :dim] != ref).float().mean()) < 0.01          # only values on a rounding boundary move
+        labels = torch.randint(0, c, (nk,), generator=g).int().cuda()
+        bank = ops.hard_bank_layout(labels, c).gather(Kn)
+        qf, kf = Qn.float() / 256.0, Kn.float() / 256.0
+        for betas in ([5.5], [0.1, 1.0, 3.5, 11.5]):
+            W = [torch.exp(b * (qf @ kf.t() - 1.0)) for b in betas]
+            outs = ops.attn_fwd_hard_multi(Qn, bank, betas)
+            for b, w, O in zip(betas, W, outs):
+                ref = torch.zeros(nq, c, device="cuda").index_add_(1, labels.long(), w)
+                torch.testing.assert_close(O, ref, rtol=3e-5, atol=1e-6 * max(1.0, ref.max().item()))
+                assert torch.equal(O, ops.attn_fwd_hard(Qn, bank, b))
+        # against unquantised fp32 features: the quantisation error itself (reported, loosely bounded)
+        x_q = torch.nn.functional.normalize(q_src.float().t() if feature_major else q_src.float(), dim=1)
+        x_k = torch.nn.functional.normalize(k_src.float().t() if feature_major else k_src.float(), dim=1)
+        exact = torch.zeros(nq, c, device="cuda").index_add_(1, labels.long(), torch.exp(5.5 * (x_q @ x_k.t() - 1.0)))
+        got = ops.attn_fwd_hard(Qn, bank, 5.5)
+        rel = (got - exact).abs() / exact.abs().clamp_min(1e-6 * exact.max())
+        assert float(rel.mean()) < 1e-2 and float(rel.max()) < 0.2
+    with pytest.raises(TypeError):
+        ops._op(e4m3)                                  # dense-values operands stay 16-bit
+
+
 def test_beta_sweep_shares_the_tensor_core_pass(ops):
     """sc_attn_fwd_hard_multi: up to 4 betas per launch off one S = Q.K^T; every beta's slab is bit-identical to
     its own single-beta launch (same arithmetic, same summation order), for any group size and ragged shapes; the

@@ -350,6 +350,75 @@ static double mean(const std::vector<long long>& v, int n) {
   return s / n;
 }
 
+
+// ------------------------------------------------------------------------------------------ exp
+// The exp warps' inner loop in isolation: per element one FFMA, one ex2.approx (MUFU) and one FADD into a running sum,
+// 16-element groups as in sc_attn_seg.cu.  mode 0: that loop; 1: MUFU only (independent); 2: 4 independent sums
+// (shorter FADD chains); 3: half of the exponentials on the FMA pipe (Cody-Waite + degree-5 polynomial).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_poly(float x) {
+  // 2^x for x <= 0 (x >= -126): split x = n + f, f in [-0.5, 0.5]; 2^f by a degree-5 minimax polynomial
+  const float n = rintf(x);
+  const float f = x - n;
+  float p = 1.3333558146e-3f;
+  p = fmaf(p, f, 9.6181291076e-3f);
+  p = fmaf(p, f, 5.5504108665e-2f);
+  p = fmaf(p, f, 2.4022650696e-1f);
+  p = fmaf(p, f, 6.9314718056e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (static_cast<int>(n) << 23));
+}
+__global__ void __launch_bounds__(128, 1) exp_loop_kernel(int iters, int mode, float c1, float c0, long long* cycles, float* sink) {
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = -0.001f * (threadIdx.x + j);
+  float acc = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += ex2_approx(fmaf(x[16 * h + j], c1, c0));
+        acc += s;
+      }
+    } else if (mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = ex2_approx(x[j]);
+    } else if (mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        acc += ex2_approx(fmaf(x[j], c1, c0));
+        acc2 += ex2_approx(fmaf(x[j + 1], c1, c0));
+        acc3 += ex2_approx(fmaf(x[j + 2], c1, c0));
+        acc4 += ex2_approx(fmaf(x[j + 3], c1, c0));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        acc += ex2_approx(fmaf(x[j], c1, c0));
+        acc2 += ex2_poly(fmaf(x[j + 1], c1, c0));
+      }
+    }
+    if (mode != 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += 1e-7f * acc;       // keep the loop body live and dependent
+    }
+  }
+  const long long t1 = clock64();
+  float r = acc + acc2 + acc3 + acc4;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r += x[j];
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (r == 12345.678f) sink[0] = r;
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   auto want = [&](const char* w) { return !strcmp(what, "all") || !strcmp(what, w); };
@@ -361,6 +430,24 @@ int main(int argc, char** argv) {
   long long* d_cycles;
   CK(cudaMalloc(&d_cycles, 4096 * sizeof(long long)));
   std::vector<long long> h(4096);
+
+  if (want("exp")) {
+    float* d_sink;
+    CK(cudaMalloc(&d_sink, 4));
+    const int iters = 4096;
+    for (int mode = 0; mode < 4; ++mode) {
+      exp_loop_kernel<<<148, 128>>>(iters, mode, 7.9f, -7.9f, d_cycles, d_sink);
+      CK(cudaDeviceSynchronize());
+      exp_loop_kernel<<<148, 128>>>(iters, mode, 7.9f, -7.9f, d_cycles, d_sink);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h.data(), d_cycles, sizeof(long long) * 148, cudaMemcpyDeviceToHost));
+      double cyc = 0;
+      for (int i = 0; i < 148; ++i) cyc += (double)h[i] / 148;
+      printf("exp mode=%d (0 loop, 1 mufu only, 2 four sums, 3 half polynomial): %.2f cycles per element per warp "
+             "(4 warps, one per SM sub-partition)\n", mode, cyc / iters / 32);
+    }
+    CK(cudaFree(d_sink));
+  }
 
   if (want("occ")) {
     for (int cs : {1, 2, 4, 8, 16}) {
