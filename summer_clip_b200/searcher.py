@@ -200,6 +200,17 @@ class ClipSearcher:
             part = torch.zeros((nq, n_cols), dtype=torch.float32, device=self.device)
         return part
 
+    def local_cache_logits_many(self, qn: torch.Tensor, betas: tp.Sequence[float]) -> tp.List[torch.Tensor]:
+        """`local_cache_logits` for a list of betas; a one-hot bank shares each tensor-core pass between four betas
+        (ops.attn_fwd_hard_multi), every result bit-identical to its single-beta launch."""
+        betas = [float(b) for b in betas]
+        if self.hard_bank is None or self.n_keys == 0 or len(betas) < 2:
+            return [self.local_cache_logits(qn, b) for b in betas]
+        splits = ops.attn_hard_splits(qn.shape[0], self.hard_bank.n_sorted, self.device)
+        outs = ops.attn_fwd_hard_multi(qn, self.hard_bank, betas, splits=splits)
+        self.gpu_launches += -(-len(betas) // 4) + (len(betas) if splits > 1 else 0)
+        return outs
+
     def cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
         """O over ALL keys for every query, on every rank (all-reduce of the per-rank partials).  `search` uses
         the cheaper reduce-scatter (`exchange_partials`) instead."""
@@ -222,8 +233,7 @@ class ClipSearcher:
         if labels is not None:
             labels = labels.to(self.device, non_blocking=True)
         results = []
-        for beta in betas:
-            o = self.cache_logits(qn, float(beta))
+        for beta, o in zip(betas, self.local_cache_logits_many(qn, betas)):
             rowsum = None
             if self.rowsum_col is not None:
                 rowsum = o[:, self.rowsum_col].contiguous()
@@ -277,13 +287,15 @@ class ClipSearcher:
             self.gpu_launches += 1
         lab_mine = labels.to(self.device, non_blocking=True)[lo:hi].contiguous() if labels is not None else None
         results = []
-        qn_mine = qn[lo:hi] if self.shard == "queries" else None
-        for beta in betas:
-            if self.shard == "queries":        # the whole bank is local: score my query slice, nothing to exchange
-                o = self.local_cache_logits(qn_mine, float(beta)) if hi > lo else \
-                    torch.zeros((0, self.n_classes + int(self.rowsum_col is not None)), dtype=torch.float32, device=self.device)
-            else:
-                o, lo, hi = exchange_partials(self.local_cache_logits(qn, float(beta)), self.group)
+        if self.shard == "queries":            # the whole bank is local: score my query slice, nothing to exchange
+            parts = self.local_cache_logits_many(qn[lo:hi], betas) if hi > lo else \
+                [torch.zeros((0, self.n_classes + int(self.rowsum_col is not None)), dtype=torch.float32, device=self.device)
+                 for _ in betas]
+        else:
+            parts = self.local_cache_logits_many(qn, betas)
+        for beta, o in zip(betas, parts):
+            if self.shard == "keys":
+                o, lo, hi = exchange_partials(o, self.group)
             res = {"beta": float(beta), "lo": lo, "hi": hi, "pred": None, "top1": None, "top5": None, "logits": None}
             na = len(alphas)
             pred_all = torch.zeros((self.world, na, per), dtype=torch.int32, device=self.device)

@@ -22,7 +22,9 @@ for nq, hard in ((1001, True), (512, True), (777, False)):
     single = ClipSearcher(dev)
     single.set_text(T)
     single.set_cache(K, L, **kw)
-    ref = single.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
+    BETAS = [5.5, 0.1, 1.0, 3.5, 11.5]                 # one-hot banks: a 4-beta launch + a 1-beta launch
+    refs = single.search(Q, BETAS, [0.5, 2.0], labels=labels, want_logits=True)
+    ref = refs[0]
     V = orc.hard_values(L.float()) if hard else orc.softmax_values(L.float(), orc.CLIP_SCALE, 0.1)
     want = orc.searcher_logits(orc.zero_shot_logits(Q.float(), T.float()), orc.image_attention(Q, K, V, 5.5), 0.5)
     e0 = (ref["logits"][0].cpu() - want).abs().max().item() / want.abs().max().item()
@@ -32,11 +34,14 @@ for nq, hard in ((1001, True), (512, True), (777, False)):
         sharded = ClipSearcher(dev, group=dist.group.WORLD, shard=shard)
         sharded.set_text(T)
         sharded.set_cache(K, L, **kw)
-        got = sharded.search(Q, [5.5], [0.5, 2.0], labels=labels, want_logits=True)[0]
-        lo, hi = got["lo"], got["hi"]
-        e = (got["logits"] - ref["logits"][:, lo:hi]).abs().max().item() / ref["logits"].abs().max().item()
-        same_pred = bool((got["pred"] == ref["pred"]).float().mean() > 0.999)
-        same_cnt = bool((got["top1"] - ref["top1"]).abs().max() <= 1) and bool((got["top5"] - ref["top5"]).abs().max() <= 1)
+        gots = sharded.search(Q, BETAS, [0.5, 2.0], labels=labels, want_logits=True)
+        e, same_pred, same_cnt = 0.0, True, True
+        for got, r in zip(gots, refs):
+            lo, hi = got["lo"], got["hi"]
+            e = max(e, (got["logits"] - r["logits"][:, lo:hi]).abs().max().item() / r["logits"].abs().max().item())
+            same_pred &= bool((got["pred"] == r["pred"]).float().mean() > 0.999) and got["pred"].shape == r["pred"].shape
+            same_cnt &= bool((got["top1"] - r["top1"]).abs().max() <= 1) and bool((got["top5"] - r["top5"]).abs().max() <= 1)
+        got = gots[0]
         good = e < 1e-4 and same_pred and same_cnt and got["pred"].shape == ref["pred"].shape
         ok &= good
         print(f"rank {rank} nq={nq} hard={hard} shard={shard}: slice=[{lo},{hi}) rel_err={e:.2e} pred={same_pred} "

@@ -515,6 +515,25 @@ def test_e4m3_feature_banks(ops):
         ops._op(e4m3)                                  # dense-values operands stay 16-bit
 
 
+def test_search_over_several_betas_equals_one_search_per_beta(ops):
+    """ClipSearcher.search groups the betas of a one-hot bank four to a launch; every result equals the search for
+    that beta alone bit for bit."""
+    from summer_clip_b200.searcher import ClipSearcher
+    banks = orc.synthetic_banks(500, 4000, 256, 120, seed=11, sigma=0.5, sigma_text=0.8, shared=3.0)
+    Q, K, L, T = (banks[n].cuda() for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    labels = banks["test_labels"].cuda()
+    s = ClipSearcher("cuda")
+    s.set_text(T)
+    s.set_cache(K, L)
+    betas, alphas = [0.1, 1.0, 1.5, 3.5, 5.5, 7.5], [0.0, 1.0, 4.0]
+    many = s.search(Q, betas, alphas, labels=labels, want_logits=True)
+    assert [r["beta"] for r in many] == betas
+    for r in many:
+        one = s.search(Q, [r["beta"]], alphas, labels=labels, want_logits=True)[0]
+        for k in ("cache_logits", "logits", "pred", "top1", "top5"):
+            assert torch.equal(r[k], one[k]), (r["beta"], k)
+
+
 def test_beta_sweep_shares_the_tensor_core_pass(ops):
     """sc_attn_fwd_hard_multi: up to 4 betas per launch off one S = Q.K^T; every beta's slab is bit-identical to
     its own single-beta launch (same arithmetic, same summation order), for any group size and ragged shapes; the
