@@ -51,6 +51,33 @@ def test_argument_errors_are_reported_without_a_gpu(cuda_lib):
     assert rc < 0 and b"SC_F16 or SC_BF16" in cuda_lib.sc_last_error()
 
 
+def test_argument_errors_of_the_one_hot_path(cuda_lib):
+    """sc_attn_fwd_hard_multi / sc_epilogue_parts / sc_normalize_cast(e4m3) validate before touching the device."""
+    p16 = ctypes.c_void_p(256)
+    one = (ctypes.c_float * 4)(1.0, 2.0, 3.0, 4.0)
+    hard = lambda *a: cuda_lib.sc_attn_fwd_hard_multi(*a)  # noqa: E731
+    assert hard(p16, p16, p16, p16, 0, 8, 256, 64, 10, one, 5, 1, p16, 10, None) < 0 and b"n_betas" in cuda_lib.sc_last_error()
+    assert hard(p16, p16, p16, p16, 0, 8, 256, 64, 10, one, 0, 1, p16, 10, None) < 0
+    assert hard(p16, p16, p16, p16, 2, 8, 256, 64, 10, one, 1, 1, p16, 10, None) < 0 and b"op_dtype" in cuda_lib.sc_last_error()
+    assert hard(p16, p16, p16, p16, 3, 8, 256, 64, 10, one, 1, 1, p16, 10, None) < 0 and b"multiple of 128" in cuda_lib.sc_last_error()
+    assert hard(p16, p16, p16, p16, 0, 8, 256, 64, 40000, one, 1, 1, p16, 40000, None) < 0        # classes beyond int16 labels
+    assert hard(p16, p16, p16, p16, 0, 8, 256, 64, 10, one, 1, 1, p16, 9, None) < 0 and b"ldo" in cuda_lib.sc_last_error()
+    assert hard(p16, p16, p16, p16, 0, 8, 256, 64, 10, one, 1, 2, p16, 10, None) < 0 and b"splits" in cuda_lib.sc_last_error()
+    assert hard(p16, None, p16, p16, 0, 8, 256, 64, 10, one, 1, 1, p16, 10, None) < 0 and b"null" in cuda_lib.sc_last_error()
+    epi = lambda *a: cuda_lib.sc_epilogue_parts(*a)  # noqa: E731
+    assert epi(None, 10, p16, 10, 3, 10, None, 8, 10, one, 1, None, None, None, None, None, None) < 0 \
+        and b"part_stride" in cuda_lib.sc_last_error()
+    assert epi(None, 10, p16, 10, 0, 0, None, 8, 10, one, 1, None, None, None, None, None, None) < 0
+    assert epi(None, 10, p16, 10, 1, 0, None, 8, 10, one, 65, None, None, None, None, None, None) < 0
+    assert epi(None, 10, p16, 10, 1, 0, None, 0, 10, one, 1, None, None, None, None, None, None) == 0      # no rows: nothing to do
+    assert cuda_lib.sc_pad_dim_op(1000, 3) == 1024 and cuda_lib.sc_pad_dim_op(1000, 0) == 1024 and cuda_lib.sc_pad_dim_op(130, 3) == 256
+    assert cuda_lib.sc_pad_dim_op(130, 1) == 192
+    rc = cuda_lib.sc_normalize_cast(p16, 2, 100, 4, 4, 1, None, 4, p16, 3, 192, 1, None)
+    assert rc < 0 and b"multiple of 128" in cuda_lib.sc_last_error()
+    rc = cuda_lib.sc_normalize_cast(p16, 2, 100, 4, 4, 1, None, 4, p16, 7, 128, 1, None)
+    assert rc < 0 and b"SC_E4M3" in cuda_lib.sc_last_error()
+
+
 def test_kernels_are_blackwell_native():
     """SASS evidence: tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA -> UTMALDG."""
     import shutil
@@ -62,7 +89,7 @@ def test_kernels_are_blackwell_native():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", str(_lib.lib_path())], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+    for mnemonic in ("UTCHMMA", "UTCQMMA", "LDTM", "UTMALDG"):          # UTCQMMA: kind::f8f6f4 (opt-in e4m3 banks)
         assert mnemonic in sass, mnemonic
 
 
