@@ -3,14 +3,13 @@ computation is a call into libsummerclip_b200.so.  CPU tensors are rejected (no 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
 from ._lib import (SC_BF16, SC_CONF_PROB, SC_CONF_RAW, SC_E4M3, SC_F16, SC_F32, SC_VALUES_HARD, SC_VALUES_SOFTMAX, check)
-
-import os
 
 E4M3 = torch.float8_e4m3fn
 _DTYPES = {torch.float16: SC_F16, torch.bfloat16: SC_BF16, torch.float32: SC_F32, E4M3: SC_E4M3}
