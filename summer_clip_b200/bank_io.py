@@ -28,7 +28,7 @@ import torch
 from . import ops
 
 FORMAT_VERSION = 1
-_DTYPES = {"float16": torch.float16, "bfloat16": torch.bfloat16}
+_DTYPES = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float8_e4m3fn": torch.float8_e4m3fn}
 
 
 def bank_key(sources: tp.Sequence[tp.Union[str, os.PathLike]], n_classes: int, op_dtype: torch.dtype,

@@ -60,3 +60,11 @@ def test_sidecar_round_trip(tmp_path):
     assert bank_io.load_hard_bank(tmp_path / "missing", "cpu") is None
     bank_io.save_hard_bank(bank, tmp_path / "bank", key)                      # overwrite in place
     assert bank_io.load_hard_bank(d, "cpu", key) is not None
+    # the opt-in 8-bit operand type travels the same way (rows are stored as raw 16-bit words)
+    bank.rows = (bank.rows.float() * 256).to(torch.float8_e4m3fn)
+    key8 = bank_io.bank_key([feats], 7, torch.float8_e4m3fn, idx=torch.arange(300))
+    assert key8 != key
+    d8 = bank_io.save_hard_bank(bank, tmp_path / "bank8", key8)
+    back8 = bank_io.load_hard_bank(d8, "cpu", key8)
+    assert back8 is not None and back8.rows.dtype == torch.float8_e4m3fn and back8.rows.shape == bank.rows.shape
+    assert torch.equal(back8.rows.view(torch.uint8), bank.rows.view(torch.uint8))
