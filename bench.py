@@ -166,7 +166,7 @@ def run_ours(args):
     n_local = hi - lo
     del k_bank, outs
     c_pad = ops.pad_classes(n_classes)
-    splits = ops.attn_hard_splits(nq, searcher.hard_bank.n_sorted, device) if searcher.hard_bank is not None \
+    splits = ops.attn_hard_splits(nq, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
         else ops.attn_splits(nq, n_local, c_pad, device)
     if os.environ.get("SC_BENCH_SPLITS"):                  # tuning knob for A/B runs
         splits = int(os.environ["SC_BENCH_SPLITS"])

@@ -158,9 +158,14 @@ int sc_gather_rows(const void* src, int64_t n_src, int64_t row_bytes, const int6
  * GEMM-1 (Q.K^T) runs as 256 x 256 CTA-pair tensor-core tiles; the exponentials are summed per class straight
  * out of tensor memory in fp32 — the weights are never rounded, stored or exchanged.  O is fp32
  * [splits, Nq, ldo]; the library zeroes it and writes only the classes each split meets (sum the splits with
- * sc_merge_partials).  splits = 0: the library chooses (sc_attn_hard_splits).  Any n_classes <= 32767. */
+ * sc_merge_partials).  splits = 0: the library chooses (sc_attn_hard_splits_for).  Any n_classes <= 32767.
+ * sc_attn_hard_splits fills the SM pairs by tensor-core work alone; sc_attn_hard_splits_for also charges every
+ * extra split the zeroing and reading back of its [Nq, n_classes] tile per beta, which decides for small banks
+ * (Tip-Adapter's 16 000 keys: 1 split instead of 3). */
 int sc_attn_hard_supported(int64_t n_classes);
 int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count);
+int sc_attn_hard_splits_for(int64_t Nq, int64_t Nks, int64_t D_pad, int op_dtype, int64_t n_classes, int n_betas,
+                            int sm_count);
 int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                      int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float beta,
                      int splits, float* O, int64_t ldo, void* stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "sc_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "sc_attn_hard_supported": (c_int, [c_int64]),
     "sc_attn_hard_splits": (c_int, [c_int64, c_int64, c_int]),
+    "sc_attn_hard_splits_for": (c_int, [c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int]),
     "sc_attn_fwd_hard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                  c_float, c_int, c_void_p, c_int64, c_void_p]),
     "sc_attn_fwd_hard_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,

@@ -35,7 +35,7 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
                   int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices, float beta,
                   int splits, float* O, int64_t ldo, cudaStream_t st);
 // sc_attn_seg.cu
-int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count);
+int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count, int64_t row_bytes, int64_t n_classes, int n_betas);
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                     int (*make_tmap_u8)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int),
                     const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, int op_dtype, int64_t Nq,
@@ -511,7 +511,11 @@ int64_t sc_pad_labels(int64_t Nk) { return sc::round_up(Nk > 0 ? Nk : 1, kBN); }
 
 int sc_attn_hard_supported(int64_t n_classes) { return (n_classes > 0 && n_classes <= 32767) ? 1 : 0; }
 
-int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count) { return sc::attn_seg_splits(Nq, Nks, sm_count); }
+int sc_attn_hard_splits(int64_t Nq, int64_t Nks, int sm_count) { return sc::attn_seg_splits(Nq, Nks, sm_count, 0, 0, 1); }
+int sc_attn_hard_splits_for(int64_t Nq, int64_t Nks, int64_t D_pad, int op_dtype, int64_t n_classes, int n_betas,
+                            int sm_count) {
+  return sc::attn_seg_splits(Nq, Nks, sm_count, D_pad * (op_dtype == SC_E4M3 ? 1 : 2), n_classes, n_betas);
+}
 
 int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                            int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes,
@@ -535,7 +539,7 @@ int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_
     int dev = 0, sms = 148;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    splits = sc::attn_seg_splits(Nq, Nks, sms);
+    splits = sc::attn_seg_splits(Nq, Nks, sms, D_pad * (op_dtype == SC_E4M3 ? 1 : 2), n_classes, n_betas);
   }
   SC_REQUIRE(splits <= steps_total && splits <= 65535, SC_ESHAPE,
              "sc_attn_fwd_hard: splits=%d exceeds the %lld key steps", splits, (long long)steps_total);

@@ -420,19 +420,26 @@ extern "C" double sc_debug_attn_hard_clock_mhz(void) {
 
 namespace sc {
 
-// key splits for the pair kernel: work items = query tiles (256 queries) x splits over sm_count / 2 pairs
-int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count) {
+// key splits for the pair kernel: work items = query tiles (256 queries) x splits over sm_count / 2 pairs.
+// Cost in key steps: waves x (steps per split + fixed prologue/epilogue) + what every extra split costs outside
+// the tensor cores — its [Nq, n_classes] fp32 tile is zeroed before and read back after (memset + merge /
+// epilogue, ~4 TB/s), per beta.  One 256-key step is 8192 UMMA cycles per 1024 bytes of row (~4.8 us at the
+// ~1.7 GHz these kernels see).  n_classes = 0 ignores the tile traffic (the historical rule).
+int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count, int64_t row_bytes, int64_t n_classes, int n_betas) {
   if (Nq <= 0 || Nks <= 0) return 1;
   if (sm_count <= 0) sm_count = 148;
   const int64_t pairs = sm_count / 2 > 0 ? sm_count / 2 : 1;
   const int64_t base = ceil_div(Nq, 2 * kBQ);
   const int64_t steps = ceil_div(Nks, kStepKeys);
+  const double step_us = 4.8 * static_cast<double>(row_bytes > 0 ? row_bytes : 2048) / 2048.0;
+  const double tile_us = static_cast<double>(Nq) * static_cast<double>(n_classes > 0 ? n_classes : 0) * 8.0 / 4.0e6;
+  const double per_split = (n_betas > 0 ? n_betas : 1) * tile_us / step_us;     // in key steps
   int best = 1;
   double best_cost = 1e300;
   const int64_t smax = steps < 128 ? steps : 128;
   for (int64_t s = 1; s <= smax; ++s) {
     const double waves = static_cast<double>(ceil_div(base * s, pairs));
-    const double cost = waves * (static_cast<double>(ceil_div(steps, s)) + 1.5);
+    const double cost = waves * (static_cast<double>(ceil_div(steps, s)) + 1.5) + per_split * static_cast<double>(s);
     if (cost < best_cost * 0.995) { best_cost = cost; best = static_cast<int>(s); }
   }
   return best;

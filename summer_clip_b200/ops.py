@@ -311,7 +311,7 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     n_classes = bank.n_classes
     n_sorted = max(bank.n_sorted, 1)
     if splits <= 0:
-        splits = attn_hard_splits(Nq, n_sorted, Qn.device)
+        splits = attn_hard_splits(Nq, n_sorted, Qn.device, bank=bank)
     O = torch.empty((splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)      # zeroed by the library
     with torch.cuda.device(Qn.device):
         check(_lib.load().sc_attn_fwd_hard(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kbits), _code(Qn), Nq,
@@ -337,7 +337,7 @@ def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float]
     assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
     n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)
     if splits <= 0:
-        splits = attn_hard_splits(Nq, n_sorted, Qn.device)
+        splits = attn_hard_splits(Nq, n_sorted, Qn.device, bank=bank)
     lib = _lib.load()
     outs = []
     betas = [float(b) for b in betas]
@@ -354,8 +354,14 @@ def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float]
     return outs
 
 
-def attn_hard_splits(Nq: int, Nks: int, device=None) -> int:
+def attn_hard_splits(Nq: int, Nks: int, device=None, bank: Optional[HardBank] = None) -> int:
+    """Key splits of the segmented kernel.  With `bank` (gathered) the choice also charges every extra split the
+    zeroing and reading back of its [Nq, n_classes] tile (sc_attn_hard_splits_for).  Deliberately independent of
+    how many betas share the launch: the split count fixes the summation grouping, so a beta computed in a sweep
+    stays bit-identical to the same beta computed alone."""
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
+    if bank is not None and bank.rows is not None:
+        return int(_lib.load().sc_attn_hard_splits_for(Nq, Nks, bank.rows.shape[1], _code(bank.rows), bank.n_classes, 1, sms))
     return int(_lib.load().sc_attn_hard_splits(Nq, Nks, sms))
 
 

@@ -189,7 +189,7 @@ class ClipSearcher:
         if self.n_keys > 0:
             if self.hard_bank is not None:
                 if splits <= 0:
-                    splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device)
+                    splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
                 part = ops.attn_fwd_hard(qn, self.hard_bank, beta, splits=splits)
             else:
                 if splits <= 0:
@@ -206,7 +206,7 @@ class ClipSearcher:
         betas = [float(b) for b in betas]
         if self.hard_bank is None or self.n_keys == 0 or len(betas) < 2:
             return [self.local_cache_logits(qn, b) for b in betas]
-        splits = ops.attn_hard_splits(qn.shape[0], self.hard_bank.n_sorted, self.device)
+        splits = ops.attn_hard_splits(qn.shape[0], self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
         outs = ops.attn_fwd_hard_multi(qn, self.hard_bank, betas, splits=splits)
         self.gpu_launches += -(-len(betas) // 4) + (len(betas) if splits > 1 else 0)
         return outs
