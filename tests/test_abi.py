@@ -41,6 +41,23 @@ def test_geometry_helpers(cuda_lib):
     assert cuda_lib.sc_attn_splits(50000, 1281167, 1024, 148) >= 1
 
 
+def test_key_split_choice(cuda_lib):
+    """sc_attn_hard_splits[_for]: whole waves of the 74 CTA pairs at the headline size on 1..8 GPUs, one split for a
+    16 000-key bank (the tile traffic of extra splits outweighs the idle pairs), every pair busy for one query tile,
+    never more splits than key steps."""
+    f, g = cuda_lib.sc_attn_hard_splits_for, cuda_lib.sc_attn_hard_splits
+    for world in (1, 2, 4, 8):
+        nks = 1281167 // world + 12000
+        assert f(50000, nks, 1024, 0, 1000, 1, 148) == 3 == g(50000, nks, 148)
+    assert f(50000, 16000, 1024, 0, 1000, 1, 148) == 1 and g(50000, 16000, 148) == 3
+    assert f(1, 1290000, 1024, 0, 1000, 1, 148) == 74
+    assert f(50000, 1290000, 1024, 3, 1000, 1, 148) == 3                       # e4m3 rows: half the step time
+    for nq, nks in ((1, 1), (300, 200), (70000, 257), (5, 5000)):
+        s = f(nq, nks, 64, 0, 10, 1, 148)
+        assert 1 <= s <= -(-nks // 256)
+    assert f(0, 0, 64, 0, 10, 1, 148) == 1
+
+
 def test_argument_errors_are_reported_without_a_gpu(cuda_lib):
     rc = cuda_lib.sc_attn_fwd(None, None, None, 0, 1, 1, 64, 1, 16, 8, 1.0, 1, None, 1, None)
     assert rc < 0 and b"null" in cuda_lib.sc_last_error()
