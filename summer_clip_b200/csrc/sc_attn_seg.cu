@@ -288,13 +288,13 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       // 32 columns (two 16-key groups) per TMEM load, double buffered: the load of chunk cc+1 is in flight
       // while chunk cc is exponentiated and summed
-      auto consume = [&](const uint32_t (&rg)[32], int cc) {
+      auto consume = [&](const uint32_t (&rg)[32], const uint32_t gwc, const uint32_t kwc) {
         // The exponentials of BOTH 16-key groups of the chunk first, as straight-line code (the two groups' sums
         // interleave and the MUFU pipe never drains: ~9 instead of ~15 cycles per element, ncu source page of the
         // per-group version), then the warp-uniform class bookkeeping.  Per group: s = e0 + e1 + ... + e15 in that
         // order, padding keys contribute an exact 0 — the results do not depend on where classes change.
         float sa[kNB], sb[kNB];
-        if (kw[cc] == 0xffffffffu) {                      // every key of the chunk is valid (the common case)
+        if (kwc == 0xffffffffu) {                         // every key of the chunk is valid (the common case)
 #pragma unroll
           for (int bi = 0; bi < kNB; ++bi) {
             float a = 0.f, b = 0.f;
@@ -307,7 +307,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             sb[bi] = b;
           }
         } else {                                          // a class segment's last group / bank padding: masked
-          const uint32_t bits = kw[cc];
+          const uint32_t bits = kwc;
 #pragma unroll
           for (int bi = 0; bi < kNB; ++bi) {
             float a = 0.f, b = 0.f;
@@ -324,7 +324,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int cls = static_cast<int>(static_cast<int16_t>((gw[cc] >> (16 * hh)) & 0xffffu));
+          const int cls = static_cast<int>(static_cast<int16_t>((gwc >> (16 * hh)) & 0xffffu));
           if (cls != cur) {                              // warp-uniform: the finished class sums go out
             flush();
             cur = cls;
@@ -340,14 +340,35 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(tcol, ra);
         tmem_ld_wait();
+        if constexpr (kNB == 1) {
 #pragma unroll
-        for (int cc = 0; cc < kStepKeys / 32; cc += 2) {
-          tmem_ld_32x32(tcol + (cc + 1) * 32, rb);
-          consume(ra, cc);
-          tmem_ld_wait();
-          if (cc + 2 < kStepKeys / 32) tmem_ld_32x32(tcol + (cc + 2) * 32, ra);
-          consume(rb, cc + 1);
-          tmem_ld_wait();
+          for (int cc = 0; cc < kStepKeys / 32; cc += 2) {
+            tmem_ld_32x32(tcol + (cc + 1) * 32, rb);
+            consume(ra, gw[cc], kw[cc]);
+            tmem_ld_wait();
+            if (cc + 2 < kStepKeys / 32) tmem_ld_32x32(tcol + (cc + 2) * 32, ra);
+            consume(rb, gw[cc + 1], kw[cc + 1]);
+            tmem_ld_wait();
+          }
+        } else {
+          // several betas: the chunk body is kNB times longer, and eight unrolled copies of it no longer fit the
+          // instruction cache (ncu: "no instruction" stalls as frequent as issues).  Roll the loop: lane l < 8 keeps
+          // group-class word l, lane 8 + l validity word l, a shuffle hands the chunk's words to the warp.
+          uint32_t myw = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            myw = lane == i ? gw[i] : myw;
+            myw = lane == 8 + i ? kw[i] : myw;
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < kStepKeys / 32; cc += 2) {
+            tmem_ld_32x32(tcol + (cc + 1) * 32, rb);
+            consume(ra, __shfl_sync(0xffffffffu, myw, cc), __shfl_sync(0xffffffffu, myw, 8 + cc));
+            tmem_ld_wait();
+            if (cc + 2 < kStepKeys / 32) tmem_ld_32x32(tcol + (cc + 2) * 32, ra);
+            consume(rb, __shfl_sync(0xffffffffu, myw, cc + 1), __shfl_sync(0xffffffffu, myw, 9 + cc));
+            tmem_ld_wait();
+          }
         }
       }
       tc_fence_before();
