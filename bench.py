@@ -125,12 +125,91 @@ def make_banks(torch, nq, nk_lo, nk_hi, dim, n_classes, seed, device):
     return q_bank, k_bank, outs, text.t().contiguous(), yq.int()
 
 
+def parity_check(torch, ops, searcher, q_bank, k_bank, outs, text, labels, pred_timed, rows, soft_scale, key_range=None):
+    """Outside the timed region: `rows` sampled query rows of the step just timed against fp32 torch arithmetic on
+    the RAW banks (the reference's expressions, cache_weights_strategy.py:18-36, cache_value_strategy.py:14-28,
+    image_attention.py:109-111, chunked over the keys).  key_range = (lo, hi) restricts the reference to one key
+    shard (N > 1, key-sharded: the rank-local partial tile is what is checked)."""
+    dev = q_bank.device
+    n_classes = text.shape[1]
+    q = q_bank[:, rows].float()
+    qn = q / q.norm(dim=0, keepdim=True)
+    z = 100.0 * qn.t() @ text.float()
+    o_ref = torch.zeros((rows.numel(), n_classes), dtype=torch.float32, device=dev)
+    nk = k_bank.shape[1]
+    for s0 in range(0, nk, 1 << 16):
+        k = k_bank[:, s0:s0 + (1 << 16)].float()
+        kn = k / k.norm(dim=0, keepdim=True)
+        w = (-1 * BETA * (1 - qn.t() @ kn)).exp()
+        l = outs[s0:s0 + (1 << 16)].float()
+        v = torch.nn.functional.one_hot(l.max(dim=1)[1], n_classes).float() if soft_scale is None else torch.softmax(soft_scale * l, dim=1)
+        o_ref += w @ v
+    # the library's result for the same rows (its own normalise / attention kernels, resident bank)
+    qn_lib = ops.normalize_cast(q_bank[:, rows].contiguous(), True)
+    o_lib = searcher.local_cache_logits(qn_lib, BETA)
+    rel = ((o_lib - o_ref).abs().max() / o_ref.abs().max()).item()
+    out = {"rows": int(rows.numel()), "cache_logits_max_rel_err": rel, "reference": "fp32 torch on the raw banks, same device"}
+    if key_range is None:
+        ref = z + ALPHA * o_ref
+        z_lib = ops.zero_shot_logits(q_bank[:, rows].contiguous(), True, searcher.text, t_split=searcher.text_split)
+        got = z_lib + ALPHA * o_lib
+        out["softmax_maxabs"] = (torch.softmax(got, 1) - torch.softmax(ref, 1)).abs().max().item()
+        out["argmax_agree"] = (got.argmax(1) == ref.argmax(1)).float().mean().item()
+        out["timed_step_pred_agree"] = (pred_timed[rows].long() == ref.argmax(1)).float().mean().item()
+        out["ok"] = bool(out["softmax_maxabs"] <= 2e-3 and out["argmax_agree"] >= 1.0 - 1.0 / rows.numel()
+                         and out["timed_step_pred_agree"] >= 1.0 - 1.0 / rows.numel())
+    else:
+        out["key_shard"] = list(key_range)
+        out["ok"] = bool(rel <= 2e-3)
+    return out
+
+
+def gpu_eager_baseline(torch, q_bank, k_bank, outs, text, labels, soft_scale, chunk=1024, steps=2):
+    """The reference's own tensor expressions in torch eager on the SAME B200 (cuBLAS hgemm + ATen element-wise
+    kernels, fp16 like the reference's cached CUDA banks), query-chunked because the [Nq, Nk] matrix it materialises
+    does not fit: cache_weights_strategy.py:18-21,33-36, cache_value_strategy.py:14-17 / :26-28,
+    image_attention.py:80-83,109-111, clip_searcher/utils.py:15-21.  The honest same-box bar."""
+    nq = q_bank.shape[1]
+    t_half = text.half()
+
+    def step():
+        qn = q_bank / q_bank.norm(dim=0, keepdim=True)
+        kn = k_bank / k_bank.norm(dim=0, keepdim=True)
+        if soft_scale is None:
+            _, ids = outs.max(dim=1)
+            v = torch.nn.functional.one_hot(ids, num_classes=outs.shape[1]).half()
+        else:
+            v = torch.softmax(soft_scale * outs, dim=1)
+        z = 100.0 * qn.t() @ t_half
+        correct = torch.zeros((), dtype=torch.int64, device=q_bank.device)
+        for s0 in range(0, nq, chunk):
+            w = (-1 * BETA * (1 - qn[:, s0:s0 + chunk].t() @ kn)).exp()
+            o = w @ v
+            out = z[s0:s0 + chunk] + o * ALPHA
+            pred = out.topk(5, 1, True, True)[1]
+            correct += (pred[:, 0] == labels[s0:s0 + chunk]).sum()
+        return correct
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        top1 = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "query_chunk": chunk,
+            "dtype": "f16", "top1_count": int(top1),
+            "kind": "reference tensor expressions in torch eager on this GPU (cuBLAS + ATen), [chunk, Nk] weights materialised per query chunk"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from summer_clip_b200 import build as _build, ops
-    from summer_clip_b200.searcher import ClipSearcher, exchange_partials, shard_range
+    from summer_clip_b200.searcher import ClipSearcher, exchange_partials, query_slice, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -153,21 +232,30 @@ def run_ours(args):
     nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
     if args.nq:
         nq = args.nq
-    lo, hi = shard_range(nk, rank, world)
+    shard_keys = world > 1 and args.shard == "keys"
+    shard_queries = world > 1 and args.shard == "queries"
+    lo, hi = shard_range(nk, rank, world) if shard_keys else (0, nk)
     q_bank, k_bank, outs, text, labels = make_banks(torch, nq, lo, hi, dim, n_classes, seed=3, device=device)
+    soft_scale = 100.00000762939453 * 0.1 if args.values == "softmax" else None     # conf/cache_value_strategy/softmax_cache.yaml
 
-    searcher = ClipSearcher(device, group=None)          # the shard is generated locally; merge is done below
+    searcher = ClipSearcher(device, group=None)          # the shard is generated locally; the exchange is done below
     searcher.set_text(text)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    searcher.set_cache(k_bank, outs)                      # normalise+transpose+cast keys, one-hot values (transposed)
+    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale)   # normalise+transpose+cast keys; label-sorted bank / dense values
     torch.cuda.synchronize()
-    bank_build_ms = (time.perf_counter() - t0) * 1e3
+    bank_build_first_ms = (time.perf_counter() - t0) * 1e3      # first call: library load, allocator growth included
+    t0 = time.perf_counter()
+    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale)
+    torch.cuda.synchronize()
+    bank_build_ms = (time.perf_counter() - t0) * 1e3            # steady state
     n_local = hi - lo
-    del k_bank, outs
     c_pad = ops.pad_classes(n_classes)
-    splits = ops.attn_hard_splits(nq, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
-        else ops.attn_splits(nq, n_local, c_pad, device)
+    # the queries this rank runs attention for: all of them (one GPU, key shards) or its slice (query shards)
+    qlo, qhi = query_slice(nq, rank, world) if shard_queries else (0, nq)
+    nq_attn = qhi - qlo
+    splits = ops.attn_hard_splits(nq_attn, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
+        else ops.attn_splits(nq_attn, n_local, c_pad, device)
     if os.environ.get("SC_BENCH_SPLITS"):                  # tuning knob for A/B runs
         splits = int(os.environ["SC_BENCH_SPLITS"])
 
@@ -193,41 +281,51 @@ def run_ours(args):
 
     per_q = -(-nq // world)
 
-    def finish(q_src, lab_src, o_part):
-        """Zero-shot logits + alpha epilogue.  With key-sharded ranks one reduce-scatter sums the partial tiles
-        and hands every rank ITS query slice, which it finishes alone; predictions are all-gathered and the
-        counters all-reduced (searcher.exchange_partials / ClipSearcher._search_sharded)."""
-        if world == 1:
-            z = ops.zero_shot_logits(q_src, True, searcher.text, t_split=searcher.text_split)
-            mark("zero_shot")
-            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)   # sums the unmerged key-split tiles as it reads
-            mark("epilogue")
-            launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
-            return res["pred"], torch.stack([res["top1"], res["top5"]])
-        if o_part.dim() == 3:
-            o_part = ops.merge_partials(o_part)
-            launches["n"] += 1
-            mark("merge_splits")
-        o_mine, lo, hi = exchange_partials(o_part, group)
-        mark("reduce_scatter")
-        z = ops.zero_shot_logits(q_src[:, lo:hi], True, searcher.text, t_split=searcher.text_split)
-        mark("zero_shot")
-        res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[lo:hi].contiguous())
-        mark("epilogue")
-        launches["n"] += 3
-        counts = torch.stack([res["top1"], res["top5"]])
+    def gather_results(pred_mine, counts, n_mine):
+        """Predictions of every rank's query slice -> all ranks; accuracy counters summed."""
         dist.all_reduce(counts, group=group)
         mine = torch.zeros((1, per_q), dtype=torch.int32, device=device)
-        mine[:, : hi - lo] = res["pred"]
+        mine[:, :n_mine] = pred_mine
         pred_all = torch.empty((world, 1, per_q), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(pred_all, mine, group=group)
         mark("counters_and_predictions")
         return pred_all.permute(1, 0, 2).reshape(1, world * per_q)[:, :nq], counts
 
+    def finish(q_src, lab_src, o_part):
+        """Zero-shot logits + alpha epilogue.  q_src / lab_src cover the queries [qlo, qhi) attention ran for.
+        Key-sharded ranks: one reduce-scatter sums the partial tiles and hands every rank ITS query slice, which it
+        finishes alone (searcher.exchange_partials / ClipSearcher._search_sharded).  Query-sharded ranks finish
+        their own slice, no exchange.  Either way predictions are all-gathered and the counters all-reduced."""
+        if not shard_keys:
+            z = ops.zero_shot_logits(q_src, True, searcher.text, t_split=searcher.text_split)
+            mark("zero_shot")
+            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)   # sums the unmerged key-split tiles as it reads
+            mark("epilogue")
+            launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
+            counts = torch.stack([res["top1"], res["top5"]])
+            if world == 1:
+                return res["pred"], counts
+            return gather_results(res["pred"], counts, nq_attn)
+        if o_part.dim() == 3:
+            o_part = ops.merge_partials(o_part)
+            launches["n"] += 1
+            mark("merge_splits")
+        o_mine, slo, shi = exchange_partials(o_part, group)
+        mark("reduce_scatter")
+        z = ops.zero_shot_logits(q_src[:, slo:shi], True, searcher.text, t_split=searcher.text_split)
+        mark("zero_shot")
+        res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[slo:shi].contiguous())
+        mark("epilogue")
+        launches["n"] += 3
+        return gather_results(res["pred"], torch.stack([res["top1"], res["top5"]]), shi - slo)
+
+    q_attn = q_bank[:, qlo:qhi] if shard_queries else q_bank          # strided view: the kernels take strides
+    lab_attn = labels_dev[qlo:qhi].contiguous() if shard_queries else labels_dev
+
     def step_device(time_attn=None):
         """Inputs resident in HBM."""
         mark("start")
-        qn = ops.normalize_cast(q_bank, True)
+        qn = ops.normalize_cast(q_attn, True)
         mark("normalize_queries")
         if time_attn is not None:
             time_attn[0].record(stream)
@@ -236,25 +334,32 @@ def run_ours(args):
             time_attn[1].record(stream)
         mark("attention")
         launches["n"] += 2
-        pred, counts = finish(q_bank, labels_dev, part if splits > 1 else part[0])
+        pred, counts = finish(q_attn, lab_attn, part if splits > 1 else part[0])
         return {"pred": pred, "top1": counts[0], "top5": counts[1]}
 
-    # e2e: the query bank and labels come from pinned host memory every step and the predictions + counters go
-    # back.  The host->device copy of step i+1 is issued on a side stream while step i computes (two device
-    # buffers), as a serving loop would; the first copy of the timed region is fully exposed.
+    # e2e: queries and labels come from pinned host memory every step and the predictions + counters go back.  Every
+    # rank copies only ITS query slice over PCIe (1/N of the bank); key-sharded ranks, which need every query, then
+    # all-gather the normalised fp16 rows over NVLink.  The host->device copy of step i+1 is issued on a side stream
+    # while step i computes (two device buffers), as a serving loop would; the first copy is fully exposed.
     copy_stream = torch.cuda.Stream(device=device)
-    q_bufs = [torch.empty_like(q_bank), torch.empty_like(q_bank)]
-    lab_bufs = [torch.empty_like(labels_dev), torch.empty_like(labels_dev)]
+    elo, ehi = query_slice(nq, rank, world)
+    n_e2e = ehi - elo
+    q_host_mine = q_host[:, elo:ehi].contiguous().pin_memory() if world > 1 else q_host
+    lab_host_mine = labels_host[elo:ehi].contiguous().pin_memory() if world > 1 else labels_host
+    q_bufs = [torch.empty_like(q_host_mine, device=device) for _ in range(2)]
+    lab_bufs = [torch.empty_like(lab_host_mine, device=device) for _ in range(2)]
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def start_copy(i):
         with torch.cuda.stream(copy_stream):
-            q_bufs[i % 2].copy_(q_host, non_blocking=True)
-            lab_bufs[i % 2].copy_(labels_host, non_blocking=True)
+            q_bufs[i % 2].copy_(q_host_mine, non_blocking=True)
+            lab_bufs[i % 2].copy_(lab_host_mine, non_blocking=True)
             copy_done[i % 2].record(copy_stream)
 
+    d_pad = ops.pad_dim(dim, ops.OP_DTYPE)
+
     def step_e2e(i, n_steps):
-        """Host buffers in, host result out: H2D of the query bank, D2H of predictions + counters."""
+        """Host buffers in, host result out: H2D of the query slice, D2H of predictions + counters."""
         if i == 0:
             start_copy(0)
         if i + 1 < n_steps:
@@ -262,8 +367,19 @@ def run_ours(args):
         torch.cuda.current_stream().wait_event(copy_done[i % 2])
         q_dev, lab = q_bufs[i % 2], lab_bufs[i % 2]
         qn = ops.normalize_cast(q_dev, True)
-        part = attn(qn, False)
-        pred, counts = finish(q_dev, lab, part if splits > 1 else part[0])
+        if shard_keys:                              # every rank needs every query: all-gather the normalised rows
+            qn_pad = qn if n_e2e == per_q else torch.cat([qn, qn.new_zeros((per_q - n_e2e, d_pad))])
+            qn_all = torch.empty((world * per_q, d_pad), dtype=qn.dtype, device=device)
+            dist.all_gather_into_tensor(qn_all, qn_pad, group=group)
+            part = attn(qn_all[:nq], False)
+            o_part = ops.merge_partials(part) if splits > 1 else part[0]
+            o_mine, slo, shi = exchange_partials(o_part, group)
+            z = ops.zero_shot_logits(q_dev, True, searcher.text, t_split=searcher.text_split)
+            res = ops.epilogue(z, o_mine, [ALPHA], labels=lab)
+            pred, counts = gather_results(res["pred"], torch.stack([res["top1"], res["top5"]]), shi - slo)
+        else:
+            part = attn(qn, False)
+            pred, counts = finish(q_dev, lab, part if splits > 1 else part[0])
         pred = pred.to("cpu", non_blocking=True)
         counts = counts.to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -309,6 +425,7 @@ def run_ours(args):
     attn_ms = sum(a.elapsed_time(b) for a, b in attn_events) / args.steps
     gpu_launches = launches["n"]
     top1 = int(res["top1"][0])
+    pred_timed = res["pred"][0].clone()
 
     # ---------------- end-to-end timing (host buffers)
     n_warm = max(1, args.warmup // 2)
@@ -320,6 +437,7 @@ def run_ours(args):
         pred, counts = step_e2e(i, args.steps)
     sync_all()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_top1 = int(counts[0][0])
 
     phases = None
     if args.phases:                                        # untimed extra steps, decomposed with events on the stream
@@ -333,6 +451,26 @@ def run_ours(args):
         phase_marks = None
         phases = {k: round(v, 4) for k, v in acc.items()}
 
+    # ---------------- output check of the step just timed (outside every timed region)
+    check = None
+    if not args.no_parity_check:
+        g = torch.Generator(device=device).manual_seed(1234)
+        rows = torch.randperm(nq_attn, generator=g, device=device)[:64].sort()[0] + qlo
+        check = parity_check(torch, ops, searcher, q_bank, k_bank, outs, text, labels_dev, pred_timed, rows, soft_scale,
+                             key_range=(lo, hi) if shard_keys else None)
+        check["e2e_top1_equals_device_top1"] = bool(e2e_top1 == top1)
+        if world > 1:
+            ok = torch.tensor([int(check["ok"])], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            check["ok_all_ranks"] = bool(ok.item())
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        try:
+            eager = gpu_eager_baseline(torch, q_bank, k_bank, outs, text, labels_dev, soft_scale)
+        except Exception as exc:  # noqa: BLE001  (an OOM of the baseline must not lose the measurement)
+            eager = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    del k_bank, outs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -340,48 +478,64 @@ def run_ours(args):
     peaks = read_peaks()
     ms_per_step = total_ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
-    flops = 2.0 * nq * n_local * (dim + n_classes)                  # 2*Nq*Nk*(D + C) per launch
+    flops = 2.0 * nq_attn * n_local * (dim + n_classes)              # 2*Nq*Nk*(D + C) per launch
     if searcher.hard_bank is not None:
         # label-sorted one-hot bank: GEMM-1 (Q.K^T) on every (padded) key on the tensor cores; W @ one_hot is a
         # per-class segmented sum done in fp32 by the exp warps (no second GEMM exists to execute)
-        executed = 2.0 * nq * searcher.hard_bank.n_sorted * dim
+        executed = 2.0 * nq_attn * searcher.hard_bank.n_sorted * dim
     else:
-        executed = 2.0 * nq * n_local * (dim + c_pad)
+        executed = 2.0 * nq_attn * n_local * (dim + c_pad)
     achieved = executed / (attn_ms * 1e-3) / 1e12                   # tensor-core work actually issued
     dense_equiv = flops / (attn_ms * 1e-3) / 1e12
     traffic = None
     try:
         with open(os.path.join(REPO, "profiles", "attn_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload if world == 1 else "", None)
+            traffic = json.load(f).get((args.workload if args.values == "hard" else args.workload + "_softmax_values") if world == 1 else "", None)
     except Exception:
         pass
+    dense = searcher.hard_bank is None
+    if dense:
+        # dense values: both GEMMs are real tensor-core work; SURVEY §8d's count is the roofline numerator
+        achieved = dense_equiv
+    sharding = "single GPU"
+    if shard_keys:
+        sharding = f"key-sharded x{world}: reduce-scatter of the partial tiles, each rank finishes its query slice"
+    elif shard_queries:
+        sharding = f"query-sharded x{world}: every rank holds the whole bank and scores its query slice; no data-path collective"
     out = {
         "metric": "clip_search_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None,
         "dtype": {torch.float16: "f16", torch.bfloat16: "bf16"}.get(ops.OP_DTYPE, "e4m3 (opt-in reduced precision; NOT the headline)"), "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
-                   "n_classes": n_classes, "beta": BETA, "alpha": ALPHA, "values": "hard (one-hot of argmax L)",
-                   "sharding": f"key-sharded x{world}: reduce-scatter of the partial tiles, each rank finishes its query slice" if world > 1 else "single GPU",
-                   "key_splits_per_gpu": splits, "accumulate": "fp32",
+                   "n_classes": n_classes, "beta": BETA, "alpha": ALPHA,
+                   "values": "hard (one-hot of argmax L)" if soft_scale is None else f"softmax({soft_scale:.6f} * L) (SoftmaxCacheStrategy, scale 0.1)",
+                   "sharding": sharding, "key_splits_per_gpu": splits, "accumulate": "fp32",
                    "l2": "inputs larger than L2: key bank = %.2f GB per GPU (+ %s)" % (
-                       2 * n_local * dim / 1e9, "sorted by label" if searcher.hard_bank is not None else "%.2f GB dense values" % (2 * n_local * c_pad / 1e9)),
-                   "values_operand": "one-hot, label-sorted bank (W @ V = per-class segmented sum out of tensor memory)" if searcher.hard_bank is not None else "dense Vt",
-                   "bank_build_ms": bank_build_ms, "top1_count": top1},
+                       2 * n_local * dim / 1e9, "sorted by label" if not dense else "%.2f GB dense values" % (2 * n_local * c_pad / 1e9)),
+                   "values_operand": "one-hot, label-sorted bank (W @ V = per-class segmented sum out of tensor memory)" if not dense else "dense Vt",
+                   "bank_build_ms": bank_build_ms, "bank_build_first_call_ms": bank_build_first_ms, "top1_count": top1},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                     "kernel": "sc_attn_seg_kernel" if searcher.hard_bank is not None else "sc_attn_t_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
+                     "kernel": "sc_attn_seg_kernel" if not dense else "sc_attn_t_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
                      "executed_flops_per_launch": executed, "dense_equivalent_tflops": dense_equiv,
-                     "note": "achieved/frac count the tensor-core FLOPs actually issued; dense_equivalent_tflops = "
-                             "2*Nq*Nk*(D+C)/time, the rate a dense-V kernel would need for the same queries/s",
+                     "note": ("one-hot values: achieved/frac count the tensor-core FLOPs actually issued (GEMM-1; W @ one_hot is a segmented fp32 "
+                              "sum, no GEMM-2 exists); dense_equivalent_tflops = 2*Nq*Nk*(D+C)/time is what a dense-V kernel would need for the "
+                              "same queries/s and is NOT a roofline figure") if not dense else
+                             "dense values: achieved = SURVEY 8d's algorithmic count 2*Nq*Nk*(D+C) / kernel time (both GEMMs execute)",
                      "peak_source": peaks["source"] + " burst (cuBLAS bf16 8192^3)",
                      "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None},
         "e2e": {"value": nq / (e2e_ms / args.steps * 1e-3), "unit": "queries/s",
-                "h2d_bytes_per_step": q_host.numel() * q_host.element_size() + labels_host.numel() * 4,
-                "d2h_bytes_per_step": pred.numel() * 4 + counts.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+                "h2d_bytes_per_step": q_host_mine.numel() * q_host_mine.element_size() + lab_host_mine.numel() * 4,
+                "d2h_bytes_per_step": pred.numel() * 4 + counts.numel() * 4, "ms_per_step": e2e_ms / args.steps,
+                "note": "bytes are per rank: every rank copies its 1/N slice of the query bank" if world > 1 else None},
         "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
+    if check is not None:
+        out["parity_check"] = check
+    if eager is not None:
+        out["gpu_eager_baseline"] = eager
     if phases is not None:
         out["phases_ms"] = phases
     if world == 1 and not args.no_cpu_baseline:
@@ -391,57 +545,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(nq, nk, dim, n_classes, budget_s=20.0, steps=1):
-    """The oracle port of the reference path (normalise both banks, Q^T K, exp, one-hot, @, Z + alpha*O,
-    top-1/5) timed on the host cores with torch fp32 on a bounded sample of the same workload; cost is
-    linear in queries and keys, so the sample time is scaled to the full key bank."""
+CPU_SAMPLE = (1024, 131072)       # queries x keys of the bounded CPU sample, the same in both arms
+
+
+def _cpu_sample_step(nq, nk, dim, n_classes):
+    """One step of the reference path on the host: the oracle port (normalise both banks, Q^T K, exp, one-hot, @,
+    Z + alpha*O, top-1/5) in torch fp32 on a CPU_SAMPLE-sized slice of the workload, all host threads."""
     import torch
     from oracle import clip_search_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sq = min(nq, 1024)
-    sk = min(nk, 131072)
-    banks = orc.synthetic_banks(sq, sk, dim, n_classes, seed=3)
-    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
-    labels = banks["test_labels"].long()
-
-    def once():
-        Z = orc.zero_shot_logits(Q, T)
-        O = orc.image_attention(Q, K, orc.hard_values(L), BETA, chunk=256)
-        out = orc.searcher_logits(Z, O, ALPHA)
-        return orc.compute_accuracy(out, labels)
-
-    once()                                                      # warm-up
-    best = float("inf")
-    t_all = time.perf_counter()
-    for _ in range(3):
-        t0 = time.perf_counter()
-        once()
-        best = min(best, time.perf_counter() - t0)
-        if time.perf_counter() - t_all > budget_s:
-            break
-    full_time = best * (nk / sk)                                # seconds for `sq` queries against the full bank
-    return {"value": sq / full_time, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{sq} queries x {sk} keys x {dim}-d, {n_classes} classes (fp32 torch CPU, best of 3, {best:.2f} s), "
-                      f"scaled linearly to {nk} keys",
-            "sample_seconds": best, "gflops": 2.0 * sq * sk * (dim + n_classes) / best / 1e9}
-
-
-def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is a pure
-    Python repo without a build or an installable package, and /root/reference is absent on the GPU
-    box, so the timed code is the oracle port (kind "port"), all host threads, on a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
-    if args.nq:
-        nq = args.nq
-    import torch
-    from oracle import clip_search_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sq, sk = min(nq, 512), min(nk, 65536)
+    sq, sk = min(nq, CPU_SAMPLE[0]), min(nk, CPU_SAMPLE[1])
     banks = orc.synthetic_banks(sq, sk, dim, n_classes, seed=3)
     Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
     labels = banks["test_labels"].long()
@@ -451,22 +565,61 @@ def run_reference(args):
         O = orc.image_attention(Q, K, orc.hard_values(L), BETA, chunk=256)
         return orc.compute_accuracy(orc.searcher_logits(Z, O, ALPHA), labels)
 
+    return step, sq, sk, cores
+
+
+def cpu_baseline(nq, nk, dim, n_classes, budget_s=20.0, steps=1):
+    """The oracle port timed on the host cores on a bounded sample of the same workload (cost is linear in queries
+    and in keys; the measured sample time and the factor to the full workload are reported separately)."""
+    step, sq, sk, cores = _cpu_sample_step(nq, nk, dim, n_classes)
+    step()                                                      # warm-up
+    best = float("inf")
+    t_all = time.perf_counter()
+    for _ in range(3):
+        t0 = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    scale = (nk / sk) * (nq / sq)
+    return {"value": nq / (best * scale), "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{sq} queries x {sk} keys x {dim}-d, {n_classes} classes (fp32 torch CPU, best of 3)",
+            "sample_seconds": best, "scale_factor_to_full_workload": scale,
+            "gflops": 2.0 * sq * sk * (dim + n_classes) / best / 1e9}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is a pure Python repo
+    without a build or an installable package, and /root/reference is absent on the GPU box, so the timed code is
+    the oracle port (kind "port"), all host threads.  Every step is the bounded CPU_SAMPLE slice of the workload:
+    `ms_per_step` is the MEASURED time of such a step (steps x ms_per_step is what ran); `value` scales it linearly
+    in queries and keys to the full workload, with the factor stated."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nq, nk, dim, n_classes, desc = WORKLOADS[args.workload]
+    if args.nq:
+        nq = args.nq
+    step, sq, sk, cores = _cpu_sample_step(nq, nk, dim, n_classes)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     sample_s = (time.perf_counter() - t0) / args.steps
-    full_s = sample_s * (nk / sk) * (nq / sq)                   # one full pass of the workload, linear scaling
-    qps = nq / full_s
+    scale = (nk / sk) * (nq / sq)
+    qps = nq / (sample_s * scale)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = f"{sq} queries x {sk} keys per step (fp32 torch CPU), scaled linearly to {nq} x {nk}"
+    sample = f"{sq} queries x {sk} keys per step (fp32 torch CPU, {cores} threads); value = the full {nq} x {nk} workload at this rate"
     out = {"impl": "reference", "metric": "clip_search_queries_per_sec", "value": qps, "unit": "queries/s",
-           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": full_s * 1e3,
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample_s * 1e3,
+           "sample_ms_per_step": sample_s * 1e3, "scale_factor_to_full_workload": scale,
+           "full_workload_ms_per_step_extrapolated": sample_s * scale * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
                       "n_classes": n_classes, "beta": BETA, "alpha": ALPHA},
-           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                            "sample_seconds": sample_s, "scale_factor_to_full_workload": scale},
            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -482,7 +635,14 @@ def main():
     ap.add_argument("--nq", type=int, default=0, help="override the number of queries (debug)")
     ap.add_argument("--op-dtype", default="", choices=["", "fp16", "bf16", "e4m3"],
                     help="tensor-core operand type of the feature banks (default fp16; e4m3 is the opt-in 8-bit mode)")
+    ap.add_argument("--values", default="hard", choices=["hard", "softmax"],
+                    help="cache values: hard = HardCacheStrategy (one-hot, the reference default; segmented kernel), "
+                         "softmax = SoftmaxCacheStrategy(clip_scale, 0.1) (dense values; dual-GEMM kernel)")
+    ap.add_argument("--shard", default="keys", choices=["keys", "queries"],
+                    help="what N > 1 ranks split: the key bank (reduce-scatter of partial tiles) or the queries (no data-path collective)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager fp16 reference expressions on the GPU")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--phases", action="store_true", help="add phases_ms: rank 0's per-phase device times of extra untimed steps")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()

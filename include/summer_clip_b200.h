@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 1
+#define SC_ABI_VERSION 2
 
 /* element types of caller buffers.  SC_E4M3 (8-bit float, 4 exponent / 3 mantissa bits) is an OPERAND type only:
  * sc_normalize_cast can write it and sc_attn_fwd_hard[_multi] can read it (tcgen05 kind::f8f6f4, fp32 accumulate:
@@ -59,7 +59,7 @@ const char* sc_last_error(void);
 int64_t sc_pad_dim(int64_t D);          /* multiple of 64 */
 int64_t sc_pad_dim_op(int64_t D, int op_dtype);  /* row length for an operand type: 128-byte chunks (64 16-bit / 128 e4m3) */
 int64_t sc_pad_keys(int64_t Nk);        /* multiple of 8  */
-int64_t sc_pad_classes(int64_t C);      /* n_slices * slice width (multiple of 16, <= 256) */
+int64_t sc_pad_classes(int64_t C);      /* n_slices * slice width (2 or 4k slices; width a multiple of 16, <= 256) */
 int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C classes */
 
 /* Column L2-normalise + gather + transpose + cast (cache_weights_strategy.py:19-20 fused with the
@@ -73,6 +73,14 @@ int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C cla
 int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
                       int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst, int dst_dtype,
                       int64_t D_pad, int normalize, void* stream);
+
+/* Tail of Tip-Adapter's build_cache_model (tip_adapter/utils.py:59-60): cache keys = row-L2-normalised mean over
+ * the E augment epochs of the encoder features.  src element (e, n, d) at src[e*stride_e + n*stride_n + d], dtype
+ * SC_F16 / SC_BF16 / SC_F32; dst [N, ld_dst] of the SAME type.  The mean, the norm and the quotient are rounded to
+ * the storage type one after the other, as the reference's tensor expressions are; sums in fp32.  The reference then
+ * stores the [D, N] permuted VIEW of this matrix (utils.py:61): pass it to sc_normalize_cast with stride_d = 1. */
+int sc_mean_normalize_rows(const void* src, int dtype, int64_t E, int64_t N, int64_t D, int64_t stride_e,
+                           int64_t stride_n, void* dst, int64_t ld_dst, void* stream);
 
 /* Per-row confidence and predicted label of a logits bank L[N, C] (leading dim ld):
  *   SC_CONF_RAW : conf = max_c L, label = first argmax          (cache_strategy.py:68)
@@ -116,6 +124,20 @@ int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count);
 int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,
                 int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
                 int splits, float* O, int64_t ldo, void* stream);
+/* The same with a per-query reference in place of the constant 1:
+ *     O[s, q, c] = sum_{k in split s} exp(beta * (Qn[q].Kn[k] - row_shift[q])) * Vt[c, k]
+ * (row_shift NULL = sc_attn_fwd).  With row_shift[q] = max_k Qn[q].Kn[k] (sc_attn_rowmax) every row's largest
+ * weight is exactly 1 whatever beta is, which is what the temperature-softmax mode needs before the weights are
+ * rounded to 16 bits: O together with a ones row in Vt (sc_values_prepare's ones_row) is the (m, l, O) partial
+ * triple of sc_merge_softmax with m = beta * log2(e) * row_shift. */
+int sc_attn_fwd_shifted(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,
+                        int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta, const float* row_shift,
+                        int splits, float* O, int64_t ldo, void* stream);
+/* rowmax[q] = max_{k < Nk} Qn[q].Kn[k] in fp32 (tensor-core GEMM-1 of the attention kernel with a running maximum
+ * in place of the exponential sum; the [Nq, Nk] matrix is not materialised).  Kn is any [Nk, D_pad] bank of op_dtype
+ * (SC_F16, SC_BF16 or SC_E4M3), in any key order. */
+int sc_attn_rowmax(const void* Qn, const void* Kn, int op_dtype, int64_t Nq, int64_t Nk, int64_t D_pad, float* rowmax,
+                   void* stream);
 
 /* Hard-label cache values for sc_attn_fwd_hard: labels16[k] = argmax_c L[idx[k]] (or labels_override[k]) as
  * int16 for k < n_out, and -1 for n_out <= k < n_pad and for labels outside [0, C) — i.e. the one-hot cache
@@ -175,6 +197,35 @@ int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class,
 int sc_attn_fwd_hard_multi(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
                            int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes,
                            const float* betas, int n_betas, int splits, float* O, int64_t ldo, void* stream);
+
+/* Temperature-softmax mode on a label-sorted bank (north-star extension; the reference has only the un-normalised
+ * Tip-Adapter weights): softmax over the KEYS of tau * Qn.Ks^T with an ONLINE running row
+ * maximum, summed per class.  Same operands, tiles and splits as sc_attn_fwd_hard; the result is the per-class
+ * log-sum-exp in base 2,
+ *     LSE[s, q, c] = log2 sum_{k in split s, class(k) == c} 2^(tau * log2(e) * Qn[q].Ks[k]),   -inf if there is none,
+ * i.e. the (m, l) pair of every class in one float — independent of the maximum it was accumulated against, so
+ * classes, key splits and key shards combine exactly (sc_softmax_partials, sc_merge_softmax).  The library fills
+ * the tile with -inf first. */
+int sc_attn_softmax_hard(const void* Qn, const void* Ks, const int16_t* group_class, const uint32_t* key_bits,
+                         int op_dtype, int64_t Nq, int64_t Nks, int64_t D_pad, int64_t n_classes, float tau, int splits,
+                         float* LSE, int64_t ldo, void* stream);
+/* LSE tiles [n_parts, Nq, ld] (parts part_stride floats apart) -> the (m, l, O) partial triple of these keys:
+ *     m[q] = max_{p, c} LSE,   O[q, c] = sum_p 2^(LSE[p, q, c] - m[q]),   l[q] = sum_c O[q, c]
+ * (m = -inf, O = 0, l = 0 for a row without keys).  O / l is the softmax attention output over these keys. */
+int sc_softmax_partials(const float* LSE, int n_parts, int64_t part_stride, int64_t Nq, int64_t C, int64_t ld,
+                        float* O, int64_t ld_out, float* m, float* l, void* stream);
+/* Log-sum-exp merge of (m, l, O) partial triples (key splits, key-sharded ranks):
+ *     M[q] = m_ref ? m_ref[q] : max_p m_scale * m_p[q],    w_p = 2^(m_scale * m_p[q] - M[q]),
+ *     out[q, c] = sum_p w_p O_p[q, c],   L[q] = sum_p w_p l_p[q],   out /= L if normalize.
+ * O_parts fp32 [n_parts, Nq, ld] (parts o_part_stride floats apart), m_parts / l_parts [n_parts, Nq] (parts
+ * ml_part_stride apart).  m_scale converts the stored m to base-2 exponents: 1 for sc_softmax_partials' output,
+ * tau * log2(e) for a row maximum of cosines (sc_attn_rowmax + sc_attn_fwd_shifted).  m_ref (nullable) = a common
+ * maximum agreed between ranks (all-reduce MAX of M), so that the rescaled O and L can be summed by a reduce-scatter.
+ * out may alias O_parts when n_parts == 1; m_out / l_out nullable. */
+int sc_merge_softmax(const float* O_parts, const float* m_parts, const float* l_parts, int n_parts,
+                     int64_t o_part_stride, int64_t ml_part_stride, int64_t Nq, int64_t C, int64_t ld, float m_scale,
+                     const float* m_ref, int normalize, float* out, int64_t ld_out, float* m_out, float* l_out,
+                     void* stream);
 
 /* out[r, c] = sum_p parts[p, r, c]  (key splits and key-sharded ranks; with the Tip weights
  * exp(beta(A-1)) <= 1 the running maximum of an LSE merge is the constant 0, so the merge of

@@ -176,6 +176,25 @@ def tip_head(features: torch.Tensor, cache_keys: torch.Tensor, cache_values: tor
     return clip_logits + cache_logits * alpha
 
 
+def tip_cache_keys(train_features: torch.Tensor) -> torch.Tensor:
+    """tip_adapter/utils.py:59-61 — mean over the augment epochs [E, Nk, D], row-normalise, permute -> [D, Nk]
+    (in the dtype given: the reference runs these lines on fp16 CUDA tensors)."""
+    cache_keys = train_features.mean(dim=0)
+    cache_keys = cache_keys / cache_keys.norm(dim=-1, keepdim=True)
+    return cache_keys.permute(1, 0)
+
+
+def tip_normalize_rows(features: torch.Tensor) -> torch.Tensor:
+    """tip_adapter/utils.py:84 — image_features /= image_features.norm(dim=-1, keepdim=True)."""
+    return features / features.norm(dim=-1, keepdim=True)
+
+
+def golds_as_outs(cache_labels: torch.Tensor, n_classes: int) -> torch.Tensor:
+    """image_attention.py:65-66 — cache.replace_outs_with_golds: the selected logits are replaced by
+    one_hot(gold).half(); the value strategy is then applied to THAT matrix."""
+    return torch.nn.functional.one_hot(cache_labels.long(), num_classes=n_classes).half()
+
+
 def search_grid(search_scale: Sequence[float], search_step: Sequence[int]) -> Tuple[List[float], List[float]]:
     """tip_adapter/utils.py:103-104 — the beta / alpha grids of search_hp."""
     beta_list = [i * (search_scale[0] - 0.1) / search_step[0] + 0.1 for i in range(search_step[0])]

@@ -28,6 +28,8 @@ SIGNATURES = {
     "sc_class_slice": (c_int64, [c_int64]),
     "sc_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                   c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "sc_mean_normalize_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                       c_void_p]),
     "sc_rowconf": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p,
                            c_void_p]),
     "sc_topk_workspace_bytes": (c_size_t, [c_int64, c_int32]),
@@ -38,6 +40,15 @@ SIGNATURES = {
     "sc_attn_splits": (c_int, [c_int64, c_int64, c_int64, c_int]),
     "sc_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                             c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_attn_fwd_shifted": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                    c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_attn_rowmax": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "sc_attn_softmax_hard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                     c_float, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_softmax_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                    c_void_p, c_void_p]),
+    "sc_merge_softmax": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                 c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "sc_pad_labels": (c_int64, [c_int64]),
     "sc_hard_labels": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                c_int64, c_void_p]),

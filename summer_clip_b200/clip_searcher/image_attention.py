@@ -10,7 +10,7 @@ same loop nest and the same JSON records in the same order (image_attention.py:8
     are read from files: `data.text_features_path` (T [D, C]) or `data.clip_logits_path`,
     `data.labels_path`, `cache.labels_path`.  Encoder forward passes are outside this path.
 
-    python -m summer_clip_b200.clip_searcher.image_attention path/to/image_attention.yaml [key=value ...]
+    python -m summer_clip_b200.clip_searcher.image_attention [path/to/image_attention.yaml] [key=value ...]
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ import torch
 from .. import ops
 from ..searcher import ClipSearcher
 from ..utils import hydra_utils
-from ..utils.config import Config, load_config
+from ..utils.config import Config, compose
 from ..utils.log_utils import JsonLinesLogger
 from .cache_strategy import CacheStrategy, IndexedCacheStrategy
 from .cache_value_strategy import GoldCacheValues, HardCacheStrategy, SoftmaxCacheStrategy
@@ -59,9 +59,12 @@ class ImageAttention:
         self.preds_saver = TensorsNumpySaver(self.run_dir / "preds_ids")
 
     def setup_dataset(self) -> None:
+        if not self.cfg.data.get("labels_path"):
+            raise ops._lib.SummerClipError("data.labels_path is required: the dataset readers of the reference are outside "
+                                           "this path, labels come from a .pt / .npy file")
         self.test_labels = _load_tensor(self.cfg.data.labels_path, self.device).to(torch.int32)
         self.cache_labels: tp.Optional[torch.Tensor] = None
-        if self.cfg.cache.get("labels_path"):
+        if self.cfg.cache.get("labels_path") and Path(self.cfg.cache.labels_path).exists():
             self.cache_labels = _load_tensor(self.cfg.cache.labels_path, self.device).to(torch.int32)
         if self.cfg.run_saves.save_labels:
             self.save_labels()
@@ -135,7 +138,8 @@ class ImageAttention:
         n_q = self.test_labels.shape[0]
         q_bank = NormalizedBank(self.test_q_norm)
         for cache_strategy_cfg in self.cfg.cache_strategies.values():
-            for cache_strategy, cache_strategy_params in hydra_utils.instantiate_all(self._strategy_cfg(cache_strategy_cfg)):
+            for cache_strategy, cache_strategy_params in hydra_utils.instantiate_all(
+                    cache_strategy_cfg, inject=self._strategy_inject(cache_strategy_cfg)):
                 k_bank, (outs, idx, gold), cache_info = self.build_cache(
                     cache_strategy, self.origin_cache_image_features, self.origin_cache_image_outs)
                 self.logger.log_info(dict(**cache_info, cache_strategy=cache_strategy_params, type="cache_info"))
@@ -145,7 +149,7 @@ class ImageAttention:
                 values_grid = list(hydra_utils.instantiate_all(self.cfg.cache_value_strategy))
                 for vi, (value_strategy, value_params) in enumerate(values_grid):
                     if gold is not None:
-                        value_cache[vi] = GoldCacheValues(outs.shape[1]).transform(gold)
+                        value_cache[vi] = self._gold_values(value_strategy, gold, outs.shape[1])
                     elif isinstance(value_strategy, (HardCacheStrategy, SoftmaxCacheStrategy)):
                         value_cache[vi] = value_strategy.transform(outs, idx=idx)
                     else:
@@ -170,14 +174,28 @@ class ImageAttention:
                                 searcher_info["preds_path"] = str(self.preds_saver.save_tensor(res["pred"][ai].long()))
                             self.logger.log_info_wandb(dict(**searcher_info, type="searcher_result"))
 
-    def _strategy_cfg(self, cfg: tp.Mapping) -> dict:
-        """`cache_dataset: [${cache.dataset}]` entries (conf/cache_strategy/topk_per_gold.yaml:3-4) carry a
-        dataset object in the reference; here the gold-label strategies take the loaded label tensor."""
-        out = dict(cfg)
-        if "cache_dataset" in out:
-            out.pop("cache_dataset")
-            out["cache_labels"] = [self.cache_labels]
-        return out
+    def _strategy_inject(self, cfg: tp.Mapping) -> dict:
+        """`cache_dataset: [${cache.dataset}]` entries (conf/cache_strategy/topk_per_gold.yaml:3-4) carry a dataset
+        object in the reference, which the strategy only reads labels from (`load_labels`, clip_searcher/utils.py:
+        10-12); here the gold-label strategies get the loaded label tensor as `cache_labels`, while the logged
+        parameters keep the configured dataset description (hydra_utils.instantiate_all)."""
+        if "cache_dataset" not in cfg:
+            return {}
+        if self.cache_labels is None:
+            raise ops._lib.SummerClipError(f"{cfg.get('_target_')} needs gold cache labels: set cache.labels_path")
+        return {"cache_dataset": ("cache_labels", self.cache_labels)}
+
+    def _gold_values(self, value_strategy, gold: torch.Tensor, n_classes: int):
+        """cache.replace_outs_with_golds (image_attention.py:65-66): the value strategy is applied to
+        one_hot(gold) instead of the logits.  HardCacheStrategy: argmax(one_hot(g)) = g, the labels themselves.
+        Strategies that take a row gather (SoftmaxCacheStrategy): rows `gold` of the C x C identity ARE
+        one_hot(gold), so softmax(s * one_hot(gold)) comes out of the same kernel without building [Nk, C]."""
+        if isinstance(value_strategy, HardCacheStrategy):
+            return GoldCacheValues(n_classes).transform(gold)
+        eye = torch.eye(n_classes, dtype=torch.float32, device=gold.device)
+        if isinstance(value_strategy, SoftmaxCacheStrategy):
+            return value_strategy.transform(eye, idx=gold.long())
+        return value_strategy.transform(eye[gold.long()])
 
 
 def run_trainer(trainer_cls, cfg, run_dir=".") -> "ImageAttention":
@@ -194,17 +212,26 @@ def run_trainer(trainer_cls, cfg, run_dir=".") -> "ImageAttention":
 
 
 def run(argv: tp.Optional[tp.Sequence[str]] = None) -> ImageAttention:
+    """`image_attention.py [CONFIG.yaml | --config-dir DIR [--config-name NAME]] [key=value | group=option ...]` —
+    the hydra command line of the reference (image_attention.py:123-125): a primary config with a defaults list is
+    composed from its directory, `key=value` overrides are applied after composition."""
     argv = list(sys.argv[1:] if argv is None else argv)
-    import yaml
-    overrides: dict = {}
-    for item in argv[1:]:
-        key, value = item.split("=", 1)
-        cur = overrides
-        parts = key.split(".")
-        for p in parts[:-1]:
-            cur = cur.setdefault(p, {})
-        cur[parts[-1]] = yaml.safe_load(value)
-    cfg = load_config(argv[0], overrides)
+    conf_dir = Path(__file__).resolve().parent.parent / "conf"
+    name = "image_attention"
+    rest: tp.List[str] = []
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a == "--config-dir":
+            conf_dir, i = Path(argv[i + 1]), i + 1
+        elif a == "--config-name":
+            name, i = argv[i + 1], i + 1
+        elif a.endswith((".yaml", ".yml")) and "=" not in a:
+            conf_dir, name = Path(a).resolve().parent, Path(a).stem
+        else:
+            rest.append(a)
+        i += 1
+    cfg = compose(conf_dir, name, rest)
     return run_trainer(ImageAttention, cfg, run_dir=(cfg.get("run_dir") or "."))
 
 

@@ -75,6 +75,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// atomic max of a float cell that starts at -inf (sign-magnitude order: non-negative floats compare as signed
+// ints, negative floats in reverse as unsigned ints; -inf loses to everything under both)
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// what the four consumer warps do with a finished S tile
+enum : int {
+  kAttn = 0,      // Tip-Adapter weights exp(beta (S - 1)), summed per class                       -> O[q, class]
+  kGemmOut = 1,   // scale * S stored as is (split-fp16 GEMM, sc_gemm_split_nt)                     -> Z[q, n]
+  kSoftmax = 2,   // temperature softmax over the keys with a RUNNING ROW MAXIMUM: per class the
+                  // log2-sum-exp of tau * S over its keys (the (m, l) pair in one float)            -> LSE[q, class]
+  kRowMax = 3,    // max_k S[q, k] over the valid keys (pre-pass of the dense-values softmax mode)   -> rowmax[q]
+};
 
 // kGemm = false: the attention kernel described above.  kGemm = true: the same TMA ring / pair-UMMA / TMEM
 // pipeline used as a plain "NT" GEMM with split-fp16 operands (sc_gemm_split_nt): three operand passes
@@ -83,7 +103,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // in image_attention.yaml, 200 in Tip-Adapter's search_hp) pays GEMM-1 once per kNB betas; the exp warps then do
 // kNB exponentials per S element — 2048 MUFU cycles per beta and step against 8192 cycles of UMMAs, so kNB = 4
 // balances the two pipes.
-template <int kOp, bool kGemm, int kNB>
+template <int kOp, int kKind, int kNB>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmQ2, const __grid_constant__ CUtensorMap tmK2, const SParams p) {
@@ -107,6 +127,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int nd = p.n_dchunks;
   constexpr bool kF8 = (kOp == SC_E4M3);
   constexpr int kChunkElems = kF8 ? 2 * kBK : kBK;      // elements in a 128-byte operand row
+  constexpr bool kGemm = (kKind == kGemmOut);
   constexpr int kPasses = kGemm ? 3 : 1;      // operand passes accumulated into one S tile
 
 #ifdef SC_ATTN_TIMING_EXPERIMENTS
@@ -160,7 +181,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // L2 prefetch of the key stream: co-resident pairs walk the same key steps at about the same time, so a
       // step's first touch pays the HBM latency for all of them; one pair in 32 (by query tile) pulls the
       // chunks of step st + pf_dist into L2 ahead of the pack
-      if (!kGemm && p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
+      if (kKind == kAttn && p.pf_dist > 0 && ((st + p.pf_dist) & 31) == static_cast<int>(blockIdx.y & 31u) && st + p.pf_dist < nsteps) {
         if (elect_one()) {
           for (int d = 0; d < nd; ++d) tma_prefetch_2d(&tmK, d * kChunkElems, krow + p.pf_dist * kStepKeys);
         }
@@ -257,6 +278,115 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
         }
       }
+    } else if constexpr (kKind == kRowMax) {
+      // ---- row maximum of S over the valid keys (key index < n_cols); thread = query
+      const int qg = q0 + row;
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int st = 0; st < nsteps; ++st) {
+        const int b = st & 1;
+        mbar_wait(smem_u32(&bars->s_full[b]), (st >> 1) & 1);
+        tc_fence_after();
+        const int n0 = (s0 + st) * kStepKeys;
+#pragma unroll 1
+        for (int cc = 0; cc < kStepKeys / 32; ++cc) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + lane_addr + b * 256 + cc * 32, rg);
+          tmem_ld_wait();
+          const int nb = n0 + cc * 32;
+          if (nb + 32 <= p.n_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(rg[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.n_cols) m = fmaxf(m, __uint_as_float(rg[j]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+          else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
+        }
+      }
+      if (qg < p.Nq && nsteps > 0) atomic_max_f32(p.Z + qg, m * p.scale);
+    } else if constexpr (kKind == kSoftmax) {
+      // ---- temperature softmax over the keys, online: m = running maximum of S over the valid keys seen so far,
+      // acc = sum of exp2(c1 (S - m)) over the keys of the current class.  When m grows acc is rescaled (one ex2 per
+      // 32-key chunk); a finished class leaves as its log2-sum-exp  c1 m + log2(acc), which does not depend on the m
+      // it was accumulated against — so classes flushed under different maxima (and different key splits, and
+      // different ranks) combine exactly: sc_softmax_partials.
+      const float c1 = p.c1[0];
+      const int q = q0 + row;
+      float* orow = p.O + (static_cast<long long>(split) * p.Nq + q) * p.ldo;
+      const bool q_ok = q < p.Nq;
+      int cur = -1;
+      float m = -1e30f, acc = 0.f;
+      auto flush = [&]() {
+        if (cur >= 0 && q_ok && acc > 0.f) orow[cur] = fmaf(c1, m, lg2_approx(acc));
+      };
+#pragma unroll 1
+      for (int st = 0; st < nsteps; ++st) {
+        const int b = st & 1;
+        const uint4* gp = reinterpret_cast<const uint4*>(p.gcls + static_cast<long long>(s0 + st) * 16);
+        const uint4 ga = __ldg(gp), gb = __ldg(gp + 1);
+        const uint4* kp = reinterpret_cast<const uint4*>(p.kbits + static_cast<long long>(s0 + st) * 8);
+        const uint4 ka = __ldg(kp), kb = __ldg(kp + 1);
+        uint32_t myw = 0;                      // lane l < 8: group-class word l, lane 8 + l: validity word l
+        {
+          const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+          const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            myw = lane == i ? gw[i] : myw;
+            myw = lane == 8 + i ? kw[i] : myw;
+          }
+        }
+        mbar_wait(smem_u32(&bars->s_full[b]), (st >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + lane_addr + b * 256;
+#pragma unroll 1
+        for (int cc = 0; cc < kStepKeys / 32; ++cc) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tcol + cc * 32, rg);
+          const uint32_t gwc = __shfl_sync(0xffffffffu, myw, cc);
+          const uint32_t bits = __shfl_sync(0xffffffffu, myw, 8 + cc);
+          tmem_ld_wait();
+          float cm = -1e30f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, ((bits >> j) & 1u) ? __uint_as_float(rg[j]) : -1e30f);
+          const float mn = fmaxf(m, cm);
+          acc *= ex2_approx(c1 * (m - mn));
+          m = mn;
+          const float off = -c1 * m;
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float ea = ex2_approx(fmaf(__uint_as_float(rg[j]), c1, off));
+            const float eb = ex2_approx(fmaf(__uint_as_float(rg[16 + j]), c1, off));
+            sa += ((bits >> j) & 1u) ? ea : 0.f;
+            sb += ((bits >> (16 + j)) & 1u) ? eb : 0.f;
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cls = static_cast<int>(static_cast<int16_t>((gwc >> (16 * hh)) & 0xffffu));
+            if (cls != cur) {
+              flush();
+              cur = cls;
+              acc = 0.f;
+            }
+            acc += hh == 0 ? sa : sb;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+          else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
+        }
+      }
+      flush();
     } else {
     float c1[kNB], cadd[kNB];
 #pragma unroll
@@ -400,10 +530,10 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int kOp, bool kGemm, int kNB>
+template <int kOp, int kKind, int kNB>
 int launch_seg(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmQ2,
                const CUtensorMap& tmK2, const SParams& p) {
-  auto kernel = sc_attn_seg_kernel<kOp, kGemm, kNB>;
+  auto kernel = sc_attn_seg_kernel<kOp, kKind, kNB>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -466,13 +596,17 @@ int attn_seg_splits(int64_t Nq, int64_t Nks, int sm_count, int64_t row_bytes, in
   return best;
 }
 
-// Called by sc_attn_fwd_hard[_multi] (sc_attn.cu) after argument validation: 1..4 betas per launch, O is
-// [n_betas, splits, Nq, ldo] and is zeroed here.
+// sc_softmax.cu
+int fill_f32_async(float* dst, size_t n, float value, cudaStream_t st);
+
+// Called by sc_attn_fwd_hard[_multi] / sc_attn_softmax_hard (sc_attn.cu) after argument validation: 1..4 betas per
+// launch, O is [n_betas, splits, Nq, ldo] and is zeroed here.  softmax != 0 (one "beta" = the temperature): O
+// receives the per-class log2-sum-exp tiles instead and is filled with -inf (= no key of that class) first.
 int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                     int (*make_tmap_u8)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int),
                     const void* Qn, const void* Ks, const int16_t* gcls, const uint32_t* kbits, int op_dtype, int64_t Nq,
                     int64_t Nks, int64_t D_pad, const float* betas, int n_betas, int splits, float* O, int64_t ldo,
-                    cudaStream_t st) {
+                    int softmax, cudaStream_t st) {
   CUtensorMap tmQ, tmK;
   int rc;
   const bool f8 = (op_dtype == SC_E4M3), f16 = (op_dtype == SC_F16);
@@ -502,11 +636,13 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   p.ldo = ldo;
   p.dbg = 0;
   p.clk = nullptr;
-  p.pf_dist = 2;
-  if (const char* env = std::getenv("SC_ATTN_PREFETCH")) {      // tuning knob: L2 prefetch distance (steps)
-    const int want = std::atoi(env);
-    if (want >= 0 && want <= 64) p.pf_dist = want;
-  }
+  // tuning knob, read once per process: L2 prefetch distance in key steps
+  static const int pf_dist = [] {
+    const char* env = std::getenv("SC_ATTN_PREFETCH");
+    const int want = env ? std::atoi(env) : 2;
+    return (want >= 0 && want <= 64) ? want : 2;
+  }();
+  p.pf_dist = pf_dist;
 #ifdef SC_ATTN_TIMING_EXPERIMENTS   // never in the shipped library: skipping work gives wrong results
   if (const char* env = std::getenv("SC_ATTN_DEBUG_SKIP")) p.dbg = std::atoi(env);
   if (std::getenv("SC_ATTN_CLKPROBE")) {
@@ -517,7 +653,11 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
     p.clk = g_clk;
   }
 #endif
-  SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(n_betas) * splits * Nq * ldo * sizeof(float), st));
+  if (softmax) {
+    if ((rc = fill_f32_async(O, static_cast<size_t>(splits) * Nq * ldo, -INFINITY, st)) != SC_OK) return rc;
+  } else {
+    SC_CUDA(cudaMemsetAsync(O, 0, static_cast<size_t>(n_betas) * splits * Nq * ldo * sizeof(float), st));
+  }
   dim3 grid(2u, static_cast<unsigned>(ceil_div(Nq, 2 * kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd_hard: too many query tiles; chunk the queries");
   p.Z = nullptr;
@@ -525,9 +665,14 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   p.n_cols = 0;
   p.scale = 1.0f;
 #define SC_SEG_LAUNCH(NB)                                                          \
-  (f8    ? launch_seg<SC_E4M3, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)         \
-   : f16 ? launch_seg<SC_F16, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)          \
-         : launch_seg<SC_BF16, false, NB>(grid, st, tmQ, tmK, tmQ, tmK, p))
+  (f8    ? launch_seg<SC_E4M3, kAttn, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)         \
+   : f16 ? launch_seg<SC_F16, kAttn, NB>(grid, st, tmQ, tmK, tmQ, tmK, p)          \
+         : launch_seg<SC_BF16, kAttn, NB>(grid, st, tmQ, tmK, tmQ, tmK, p))
+  if (softmax) {
+    return f8    ? launch_seg<SC_E4M3, kSoftmax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p)
+           : f16 ? launch_seg<SC_F16, kSoftmax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p)
+                 : launch_seg<SC_BF16, kSoftmax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p);
+  }
   int rc2;
   switch (n_betas) {
     case 1: rc2 = SC_SEG_LAUNCH(1); break;
@@ -537,6 +682,49 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   }
 #undef SC_SEG_LAUNCH
   return rc2;
+}
+
+// rowmax[q] = max over the Nk keys of Qn[q].Kn[k] (any key order; rows past Nk are never counted): GEMM-1 of the
+// attention kernel with a max instead of the exponential sum.  Pre-pass of the dense-values softmax mode, which
+// needs the exact row maximum before it rounds weights to 16 bits (sc_attn_fwd_shifted).
+int attn_rowmax_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                       int (*make_tmap_u8)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int),
+                       const void* Qn, const void* Kn, int op_dtype, int64_t Nq, int64_t Nk, int64_t D_pad, int splits,
+                       float* rowmax, cudaStream_t st) {
+  CUtensorMap tmQ, tmK;
+  int rc;
+  const bool f8 = (op_dtype == SC_E4M3), f16 = (op_dtype == SC_F16);
+  if (f8) {
+    if ((rc = make_tmap_u8(&tmQ, Qn, Nq, D_pad, D_pad, kBQ)) != SC_OK) return rc;
+    if ((rc = make_tmap_u8(&tmK, Kn, Nk, D_pad, D_pad, kBKeys)) != SC_OK) return rc;
+  } else {
+    if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;
+    if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;
+  }
+  SParams p;
+  p.Nq = static_cast<int>(Nq);
+  p.n_dchunks = static_cast<int>(D_pad / (f8 ? 2 * kBK : kBK));
+  p.steps_total = static_cast<int>(ceil_div(Nk, kStepKeys));
+  p.splits = splits;
+  for (int bi = 0; bi < 4; ++bi) p.c1[bi] = p.c0[bi] = 0.f;
+  p.o_beta_stride = 0;
+  p.gcls = nullptr;
+  p.kbits = nullptr;
+  p.O = nullptr;
+  p.ldo = 0;
+  p.dbg = 0;
+  p.clk = nullptr;
+  p.pf_dist = 0;
+  p.Z = rowmax;
+  p.ldz = 0;
+  p.n_cols = static_cast<int>(Nk);
+  p.scale = f8 ? 1.0f / (SC_E4M3_SCALE * SC_E4M3_SCALE) : 1.0f;
+  if ((rc = fill_f32_async(rowmax, static_cast<size_t>(Nq), -INFINITY, st)) != SC_OK) return rc;
+  dim3 grid(2u, static_cast<unsigned>(ceil_div(Nq, 2 * kBQ)), static_cast<unsigned>(splits));
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_rowmax: too many query tiles; chunk the queries");
+  return f8    ? launch_seg<SC_E4M3, kRowMax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p)
+         : f16 ? launch_seg<SC_F16, kRowMax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p)
+               : launch_seg<SC_BF16, kRowMax, 1>(grid, st, tmQ, tmK, tmQ, tmK, p);
 }
 
 // Z[m, n] = scale * sum_d (Ah[m,d] Bh[n,d] + Ah[m,d] Bl[n,d] + Al[m,d] Bh[n,d]): fp32-accurate "NT" GEMM of
@@ -570,7 +758,7 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.scale = scale;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
   SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
-  return launch_seg<SC_F16, true, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
+  return launch_seg<SC_F16, kGemmOut, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
 }
 
 }  // namespace sc

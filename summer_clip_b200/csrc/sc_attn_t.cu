@@ -1,6 +1,6 @@
 // Transposed CTA-pair variant of the fused CLIP-search attention kernel ("T").
 //
-// Same maths and reference lines as sc_attn.cu (cache_weights_strategy.py:33-36, image_attention.py:109,
+// Reference lines: (cache_weights_strategy.py:33-36, image_attention.py:109,
 // tip_adapter/utils.py:114-116), different operand roles.  All 2*NPAIR CTAs of a cluster work on the SAME
 // 128-query tile; CTA `rank` owns the class slice blockIdx.x and one key tile per round (tile r*CS+rank).
 //   GEMM-1  S^T[256k x 128q]      (cta_group::2, M = the two CTAs' key tiles)
@@ -42,7 +42,7 @@ constexpr int kColO = 256;
 constexpr int kMaxStages = 8;
 constexpr int kMaxCluster = 4;
 constexpr int kSmemPayload = 7 * 32768;
-constexpr int kSmemBytes = kSmemPayload + 1024 + 512;
+constexpr int kSmemBytes = kSmemPayload + 1024 + 1024;   // + alignment slack + barriers and the per-query offsets
 constexpr float kPShift = 8.0f;      // see sc_attn.cu
 
 struct TParams {
@@ -56,6 +56,7 @@ struct TParams {
   int dbg;          // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit0/1/2 skip Q/V/K loads,
                     // 3 exp math, 4/5 GEMM-1/2 MMAs, 6 shrink the exchange to 1 KB
   float c1, c0, o_scale;
+  const float* row_shift;   // nullable [Nq]: weights exp(beta (A - row_shift[q])) instead of exp(beta (A - 1))
   float* O;
   long long ldo;
 };
@@ -70,7 +71,10 @@ struct Bars {
   uint64_t p_empty;                // both: every consumer pair retired GEMM-2 on MY last tile
   uint64_t o_full;                 // both
   uint32_t tmem_slot;
+  uint32_t pad_[3];
+  float c0q[kBQ];                  // exponent offset of every query of the tile: c0 - c1 * (row_shift[q] - 1)
 };
+static_assert(sizeof(Bars) <= 1024, "barrier block");
 
 template <bool kF16>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
@@ -144,6 +148,11 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1) {
     tmem_alloc2(smem_u32(&bars->tmem_slot), kTmemCols);
     tmem_relinquish2();
+  }
+  if (threadIdx.x >= 64) {                       // exp warps: exponent offset per query of the tile
+    const int t = threadIdx.x - 64;
+    const int q = blockIdx.y * kBQ + t;
+    bars->c0q[t] = (p.row_shift != nullptr && q < p.Nq) ? fmaf(-p.c1, p.row_shift[q] - 1.0f, p.c0) : p.c0;
   }
   tc_fence_before();
   __syncthreads();
@@ -329,7 +338,6 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = quad * 32 + lane;                 // TMEM lane = key within my tile (exp) / class (epilogue)
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float c1 = p.c1;
-    const float cadd = p.c0;
     const float o_scale = p.o_scale;
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -342,29 +350,52 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int b = own & 1;
       mbar_wait(smem_u32(&bars->s_full[b]), (own >> 1) & 1);
       tc_fence_after();
-      if (has_tile) {
-        mbar_wait(smem_u32(&bars->p_empty), (sent & 1) ^ 1u);     // both pairs retired my previous tile
+      // The two 64-query halves of the weight tile leave as soon as each is complete: the DSMEM copies of the first
+      // half travel while the second half is exponentiated (the exchange sits on the GEMM-1 -> exp -> GEMM-2 chain).
+      // Half hh goes to the CTAs whose pair rank is hh: my own slot + the other pair's rank-hh CTA when hh == h,
+      // my partner + the other pair's partner-side CTA otherwise (through the staging buffer).
+      if (has_tile) mbar_wait(smem_u32(&bars->p_empty), (sent & 1) ^ 1u);     // both pairs retired my previous tile
 #pragma unroll
-        for (int cc = 0; cc < ((p.dbg & 8) ? 0 : kBQ / 32); ++cc) {
-          uint32_t rg[32];
-          tmem_ld_32x32(tmem_base + lane_addr + b * 128 + cc * 32, rg);
-          tmem_ld_wait();
-          uint32_t pk[16];
+      for (int hh = 0; hh < 2; ++hh) {
+        if (has_tile) {
+          const uint32_t base = ((hh == h) ? my_slot : stag0) + row_off;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(rg[2 * j]), c1, cadd));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(rg[2 * j + 1]), c1, cadd));
-            pk[j] = pack_16x2<kF16>(e0, e1);
+          for (int c2 = 0; c2 < ((p.dbg & 8) ? 0 : 2); ++c2) {
+            const int cc = hh * 2 + c2;
+            uint32_t rg[32];
+            tmem_ld_32x32(tmem_base + lane_addr + b * 128 + cc * 32, rg);
+            const float4* cq = reinterpret_cast<const float4*>(&bars->c0q[cc * 32]);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o4 = cq[j];       // warp-wide broadcast: the offsets of queries cc*32 + 4j .. + 3
+              pk[2 * j] = pack_16x2<kF16>(ex2_approx(fmaf(__uint_as_float(rg[4 * j]), c1, o4.x)),
+                                          ex2_approx(fmaf(__uint_as_float(rg[4 * j + 1]), c1, o4.y)));
+              pk[2 * j + 1] = pack_16x2<kF16>(ex2_approx(fmaf(__uint_as_float(rg[4 * j + 2]), c1, o4.z)),
+                                              ex2_approx(fmaf(__uint_as_float(rg[4 * j + 3]), c1, o4.w)));
+            }
+            // queries cc*32 .. +31 of key `row`: 16-byte chunks c2*4 .. +3 of its row in half hh
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t chunk = static_cast<uint32_t>(c2 * 4 + j);
+              const uint32_t addr = base + ((chunk ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+            }
           }
-          // queries cc*32 .. +31 of key `row`: half (cc>>1) of P^T, 16-byte chunks (cc&1)*4 .. +3 of its row
-          const uint32_t base = (((cc >> 1) == h) ? my_slot : stag0) + row_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t chunk = static_cast<uint32_t>((cc & 1) * 4 + j);
-            const uint32_t addr = base + ((chunk ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * j]),
-                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                         : "memory");
+          fence_proxy_async_smem();
+          named_bar_sync(1, kExpThreads);
+          if (threadIdx.x == 64) {
+            const uint32_t pf = smem_u32(&bars->p_full[rank]);
+            if (hh == h) {
+              mbar_arrive(pf);                                                                           // my own half-slot
+              if (CS == 4) bulk_copy_to_peer(mapa(my_slot, rank ^ 2u), my_slot, xbytes, mapa(pf, rank ^ 2u));   // same half, other pair
+            } else {
+              bulk_copy_to_peer(mapa(my_slot, rank ^ 1u), stag0, xbytes, mapa(pf, rank ^ 1u));                  // partner: other half
+              if (CS == 4) bulk_copy_to_peer(mapa(my_slot, rank ^ 3u), stag0, xbytes, mapa(pf, rank ^ 3u));     // other half, other pair
+            }
           }
         }
       }
@@ -374,20 +405,7 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
         else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), leader);
       }
-      if (has_tile) {
-        fence_proxy_async_smem();
-        named_bar_sync(1, kExpThreads);
-        if (threadIdx.x == 64) {
-          const uint32_t pf = smem_u32(&bars->p_full[rank]);
-          mbar_arrive(pf);                                                   // my own half-slot
-          bulk_copy_to_peer(mapa(my_slot, rank ^ 1u), stag0, xbytes, mapa(pf, rank ^ 1u));          // partner: other half
-          if (CS == 4) {
-            bulk_copy_to_peer(mapa(my_slot, rank ^ 2u), my_slot, xbytes, mapa(pf, rank ^ 2u));      // same half, other pair
-            bulk_copy_to_peer(mapa(my_slot, rank ^ 3u), stag0, xbytes, mapa(pf, rank ^ 3u));        // other half, other pair
-          }
-        }
-        ++sent;
-      }
+      if (has_tile) ++sent;
       ++own;
     }
     // ---- epilogue: O^T blocks (lane = class, column = query) -> O[q, class]
@@ -407,8 +425,8 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int j = 0; j < 16; ++j) {
             const int q = q0 + cc * 16 + j;
             if (q < p.Nq)
-              p.O[(static_cast<long long>(split) * p.Nq + q) * p.ldo + cls] =
-                  (T > 0) ? __uint_as_float(rg[j]) * o_scale : 0.0f;
+              __stcs(&p.O[(static_cast<long long>(split) * p.Nq + q) * p.ldo + cls],
+                     (T > 0) ? __uint_as_float(rg[j]) * o_scale : 0.0f);      // streaming: keep the key bank in L2
           }
         }
       }
@@ -454,7 +472,7 @@ namespace sc {
 int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                   const void* Qn, const void* Kn, const void* Vt, bool f16, int64_t Nq, int64_t Nk, int64_t D_pad,
                   int64_t n_cols, int64_t C_pad, int64_t Nk_pad, int slice, int64_t n_slices, float beta,
-                  int splits, float* O, int64_t ldo, cudaStream_t st) {
+                  const float* row_shift, int splits, float* O, int64_t ldo, cudaStream_t st) {
   SC_REQUIRE(n_slices == 2 || n_slices % 4 == 0, SC_EUNSUPPORTED, "transposed kernel needs 2 or 4k class slices");
   CUtensorMap tmQ, tmK, tmV;
   int rc;
@@ -472,6 +490,7 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
   p.c1 = beta * 1.4426950408889634f;
   p.c0 = -p.c1 + (f16 ? kPShift : 0.0f);
   p.o_scale = f16 ? exp2f(-kPShift) : 1.0f;
+  p.row_shift = row_shift;
   p.O = O;
   p.ldo = ldo;
   p.dbg = 0;
@@ -480,10 +499,8 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
 #endif
   dim3 grid(static_cast<unsigned>(n_slices), static_cast<unsigned>(ceil_div(Nq, kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: too many query tiles; chunk the queries");
-  int cps = 1;
-  if (const char* env = std::getenv("SC_ATTN_T_CHUNKS")) {        // tuning knob: K chunks per ring stage
-    if (std::atoi(env) == 2) cps = 2;
-  }
+  // tuning knob, read once per process: K chunks per ring stage
+  static const int cps = [] { const char* env = std::getenv("SC_ATTN_T_CHUNKS"); return (env && std::atoi(env) == 2) ? 2 : 1; }();
 #define SC_T_LAUNCH(F, NPV)                                                                       \
   (cps == 2 ? launch_t<F, NPV, 2>(grid, st, tmQ, tmK, tmV, p) : launch_t<F, NPV, 1>(grid, st, tmQ, tmK, tmV, p))
   if (n_slices == 2) {

@@ -289,6 +289,34 @@ split_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
   }
 }
 
+// ---- Tip-Adapter cache keys (tip_adapter/utils.py:59-60): mean over the augment epochs, then row L2-normalise,
+// in the storage type's own rounding steps (the reference runs `torch.cat(...).mean(dim=0)` and
+// `cache_keys /= cache_keys.norm(dim=-1, keepdim=True)` on fp16 tensors: the mean, the norm and the quotient are
+// each rounded to fp16; sums are fp32 as in torch's reductions).  Warp per key row, the row read once per epoch.
+template <typename T>
+__global__ void __launch_bounds__(256)
+mean_normalize_rows_kernel(const T* __restrict__ src, int64_t E, int64_t N, int64_t D, int64_t stride_e, int64_t stride_n,
+                           T* __restrict__ dst, int64_t ld_dst) {
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float inv_e = 1.0f / static_cast<float>(E);
+  float ss = 0.f;
+  for (int64_t d = lane; d < D; d += 32) {
+    float acc = 0.f;
+    for (int64_t e = 0; e < E; ++e) acc += sc::to_f32<T>(src[e * stride_e + n * stride_n + d]);
+    const T mean = sc::from_f32<T>(E == 1 ? acc : acc * inv_e);       // rounded like the reference's stored mean
+    dst[n * ld_dst + d] = mean;
+    const float mf = sc::to_f32<T>(mean);
+    ss += mf * mf;
+  }
+  ss = sc::warp_sum(ss);
+  const float norm = sc::to_f32<T>(sc::from_f32<T>(sqrtf(ss)));        // .norm() returns the storage type
+  __syncwarp();
+  for (int64_t d = lane; d < D; d += 32)
+    dst[n * ld_dst + d] = sc::from_f32<T>(sc::to_f32<T>(dst[n * ld_dst + d]) / norm);
+}
+
 }  // namespace
 
 extern "C" int sc_normalize_split(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
@@ -358,6 +386,19 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
                             static_cast<TO*>(dst), D_pad, normalize)));
     });
   }
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+extern "C" int sc_mean_normalize_rows(const void* src, int dtype, int64_t E, int64_t N, int64_t D, int64_t stride_e,
+                                      int64_t stride_n, void* dst, int64_t ld_dst, void* stream) {
+  SC_REQUIRE(src && dst, SC_EINVAL, "sc_mean_normalize_rows: null pointer");
+  SC_REQUIRE(E >= 1 && N >= 0 && D >= 1 && ld_dst >= D, SC_ESHAPE, "sc_mean_normalize_rows: bad shape");
+  if (N == 0) return SC_OK;
+  const unsigned blocks = static_cast<unsigned>(sc::ceil_div(N, 8));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SC_DISPATCH_DTYPE(dtype, T, (mean_normalize_rows_kernel<T><<<blocks, 256, 0, st>>>(
+                                  static_cast<const T*>(src), E, N, D, stride_e, stride_n, static_cast<T*>(dst), ld_dst)));
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }

@@ -133,6 +133,8 @@ extern "C" int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C,
                                  int64_t Nk_pad, int64_t ones_row, void* stream) {
   SC_REQUIRE(Vt, SC_EINVAL, "sc_values_prepare: null Vt");
   SC_REQUIRE(L || (labels_override && mode == SC_VALUES_HARD), SC_EINVAL, "sc_values_prepare: null L");
+  SC_REQUIRE(!(labels_override && mode != SC_VALUES_HARD), SC_EINVAL,
+             "sc_values_prepare: labels_override replaces the argmax of SC_VALUES_HARD only (softmax values come from L[idx])");
   SC_REQUIRE(C > 0 && C_pad >= C && Nk_pad >= n_out && n_out >= 0, SC_ESHAPE, "sc_values_prepare: bad shape");
   SC_REQUIRE(idx || labels_override || n_out == N, SC_ESHAPE, "sc_values_prepare: n_out must equal N without idx");
   SC_REQUIRE(mode == SC_VALUES_HARD || mode == SC_VALUES_SOFTMAX, SC_EINVAL, "sc_values_prepare: bad mode %d", mode);

@@ -94,10 +94,28 @@ def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Ten
         out = torch.empty((n_out, D_pad), dtype=op_dtype, device=x.device)
     else:
         assert out.is_cuda and out.is_contiguous() and out.shape[1] == D_pad and out.shape[0] >= n_out
+        # the library writes through the raw pointer: tell torch, so that caches keyed on the tensor's version
+        # (CacheValues.hard_bank, _BankCache) notice that a preallocated bank was refilled
+        torch.autograd.graph.increment_version(out)
     with torch.cuda.device(x.device):
         check(_lib.load().sc_normalize_cast(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
                                             _ptr(out), _code(out), D_pad, int(normalize), _stream()),
               "sc_normalize_cast")
+    return out
+
+
+def mean_normalize_rows(feats: torch.Tensor) -> torch.Tensor:
+    """Tip-Adapter cache keys from encoder features [E, N, D] (E augment epochs) or [N, D]: row-normalised mean over
+    the epochs, [N, D] of the input dtype (tip_adapter/utils.py:59-60)."""
+    _cuda(feats, "feats")
+    if feats.dim() == 2:
+        feats = feats.unsqueeze(0)
+    assert feats.dim() == 3 and feats.stride(2) == 1
+    E, N, D = feats.shape
+    out = torch.empty((N, D), dtype=feats.dtype, device=feats.device)
+    with torch.cuda.device(feats.device):
+        check(_lib.load().sc_mean_normalize_rows(_ptr(feats), _code(feats), E, N, D, feats.stride(0), feats.stride(1),
+                                                 _ptr(out), D, _stream()), "sc_mean_normalize_rows")
     return out
 
 
@@ -157,6 +175,8 @@ def values_prepare(L: Optional[torch.Tensor], n_classes: int, idx: Optional[torc
     else:
         N, C, ld = 0, n_classes, n_classes
     if labels is not None:
+        if softmax_scale is not None:
+            raise ValueError("values_prepare: `labels` replace the argmax of one-hot values; softmax values are built from L[idx]")
         labels = _cuda(labels, "labels").to(torch.int32).contiguous()
         n_out = labels.numel()
     elif idx is not None:
@@ -241,12 +261,9 @@ class HardBank:
 def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:
     """Layout of the label-sorted bank (once per cache): stable sort of the keys by label, class segments padded
     to multiples of 16, the whole bank padded to whole 256-key steps.  Labels outside [0, n_classes) select no
-    class and are dropped (their one-hot row is zero).  CUDA labels go through sc_hard_bank_layout; CPU labels
-    (the host-logic tests) through the index arithmetic below, which is also the specification the kernel is
-    tested against."""
-    if labels.is_cuda:
-        return _hard_bank_layout_cuda(labels, n_classes)
-    return _hard_bank_layout_torch(labels, n_classes)
+    class and are dropped (their one-hot row is zero).  One library call (sc_hard_bank_layout); the index
+    arithmetic it is tested against, element for element, lives in tests/bank_layout_spec.py."""
+    return _hard_bank_layout_cuda(_cuda(labels, "labels"), n_classes)
 
 
 def _hard_bank_layout_cuda(labels: torch.Tensor, n_classes: int) -> HardBank:
@@ -272,31 +289,6 @@ def _hard_bank_layout_cuda(labels: torch.Tensor, n_classes: int) -> HardBank:
     ns = int(n_sorted.item())                          # the one host sync of a cache build: sizes the bank
     steps = max(1, -(-ns // 256))
     return HardBank(perm[: steps * 256], gcls[: steps * 16], kbits[: steps * 8], ns, n_keys, n_classes)
-
-
-def _hard_bank_layout_torch(labels: torch.Tensor, n_classes: int) -> HardBank:
-    dev = labels.device
-    lab = labels.reshape(-1).to(torch.int64)
-    n_keys = lab.numel()
-    valid = (lab >= 0) & (lab < n_classes)
-    lab_v = torch.where(valid, lab, torch.full_like(lab, n_classes))
-    order = torch.argsort(lab_v, stable=True)
-    counts = torch.bincount(lab_v, minlength=n_classes + 1)[:n_classes]
-    padded = (counts + 15) // 16 * 16
-    seg_start = torch.cumsum(padded, 0) - padded
-    cls_start = torch.cumsum(counts, 0) - counts
-    n_valid, n_sorted = (int(v) for v in torch.stack([counts.sum(), padded.sum()]).tolist())
-    order_v = order[:n_valid]
-    lab_sorted = lab_v[order_v]
-    dest = seg_start[lab_sorted] + (torch.arange(n_valid, device=dev) - cls_start[lab_sorted])
-    steps = max(1, -(-n_sorted // 256))
-    perm = torch.full((steps * 256,), -1, dtype=torch.int64, device=dev)
-    perm[dest] = order_v
-    gcls = torch.full((steps * 16,), -1, dtype=torch.int16, device=dev)
-    gcls[dest // 16] = lab_sorted.to(torch.int16)
-    words = ((perm >= 0).view(-1, 32).to(torch.int64) << torch.arange(32, device=dev)).sum(1)
-    kbits = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
-    return HardBank(perm, gcls, kbits, n_sorted, n_keys, n_classes)
 
 
 def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0, merge: bool = True) -> torch.Tensor:
@@ -384,9 +376,10 @@ def merge_partials(parts: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
 
 
 def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, n_cols: int, beta: float,
-             splits: int = 0, merge: bool = True) -> torch.Tensor:
+             splits: int = 0, merge: bool = True, row_shift: Optional[torch.Tensor] = None) -> torch.Tensor:
     """O[q, c] = sum_k exp(beta (Qn[q].Kn[k] - 1)) Vt[c, k]  ->  fp32 [Nq, n_cols] (or the
-    [splits, Nq, n_cols] partials when merge=False)."""
+    [splits, Nq, n_cols] partials when merge=False).  `row_shift` fp32 [Nq] replaces the constant 1 per query
+    (sc_attn_fwd_shifted: the softmax mode passes the row maximum of `attn_rowmax`)."""
     for t, n in ((Qn, "Qn"), (Kn, "Kn"), (Vt, "Vt")):
         _cuda(t, n)
         assert t.dtype == Qn.dtype and t.dtype in (torch.float16, torch.bfloat16) and t.is_contiguous(), \
@@ -397,14 +390,85 @@ def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, 
     if splits <= 0:
         splits = attn_splits(Nq, n_keys, C_pad, Qn.device)
     O = torch.empty((splits, Nq, n_cols), dtype=torch.float32, device=Qn.device)
+    if row_shift is not None:
+        row_shift = _cuda(row_shift, "row_shift")
+        assert row_shift.dtype == torch.float32 and row_shift.is_contiguous() and row_shift.numel() == Nq
     with torch.cuda.device(Qn.device):
-        check(_lib.load().sc_attn_fwd(_ptr(Qn), _ptr(Kn), _ptr(Vt), _code(Qn), Nq, n_keys, D_pad, n_cols, C_pad, Nk_pad,
-                                      float(beta), splits, _ptr(O), n_cols, _stream()), "sc_attn_fwd")
+        check(_lib.load().sc_attn_fwd_shifted(_ptr(Qn), _ptr(Kn), _ptr(Vt), _code(Qn), Nq, n_keys, D_pad, n_cols, C_pad,
+                                              Nk_pad, float(beta), _ptr(row_shift), splits, _ptr(O), n_cols, _stream()),
+              "sc_attn_fwd")
     if not merge:
         return O
     if splits == 1:
         return O[0]
     return merge_partials(O)
+
+
+def attn_rowmax(Qn: torch.Tensor, Kn: torch.Tensor, n_keys: int) -> torch.Tensor:
+    """fp32 [Nq]: max_k Qn[q].Kn[k] over the first n_keys rows of Kn (tensor-core pass, nothing materialised)."""
+    _cuda(Qn, "Qn"), _cuda(Kn, "Kn")
+    assert Qn.dtype == Kn.dtype and Qn.is_contiguous() and Kn.is_contiguous() and Kn.shape[1] == Qn.shape[1]
+    out = torch.empty(Qn.shape[0], dtype=torch.float32, device=Qn.device)
+    with torch.cuda.device(Qn.device):
+        check(_lib.load().sc_attn_rowmax(_ptr(Qn), _ptr(Kn), _code(Qn), Qn.shape[0], int(n_keys), Qn.shape[1], _ptr(out),
+                                         _stream()), "sc_attn_rowmax")
+    return out
+
+
+def attn_softmax_hard(Qn: torch.Tensor, bank: HardBank, tau: float, splits: int = 0) -> torch.Tensor:
+    """Temperature-softmax attention on a label-sorted bank: fp32 [splits, Nq, n_classes] per-class base-2
+    log-sum-exp of tau * Qn.Ks^T (online running maximum inside the kernel; -inf = no key of that class)."""
+    _cuda(Qn, "Qn")
+    Ks = bank.rows
+    assert Ks is not None, "HardBank.gather(k_norm) must be called first"
+    assert Ks.dtype == Qn.dtype and Ks.is_contiguous() and Qn.is_contiguous() and Ks.shape[1] == Qn.shape[1]
+    Nq, D_pad = Qn.shape
+    n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)
+    if splits <= 0:
+        splits = attn_hard_splits(Nq, n_sorted, Qn.device, bank=bank)
+    lse = torch.empty((splits, Nq, n_classes), dtype=torch.float32, device=Qn.device)     # filled with -inf by the library
+    with torch.cuda.device(Qn.device):
+        check(_lib.load().sc_attn_softmax_hard(_ptr(Qn), _ptr(Ks), _ptr(bank.gcls), _ptr(bank.kbits), _code(Qn), Nq,
+                                               n_sorted, D_pad, n_classes, float(tau), splits, _ptr(lse), n_classes,
+                                               _stream()), "sc_attn_softmax_hard")
+    return lse
+
+
+def softmax_partials(lse: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """LSE tiles [n_parts, Nq, C] -> the (O [Nq, C], m [Nq], l [Nq]) partial triple of those keys."""
+    _cuda(lse, "lse")
+    assert lse.dim() == 3 and lse.dtype == torch.float32 and lse.is_contiguous()
+    n_parts, Nq, C = lse.shape
+    O = torch.empty((Nq, C), dtype=torch.float32, device=lse.device)
+    m = torch.empty(Nq, dtype=torch.float32, device=lse.device)
+    l = torch.empty(Nq, dtype=torch.float32, device=lse.device)
+    with torch.cuda.device(lse.device):
+        check(_lib.load().sc_softmax_partials(_ptr(lse), n_parts, lse.stride(0), Nq, C, C, _ptr(O), C, _ptr(m), _ptr(l),
+                                              _stream()), "sc_softmax_partials")
+    return O, m, l
+
+
+def merge_softmax(O_parts: torch.Tensor, m_parts: torch.Tensor, l_parts: torch.Tensor, m_scale: float = 1.0,
+                  m_ref: Optional[torch.Tensor] = None, normalize: bool = True, inplace: bool = False):
+    """Log-sum-exp merge of (O [P, Nq, C], m [P, Nq], l [P, Nq]) partial triples -> (out [Nq, C], M [Nq], L [Nq]);
+    out is divided by L when `normalize`.  `m_ref`: a common maximum agreed between ranks."""
+    for t, n in ((O_parts, "O_parts"), (m_parts, "m_parts"), (l_parts, "l_parts")):
+        _cuda(t, n)
+        assert t.dtype == torch.float32
+    P, Nq, C = O_parts.shape
+    assert O_parts.stride(2) == 1 and (P == 1 or O_parts.stride(0) >= Nq * O_parts.stride(1))
+    m_parts, l_parts = m_parts.contiguous(), l_parts.contiguous()
+    assert m_parts.shape == (P, Nq) and l_parts.shape == (P, Nq)
+    out = O_parts[0] if (inplace and P == 1) else torch.empty((Nq, C), dtype=torch.float32, device=O_parts.device)
+    M = torch.empty(Nq, dtype=torch.float32, device=O_parts.device)
+    L = torch.empty(Nq, dtype=torch.float32, device=O_parts.device)
+    if m_ref is not None:
+        m_ref = _cuda(m_ref, "m_ref").to(torch.float32).contiguous()
+    with torch.cuda.device(O_parts.device):
+        check(_lib.load().sc_merge_softmax(_ptr(O_parts), _ptr(m_parts), _ptr(l_parts), P, O_parts.stride(0), Nq, Nq, C,
+                                           O_parts.stride(1), float(m_scale), _ptr(m_ref), int(normalize), _ptr(out),
+                                           out.stride(0), _ptr(M), _ptr(L), _stream()), "sc_merge_softmax")
+    return out, M, L
 
 
 def normalize_split(x: torch.Tensor, feature_major: bool, normalize: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -4,8 +4,9 @@ It keeps the (selected, normalised, K-major) key bank and the transposed cache v
 device, streams query banks through normalise -> zero-shot logits -> fused attention -> epilogue,
 and — when a torch.distributed process group is given — shards the KEY bank across ranks: every
 rank scores all queries against its slice of the keys and the partial O tiles are combined with one
-NCCL all-gather + the merge kernel (the Tip weights exp(beta(A-1)) <= 1 need no running maximum, so
-the (m, l, O) log-sum-exp merge degenerates to a sum).
+NCCL reduce-scatter (the Tip weights exp(beta(A-1)) <= 1 need no running maximum, so the (m, l, O)
+log-sum-exp merge degenerates to a sum).  The temperature-softmax mode
+(`set_cache(softmax_normalize=True)`) keeps a running row maximum and merges real (m, l, O) triples.
 
 Reference call sites this engine implements: image_attention.py:48-70 (build_cache), :80-83
 (compute_clip_logits), :106-117 (weights, values, `@`, alpha sweep, accuracy).
@@ -90,6 +91,7 @@ class ClipSearcher:
         self.n_keys_global = 0
         self.n_classes = 0
         self.rowsum_col: tp.Optional[int] = None
+        self.softmax = False                                 # temperature-softmax mode: `betas` are temperatures
         self.gpu_launches = 0                                # kernels of ours launched (bench bookkeeping)
 
     # ------------------------------------------------------------------ bank
@@ -105,7 +107,13 @@ class ClipSearcher:
         """Build the resident cache: K[:, idx] normalised/cast (image_attention.py:54-55 +
         cache_weights_strategy.py:20) and V = f(L[idx]) (cache_value_strategy.py).  With a process group the
         selected keys are sharded contiguously across ranks.  `labels` (gold, already per selected key)
-        replaces argmax(L)."""
+        replaces argmax(L) (one-hot values only).
+        `softmax_normalize=True` selects the temperature-softmax mode (north-star extension, no reference
+        implementation): `search(betas=...)` then computes softmax_k(beta * A) @ V with a running row maximum
+        instead of the Tip-Adapter weights exp(-beta (1 - A)) @ V."""
+        if labels is not None and softmax_scale is not None:
+            raise ValueError("set_cache: `labels` replace the argmax of one-hot values; softmax values are built from "
+                             "cache_image_outs[idx]")
         feats = cache_image_features.to(self.device, non_blocking=True)
         n_total = feats.shape[1] if feature_major else feats.shape[0]
         if idx is not None:
@@ -127,13 +135,17 @@ class ClipSearcher:
             assert n_classes is not None
             self.n_classes = n_classes
         self.k_norm = self.vt = self.hard_bank = None
+        # decided from the arguments alone, so that every rank of a key-sharded group — including one whose shard
+        # is empty — agrees on the mode and on the width of the partial tiles
+        self.softmax = bool(softmax_normalize)
+        hard = softmax_scale is None and ops.hard_supported(self.n_classes)
+        self.rowsum_col = self.n_classes if (softmax_normalize and not hard) else None
         if self.n_keys == 0:
             return
         self.k_norm = ops.normalize_cast(feats, feature_major=feature_major, idx=local_idx, op_dtype=self.op_dtype)
         self.gpu_launches += 1
         local_labels = labels.to(self.device)[lo:hi].contiguous() if labels is not None else None
-        self.rowsum_col = None
-        if softmax_scale is None and not softmax_normalize and ops.hard_supported(self.n_classes):
+        if hard:
             # one-hot values: W @ V is a per-class segmented row sum; sort the keys by label once and let the
             # kernel sum the exponentials per class straight out of tensor memory (sc_attn_fwd_hard)
             labels16 = ops.hard_labels(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
@@ -146,7 +158,6 @@ class ClipSearcher:
                                      labels=local_labels, softmax_scale=softmax_scale, ones_row=softmax_normalize,
                                      op_dtype=self.op_dtype)
         self.gpu_launches += 2 + int(softmax_normalize)
-        self.rowsum_col = self.n_classes if softmax_normalize else None
 
     def save_bank(self, directory, key: str = ""):
         """Write the resident label-sorted bank as a sidecar directory (bank_io.save_hard_bank)."""
@@ -164,7 +175,7 @@ class ClipSearcher:
             return False
         if bank.rows.dtype != self.op_dtype:
             return False
-        self.hard_bank, self.k_norm, self.vt, self.rowsum_col = bank, None, None, None
+        self.hard_bank, self.k_norm, self.vt, self.rowsum_col, self.softmax = bank, None, None, None, False
         self.n_keys = self.n_keys_global = bank.n_keys
         self.n_classes = bank.n_classes
         return True
@@ -182,9 +193,9 @@ class ClipSearcher:
         return qn, z
 
     def local_cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
-        """O_r = exp(-beta (1 - Qn Kn^T)) @ V over THIS rank's keys: fp32 [Nq, C (+1 if a row-sum column was
-        requested)]."""
-        n_cols = self.n_classes + (1 if self.rowsum_col is not None else 0)
+        """O_r = exp(-beta (1 - Qn Kn^T)) @ V over THIS rank's keys: fp32 [Nq, C]."""
+        assert not self.softmax, "temperature-softmax caches go through local_softmax_partials"
+        n_cols = self.n_classes
         nq = qn.shape[0]
         if self.n_keys > 0:
             if self.hard_bank is not None:
@@ -200,10 +211,51 @@ class ClipSearcher:
             part = torch.zeros((nq, n_cols), dtype=torch.float32, device=self.device)
         return part
 
+    def local_softmax_partials(self, qn: torch.Tensor, tau: float) -> tp.Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Temperature-softmax mode, THIS rank's keys: the partial triple (O [Nq, C], m [Nq], l [Nq]) with
+        O[q, c] = sum_k 2^(tau log2(e) A[q, k] - m[q]) V[k, c], l[q] = sum_k 2^(...), m in base-2 exponent units —
+        what `ops.merge_softmax` merges across key shards (the north star's (max, sum, O) tiles).
+        One-hot values: the segmented kernel keeps a running row maximum and emits per-class log-sum-exp tiles.
+        Dense values: the weights are rounded to 16 bits for GEMM-2, so the exact row maximum comes from a
+        tensor-core pre-pass (`ops.attn_rowmax`) and is subtracted inside the dual-GEMM kernel."""
+        nq, c = qn.shape[0], self.n_classes
+        if self.n_keys == 0:
+            return (torch.zeros((nq, c), dtype=torch.float32, device=self.device),
+                    torch.full((nq,), float("-inf"), dtype=torch.float32, device=self.device),
+                    torch.zeros((nq,), dtype=torch.float32, device=self.device))
+        if self.hard_bank is not None:
+            lse = ops.attn_softmax_hard(qn, self.hard_bank, tau)
+            self.gpu_launches += 3
+            return ops.softmax_partials(lse)
+        rowmax = ops.attn_rowmax(qn, self.k_norm, self.n_keys)
+        splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
+        o = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, c + 1, tau, splits=splits, merge=True, row_shift=rowmax)
+        self.gpu_launches += 4 + int(splits > 1)
+        out, m, l = ops.merge_softmax(o[None, :, :c], rowmax[None], o[None, :, c].contiguous(),
+                                      m_scale=float(tau) * 1.4426950408889634, normalize=False)
+        return out, m, l
+
+    def softmax_logits(self, qn: torch.Tensor, tau: float) -> torch.Tensor:
+        """softmax_k(tau * Qn Kn^T) @ V over ALL keys (merged over the key shards): fp32 [Nq, C] on every rank."""
+        o, m, l = self.local_softmax_partials(qn, tau)
+        if self.world > 1 and self.shard == "keys":
+            import torch.distributed as dist
+            m_all = m.clone()
+            dist.all_reduce(m_all, op=dist.ReduceOp.MAX, group=self.group)
+            o, _, l = ops.merge_softmax(o[None], m[None], l[None], m_ref=m_all, normalize=False, inplace=True)
+            dist.all_reduce(o, group=self.group)
+            dist.all_reduce(l, group=self.group)
+            m = m_all
+        out, _, _ = ops.merge_softmax(o[None], m[None], l[None], normalize=True, inplace=True)
+        self.gpu_launches += 1
+        return out
+
     def local_cache_logits_many(self, qn: torch.Tensor, betas: tp.Sequence[float]) -> tp.List[torch.Tensor]:
         """`local_cache_logits` for a list of betas; a one-hot bank shares each tensor-core pass between four betas
         (ops.attn_fwd_hard_multi), every result bit-identical to its single-beta launch."""
         betas = [float(b) for b in betas]
+        if self.softmax:
+            return [self.softmax_logits(qn, b) for b in betas]
         if self.hard_bank is None or self.n_keys == 0 or len(betas) < 2:
             return [self.local_cache_logits(qn, b) for b in betas]
         splits = ops.attn_hard_splits(qn.shape[0], self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
@@ -234,11 +286,7 @@ class ClipSearcher:
             labels = labels.to(self.device, non_blocking=True)
         results = []
         for beta, o in zip(betas, self.local_cache_logits_many(qn, betas)):
-            rowsum = None
-            if self.rowsum_col is not None:
-                rowsum = o[:, self.rowsum_col].contiguous()
-            res = ops.epilogue(z, o[:, : self.n_classes] if self.rowsum_col is not None else o, alphas,
-                               labels=labels, rowsum=rowsum, want_logits=want_logits, want_pred=want_pred)
+            res = ops.epilogue(z, o, alphas, labels=labels, want_logits=want_logits, want_pred=want_pred)
             self.gpu_launches += 1
             res["beta"] = float(beta)
             res["cache_logits"] = o
@@ -289,20 +337,19 @@ class ClipSearcher:
         results = []
         if self.shard == "queries":            # the whole bank is local: score my query slice, nothing to exchange
             parts = self.local_cache_logits_many(qn[lo:hi], betas) if hi > lo else \
-                [torch.zeros((0, self.n_classes + int(self.rowsum_col is not None)), dtype=torch.float32, device=self.device)
-                 for _ in betas]
+                [torch.zeros((0, self.n_classes), dtype=torch.float32, device=self.device) for _ in betas]
+        elif self.softmax:                      # log-sum-exp merge of the (m, l, O) partials inside softmax_logits
+            parts = [o[lo:hi] for o in self.local_cache_logits_many(qn, betas)]
         else:
             parts = self.local_cache_logits_many(qn, betas)
         for beta, o in zip(betas, parts):
-            if self.shard == "keys":
+            if self.shard == "keys" and not self.softmax:
                 o, lo, hi = exchange_partials(o, self.group)
             res = {"beta": float(beta), "lo": lo, "hi": hi, "pred": None, "top1": None, "top5": None, "logits": None}
             na = len(alphas)
             pred_all = torch.zeros((self.world, na, per), dtype=torch.int32, device=self.device)
             if hi > lo:
-                rowsum = o[:, self.rowsum_col].contiguous() if self.rowsum_col is not None else None
-                r = ops.epilogue(z, o[:, : self.n_classes] if self.rowsum_col is not None else o, alphas,
-                                 labels=lab_mine, rowsum=rowsum, want_logits=want_logits, want_pred=want_pred)
+                r = ops.epilogue(z, o, alphas, labels=lab_mine, want_logits=want_logits, want_pred=want_pred)
                 self.gpu_launches += 1
                 res.update(logits=r["logits"], top1=r["top1"], top5=r["top5"])
                 mine = torch.zeros((na, per), dtype=torch.int32, device=self.device)

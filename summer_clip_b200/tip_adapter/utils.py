@@ -5,8 +5,10 @@ The reference recomputes Q@K, exp, @V and the zero-shot GEMM for each of the 200
 (13.4 PFLOP executed at ImageNet scale).  Here the operands are cast once, each beta is one fused
 attention launch and its 20 alphas are one epilogue launch with on-device accuracy counters; the
 search order and the strict `>` (first best wins) are the reference's.
-CLIP feature extraction (build_cache_model / pre_load_features) is outside this path: the cached
-`keys_*.pt`, `values_*.pt`, `*_f.pt`, `*_l.pt` tensors are the inputs.
+The CLIP encoder forward passes of build_cache_model / pre_load_features are outside this path; what those
+functions do AFTER the encoder (mean over augment epochs, row normalisation, permute, one-hot, the
+`keys_*.pt` / `values_*.pt` / `*_f.pt` / `*_l.pt` cache files and their load_cache / load_pre_feat switches) is
+here, on encoder outputs given as tensors.
 """
 from __future__ import annotations
 
@@ -16,6 +18,48 @@ import torch
 
 from .. import ops
 from ..clip_searcher.cache_value_strategy import CacheValues
+
+
+def build_cache_model(cfg, train_features: tp.Optional[torch.Tensor] = None,
+                      train_labels: tp.Optional[torch.Tensor] = None) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+    """tip_adapter/utils.py:38-71 from the encoder outputs on: `train_features` [augment_epoch, Nk, D] (or [Nk, D])
+    are the image features of the few-shot training set per augment epoch, `train_labels` [Nk] their targets.
+    cfg['load_cache'] False: cache_keys = the [D, Nk] permuted view of the row-normalised epoch mean (one kernel,
+    sc_mean_normalize_rows), cache_values = one_hot(labels).half(); both are saved as
+    cache_dir/keys_<shots>shots.pt and values_<shots>shots.pt exactly like the reference.  True: load those files."""
+    keys_path = cfg['cache_dir'] + '/keys_' + str(cfg['shots']) + "shots.pt"
+    values_path = cfg['cache_dir'] + '/values_' + str(cfg['shots']) + "shots.pt"
+    if cfg['load_cache'] == False:  # noqa: E712  (the reference's own test)
+        if train_features is None or train_labels is None:
+            raise ops._lib.SummerClipError("build_cache_model: load_cache is False and no encoder outputs were given "
+                                           "(the CLIP image tower is outside this path)")
+        cache_keys = ops.mean_normalize_rows(train_features).permute(1, 0)
+        # the one-hot matrix exists for the cache FILE only (the format the reference and its notebooks read); the
+        # attention path consumes the labels themselves (CacheValues.from_dense recognises one-hot rows)
+        cache_values = torch.nn.functional.one_hot(train_labels.long()).half()
+        torch.save(cache_keys, keys_path)
+        torch.save(cache_values, values_path)
+    else:
+        cache_keys = torch.load(keys_path)
+        cache_values = torch.load(values_path)
+    return cache_keys, cache_values
+
+
+def pre_load_features(cfg, split: str, features: tp.Optional[torch.Tensor] = None,
+                      labels: tp.Optional[torch.Tensor] = None) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+    """tip_adapter/utils.py:74-96 from the encoder outputs on: `features` [Nq, D] un-normalised image features of
+    the split, row-normalised here (:84) in their own dtype and saved as cache_dir/<split>_f.pt, <split>_l.pt."""
+    f_path, l_path = cfg['cache_dir'] + "/" + split + "_f.pt", cfg['cache_dir'] + "/" + split + "_l.pt"
+    if cfg['load_pre_feat'] == False:  # noqa: E712
+        if features is None or labels is None:
+            raise ops._lib.SummerClipError("pre_load_features: load_pre_feat is False and no encoder outputs were given")
+        features = ops.mean_normalize_rows(features)
+        torch.save(features, f_path)
+        torch.save(labels, l_path)
+    else:
+        features = torch.load(f_path)
+        labels = torch.load(l_path)
+    return features, labels
 
 
 def cls_acc(output: torch.Tensor, target: torch.Tensor, topk: int = 1) -> float:
@@ -79,14 +123,15 @@ class TipAdapterHead:
         return ops.epilogue(self.clip_logits, self.cache_logits(beta), alphas, labels=labels, want_pred=False)["top1"]
 
 
-def search_hp(cfg, cache_keys, cache_values, features, labels, clip_weights, adapter=None):
-    """tip_adapter/utils.py:99-129."""
+def search_hp(cfg, cache_keys, cache_values, features, labels, clip_weights, adapter=None, head=None):
+    """tip_adapter/utils.py:99-129.  `head` (optional): a TipAdapterHead already built from the same operands."""
     best_beta, best_alpha = 0, 0
     if cfg['search_hp'] == True:  # noqa: E712  (the reference's own test)
         beta_list = [i * (cfg['search_scale'][0] - 0.1) / cfg['search_step'][0] + 0.1 for i in range(cfg['search_step'][0])]
         alpha_list = [i * (cfg['search_scale'][1] - 0.1) / cfg['search_step'][1] + 0.1 for i in range(cfg['search_step'][1])]
 
-        head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
+        if head is None:
+            head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
         n = labels.shape[0]
         counts = head.top1_counts_many(beta_list, alpha_list, labels).cpu()                             # one D2H
 

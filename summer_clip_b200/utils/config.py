@@ -1,5 +1,14 @@
-"""YAML config loading with OmegaConf-style `${a.b.c}` interpolation (the subset the hot-path
-configs use: conf/image_attention.yaml:21-44, conf/tip_adapter*.yaml)."""
+"""YAML config loading for the reference's Hydra config tree without hydra/omegaconf (neither is installable
+here): OmegaConf-style `${a.b.c}` interpolation plus the part of Hydra's defaults-list composition the hot-path
+configs use (conf/image_attention.yaml:1-19, conf/tip_adapter*.yaml:1-4, conf/img_attn_dataset/*.yaml:1-2):
+
+  - name                      a config of the same directory, merged at the parent's package
+  - group: option             conf/<group>/<option>.yaml placed under the key `group`
+  - group@pkg.path: option    ... placed under `pkg.path` (relative to the parent's package)
+  - /group: option            group path taken from the config root instead of the parent's directory
+  - _self_                    where the file's own keys merge (last when absent, Hydra >= 1.1)
+
+so that the reference's own YAML files load unmodified (`compose("/…/summer_clip/conf", "image_attention")`)."""
 from __future__ import annotations
 
 import re
@@ -68,9 +77,92 @@ def merge(base: tp.MutableMapping, override: tp.Mapping) -> tp.MutableMapping:
     return base
 
 
+def _set_at(root: dict, package: tp.Sequence[str], content: tp.Mapping) -> None:
+    cur = root
+    for key in package:
+        nxt = cur.get(key)
+        if not isinstance(nxt, dict):
+            nxt = cur[key] = {}
+        cur = nxt
+    merge(cur, content)
+
+
+def _compose_file(conf_root: Path, rel: str, package: tp.List[str], out: dict, choices: tp.Mapping[str, str]) -> None:
+    """Merge conf_root/<rel>.yaml (and, recursively, its defaults list) into `out` at `package`."""
+    path = conf_root / (rel + ".yaml")
+    if not path.exists():
+        raise FileNotFoundError(f"config {rel!r} not found under {conf_root}")
+    with open(path) as f:
+        content = yaml.safe_load(f) or {}
+    defaults = content.pop("defaults", None) or []
+    if "_self_" not in defaults:
+        defaults = list(defaults) + ["_self_"]
+    parent_dir = rel.rsplit("/", 1)[0] if "/" in rel else ""
+    for item in defaults:
+        if item == "_self_":
+            _set_at(out, package, content)
+            continue
+        if isinstance(item, str):                                   # a sibling config, same package
+            _compose_file(conf_root, f"{parent_dir}/{item}" if parent_dir else item, package, out, choices)
+            continue
+        (key, option), = item.items()
+        key = str(key)
+        if key.startswith("override "):
+            key = key[len("override "):]
+        option = choices.get(key, option)
+        if option is None:
+            continue
+        group, _, pkg = key.partition("@")
+        if group.startswith("/"):
+            group_dir = group.lstrip("/")
+        else:
+            group_dir = f"{parent_dir}/{group}" if parent_dir else group
+        if pkg == "_global_":
+            sub_package: tp.List[str] = []
+        elif pkg:
+            sub_package = package + pkg.split(".")
+        else:
+            sub_package = package + group.lstrip("/").split("/")
+        _compose_file(conf_root, f"{group_dir}/{option}", sub_package, out, choices)
+
+
+def compose(conf_root: tp.Union[str, Path], config_name: str, overrides: tp.Optional[tp.Sequence[str]] = None) -> Config:
+    """hydra.compose for the subset above.  `overrides`: `a.b=value` sets a key after composition (value parsed as
+    YAML); `group=option` / `group@pkg=option` picks another option of a defaults-list entry of the primary config
+    (e.g. `cache_value_strategy=softmax_cache`, `img_attn_dataset@dataset_cfg=imagenet`)."""
+    conf_root = Path(conf_root)
+    with open(conf_root / (config_name + ".yaml")) as f:
+        primary = yaml.safe_load(f) or {}
+    group_keys = {str(next(iter(d))) for d in (primary.get("defaults") or []) if isinstance(d, dict)}
+    choices: tp.Dict[str, str] = {}
+    sets: tp.List[tp.Tuple[str, tp.Any]] = []
+    for item in overrides or []:
+        key, _, value = item.partition("=")
+        key = key.lstrip("+")
+        if key in group_keys:
+            choices[key] = value
+        else:
+            sets.append((key, yaml.safe_load(value)))
+    out: dict = {}
+    _compose_file(conf_root, config_name, [], out, choices)
+    for key, value in sets:
+        parts = key.split(".")
+        _set_at(out, parts[:-1], {parts[-1]: value})
+    return resolve(out)
+
+
+def split_overrides(items: tp.Sequence[str]) -> tp.List[str]:
+    """Command-line `key=value` items as given to hydra (kept as strings for `compose`)."""
+    return [it for it in items if "=" in it]
+
+
 def load_config(path: tp.Union[str, Path], overrides: tp.Optional[tp.Mapping] = None) -> Config:
+    path = Path(path)
     with open(path) as f:
         raw = yaml.safe_load(f) or {}
+    if "defaults" in raw:                      # a Hydra primary config: compose it from its own directory
+        raw = {}
+        _compose_file(path.parent, path.stem, [], raw, {})
     if overrides:
         merge(raw, overrides)
     return resolve(raw)

@@ -54,12 +54,26 @@ def instantiate(cfg: tp.Mapping[str, tp.Any], **overrides: tp.Any) -> tp.Any:
     return load_obj(resolve_target(cfg["_target_"]))(**params)
 
 
-def instantiate_all(cfg: tp.Mapping[str, tp.Any]) -> tp.Iterator[tp.Tuple[tp.Any, tp.Dict[str, tp.Any]]]:
+def instantiate_all(cfg: tp.Mapping[str, tp.Any], inject: tp.Optional[tp.Mapping[str, tp.Tuple[str, tp.Any]]] = None) \
+        -> tp.Iterator[tp.Tuple[tp.Any, tp.Dict[str, tp.Any]]]:
     """hydra_utils.py:38-50 — every non-`_target_` key holds a LIST; yield (instance, params) for the
-    Cartesian product in key order.  The yielded params dict keeps the ORIGINAL `_target_` string, so
-    log records are identical to the reference's (notebooks map by class name)."""
+    Cartesian product in key order.  The yielded params dict keeps the ORIGINAL `_target_` string and the
+    ORIGINAL parameter values, so log records are identical to the reference's (notebooks map by class name).
+    `inject` maps a config key to (constructor argument, object): the key's configured value is logged as is but
+    the constructor receives the object under the other name — e.g. `cache_dataset: [${cache.dataset}]`
+    (conf/cache_strategy/topk_per_gold.yaml:3-4) is a dataset description in the record and the loaded label
+    tensor (`cache_labels`) for the strategy, without the tensor ever entering the JSON record or a deepcopy."""
     cfg_dict = copy.deepcopy(dict(cfg))
     target = cfg_dict.pop("_target_")
+    inject = dict(inject or {})
     for param_values in itertools.product(*cfg_dict.values()):
         param_to_value = dict(zip(cfg_dict.keys(), param_values))
-        yield instantiate({"_target_": target, **param_to_value}), {"_target_": target, **copy.deepcopy(param_to_value)}
+        ctor_args = {k: v for k, v in param_to_value.items() if k not in inject}
+        ctor_args.update({new: obj for key, (new, obj) in inject.items() if key in param_to_value})
+        yield _construct(target, ctor_args), {"_target_": target, **copy.deepcopy(param_to_value)}
+
+
+def _construct(target: str, params: tp.Mapping[str, tp.Any]) -> tp.Any:
+    """`instantiate` for arguments that are already objects (no recursion into dict values: an injected-for
+    parameter such as a dataset description must not be instantiated)."""
+    return load_obj(resolve_target(target))(**params)

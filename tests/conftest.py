@@ -5,8 +5,9 @@ from pathlib import Path
 import pytest
 
 REPO = Path(__file__).resolve().parent.parent
-if str(REPO) not in sys.path:
-    sys.path.insert(0, str(REPO))
+for _p in (REPO, REPO / "tests"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
 
 GOLDEN = REPO / "tests" / "golden"
 

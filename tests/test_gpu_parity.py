@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+import bank_layout_spec
 from oracle import clip_search_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -375,7 +376,7 @@ def test_sorted_bank_layout_kernel_matches_the_specification(ops, n_keys, n_clas
     sc_gather_rows == index_select with zero padding rows."""
     g = torch.Generator().manual_seed(84)
     labels = torch.randint(-1, n_classes + 1, (n_keys,), generator=g).int()
-    want = ops._hard_bank_layout_torch(labels, n_classes)
+    want = bank_layout_spec.hard_bank_layout_spec(labels, n_classes)
     for lab in (labels.cuda(), ops.hard_labels(None, n_classes, labels=labels.cuda())[:n_keys]):
         got = ops.hard_bank_layout(lab, n_classes)
         assert got.n_sorted == want.n_sorted and got.n_keys == n_keys
@@ -789,26 +790,3 @@ def test_full_size_key_bank_properties(ops, nq):
     torch.testing.assert_close(ops.merge_partials(torch.stack(hparts)), Oh, rtol=1e-4, atol=1e-4)
     Oh0 = ops.attn_fwd_hard(Qn[:128].contiguous(), bank, 0.0)
     assert torch.equal(Oh0, torch.bincount(yk, minlength=c).float().expand(128, c))
-
-
-# ----------------------------------------------------------------------------- the three attention kernels agree
-@pytest.mark.parametrize("shape", [(300, 2000, 512, 1000), (257, 900, 1024, 397), (129, 300, 128, 100)])
-def test_attention_kernel_variants_agree(ops, shape, monkeypatch):
-    """SC_ATTN_IMPL selects the transposed pair kernel (default), the pair kernel or the single-CTA-MMA
-    cluster kernel.  Same operands -> same result up to the fp32 summation order."""
-    nq, nk, dim, c = shape
-    g = torch.Generator().manual_seed(71)
-    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
-    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda(), False)
-    Vt = ops.values_prepare(torch.randn(nk, c, generator=g).cuda(), c, softmax_scale=2.0)
-    outs = {}
-    for name, env in (("t", {"SC_ATTN_IMPL": "t"}),
-                      ("pair", {"SC_ATTN_IMPL": "pair"}), ("cluster", {"SC_ATTN_IMPL": "cluster"}),
-                      ("cluster1", {"SC_ATTN_IMPL": "cluster", "SC_ATTN_CLUSTER": "1"})):
-        for k in ("SC_ATTN_IMPL", "SC_ATTN_CLUSTER"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        outs[name] = ops.attn_fwd(Qn, Kn, Vt, nk, c, 5.5, splits=2)
-    for name, o in outs.items():
-        torch.testing.assert_close(o, outs["cluster1"], rtol=2e-4, atol=1e-5, msg=lambda m: f"{name}: {m}")

@@ -1,7 +1,10 @@
-"""Host-side index plumbing of the label-sorted key bank (ops.hard_bank_layout): runs on CPU tensors."""
+"""Index plumbing of the label-sorted key bank on CPU tensors: the torch specification the CUDA layout kernel is
+tested against (tests/bank_layout_spec.py) and the sidecar round trip."""
 import numpy as np
 import pytest
 import torch
+
+from bank_layout_spec import hard_bank_layout_spec
 
 
 @pytest.mark.parametrize("n_keys,n_classes,seed", [(1, 1, 0), (17, 3, 1), (1000, 37, 2), (5000, 1000, 3), (300, 5, 4)])
@@ -9,7 +12,7 @@ def test_layout_invariants(n_keys, n_classes, seed):
     from summer_clip_b200 import ops
     g = torch.Generator().manual_seed(seed)
     labels = torch.randint(-1, n_classes + 1, (n_keys,), generator=g).int()      # -1 and n_classes are invalid
-    bank = ops.hard_bank_layout(labels, n_classes)
+    bank = hard_bank_layout_spec(labels, n_classes)
     perm, gcls = bank.perm.numpy(), bank.gcls.numpy()
     bits = bank.kbits.numpy().astype(np.int64) & 0xFFFFFFFF
     valid = (labels >= 0) & (labels < n_classes)
@@ -41,7 +44,7 @@ def test_sidecar_round_trip(tmp_path):
     from summer_clip_b200 import bank_io, ops
     g = torch.Generator().manual_seed(9)
     labels = torch.randint(0, 7, (300,), generator=g).int()
-    bank = ops.hard_bank_layout(labels, 7)
+    bank = hard_bank_layout_spec(labels, 7)
     rows = torch.randn(300, 64, generator=g).half()
     src = bank.perm.clamp_min(0)
     bank.rows = rows[src]

@@ -29,7 +29,8 @@ def _worker(rank: int, world: int, port: int, nq: int, out_dir: str) -> None:
         Q, K, L = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs"))
         lo, hi = shard_range(K.shape[1], rank, world)
         labels = L[lo:hi].argmax(1).int()
-        bank = ops.hard_bank_layout(labels, 23)                       # the shard's own label-sorted layout
+        from bank_layout_spec import hard_bank_layout_spec
+        bank = hard_bank_layout_spec(labels, 23)                       # the shard's own label-sorted layout
         assert sorted(bank.perm[bank.perm >= 0].tolist()) == list(range(hi - lo))
         part = orc.image_attention(Q, K[:, lo:hi], orc.hard_values(L[lo:hi]), 5.5)   # stand-in for the kernel
         rows, qlo, qhi = exchange_partials(part, dist.group.WORLD)

@@ -120,3 +120,33 @@ def test_synthetic_banks_are_seeded_and_feature_major():
     assert a["test_image_features"].shape == (16, 10) and a["cache_image_outs"].shape == (20, 5)
     for k in a:
         assert torch.equal(a[k], b[k])
+
+
+def test_round2_goldens_gold_replace_and_tip_tail(golden_dir):
+    """tests/golden/round2.npz (reference's build_cache with replace_outs_with_golds; build_cache_model tail)."""
+    r2 = np.load(golden_dir / "round2.npz")
+    Q, K, L, T = (torch.from_numpy(r2[f"gr_{n}"]) for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    gold, labels = torch.from_numpy(r2["gr_cache_labels"]), torch.from_numpy(r2["gr_test_labels"]).long()
+    idx = torch.from_numpy(orc.topk_select(L, 4))
+    assert idx.numel() == int(r2["gr_info"][0])
+    outs = orc.golds_as_outs(gold[idx], L.shape[1])
+    assert np.array_equal(outs.float().numpy(), r2["gr_outs_replaced"])
+    acc = orc.compute_accuracy(L[idx], gold[idx].long())
+    assert np.allclose(acc, r2["gr_info"][1:3]) and orc.compute_accuracy(outs.float(), gold[idx].long()) == [100.0, 100.0]
+    Z = orc.zero_shot_logits(Q, T)
+    for vi, values in enumerate((orc.hard_values(outs), orc.softmax_values(outs, orc.CLIP_SCALE, 0.1), orc.softmax_values(outs, orc.CLIP_SCALE, 10.0))):
+        np.testing.assert_allclose(values.float().numpy(), r2[f"gr_values_{vi}"], atol=1e-6)
+        O = orc.image_attention(Q, K[:, idx], values.float(), 5.5)
+        np.testing.assert_allclose(O.numpy(), r2[f"gr_cache_logits_{vi}"], rtol=2e-5, atol=2e-5)
+        accs = np.array([orc.compute_accuracy(orc.searcher_logits(Z, O, a), labels) for a in (0.5, 1.0, 4.0)])
+        np.testing.assert_allclose(accs, r2[f"gr_acc_{vi}"], atol=1e-9)
+    keys = orc.tip_cache_keys(torch.from_numpy(r2["tip_train_features"]))
+    assert np.array_equal(keys.contiguous().numpy(), r2["tip_cache_keys"])
+    assert np.array_equal(orc.tip_normalize_rows(torch.from_numpy(r2["tip_test_features"])).numpy(), r2["tip_test_f"])
+    f32, k32 = torch.from_numpy(r2["tip_test_f"]).float(), torch.from_numpy(r2["tip_cache_keys"]).float()
+    v32, w32 = torch.from_numpy(r2["tip_cache_values"]).float(), torch.from_numpy(r2["tip_clip_weights"]).float()
+    tl = torch.from_numpy(r2["tip_test_labels"])
+    np.testing.assert_allclose(orc.tip_head(f32, k32, v32, w32, 5.5, 1.0).numpy(), r2["tip_logits"], rtol=1e-5, atol=1e-4)
+    assert orc.cls_acc(orc.tip_head(f32, k32, v32, w32, 5.5, 1.0), tl) == float(r2["tip_acc"])
+    bb, ba, _ = orc.search_hp([7, 3], [20, 5], k32, v32, f32, tl, w32)
+    assert np.allclose([bb, ba], r2["tip_best"])
