@@ -710,6 +710,8 @@ def test_image_attention_runner_matches_oracle_sweep(ops, tmp_path):
         "cache_strategies": {"topk": {"topk": [2, 16]}, "topk_prob": {"topk": [4]},
                              "per_pred_class_random": {"topk": [2]}, "global_random": {"topk": [1]}},
     })
+    for group in ("topk_per_gold", "topk_prob_per_gold", "per_gold_class_random"):      # covered by test_gpu_round2.py
+        cfg.cache_strategies.pop(group)
     trainer = run_trainer(ImageAttention, cfg, run_dir=tmp_path / "run")
     records = [json.loads(l) for l in (tmp_path / "run" / "image_attention.log").read_text().splitlines()]
     kinds = [r.get("type") for r in records]
