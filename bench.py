@@ -238,15 +238,16 @@ def run_ours(args):
     q_bank, k_bank, outs, text, labels = make_banks(torch, nq, lo, hi, dim, n_classes, seed=3, device=device)
     soft_scale = 100.00000762939453 * 0.1 if args.values == "softmax" else None     # conf/cache_value_strategy/softmax_cache.yaml
 
-    searcher = ClipSearcher(device, group=None)          # the shard is generated locally; the exchange is done below
+    searcher = ClipSearcher(device, group=group, shard=args.shard)
     searcher.set_text(text)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale)   # normalise+transpose+cast keys; label-sorted bank / dense values
+    # normalise+transpose+cast keys; label-sorted bank / dense values.  Key shards are generated per rank (local_shard)
+    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale, local_shard=shard_keys)
     torch.cuda.synchronize()
     bank_build_first_ms = (time.perf_counter() - t0) * 1e3      # first call: library load, allocator growth included
     t0 = time.perf_counter()
-    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale)
+    searcher.set_cache(k_bank, outs, softmax_scale=soft_scale, local_shard=shard_keys)
     torch.cuda.synchronize()
     bank_build_ms = (time.perf_counter() - t0) * 1e3            # steady state
     n_local = hi - lo
@@ -254,96 +255,28 @@ def run_ours(args):
     # the queries this rank runs attention for: all of them (one GPU, key shards) or its slice (query shards)
     qlo, qhi = query_slice(nq, rank, world) if shard_queries else (0, nq)
     nq_attn = qhi - qlo
-    splits = ops.attn_hard_splits(nq_attn, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
-        else ops.attn_splits(nq_attn, n_local, c_pad, device)
-    if os.environ.get("SC_BENCH_SPLITS"):                  # tuning knob for A/B runs
-        splits = int(os.environ["SC_BENCH_SPLITS"])
-
-    def attn(qn, merge):
-        """Fused attention against the resident bank: one-hot values go through the hard-label kernel (GEMM-2
-        segmented per-class sum on a label-sorted bank), dense values through the Vt-streaming kernel."""
-        if searcher.hard_bank is not None:
-            return ops.attn_fwd_hard(qn, searcher.hard_bank, BETA, splits=splits, merge=merge)
-        return ops.attn_fwd(qn, searcher.k_norm, searcher.vt, n_local, n_classes, BETA, splits=splits, merge=merge)
+    blocks = (int(os.environ["SC_BENCH_BLOCKS"]) if os.environ.get("SC_BENCH_BLOCKS") else None) if shard_keys else None
+    nq_launch = nq_attn // (blocks or 4) if shard_keys else nq_attn        # queries per attention launch
+    splits = ops.attn_hard_splits(nq_launch, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
+        else ops.attn_splits(nq_launch, n_local, c_pad, device)
 
     q_host = q_bank.cpu().pin_memory()
     labels_host = labels.cpu().pin_memory()
     labels_dev = labels
     stream = torch.cuda.current_stream()
-    launches = {"n": 0}
-    phase_marks = None                                     # --phases: [(name, event)] of the step being decomposed
 
-    def mark(name):
-        if phase_marks is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-            phase_marks.append((name, ev))
-
-    per_q = -(-nq // world)
-
-    def gather_results(pred_mine, counts, n_mine):
-        """Predictions of every rank's query slice -> all ranks; accuracy counters summed."""
-        dist.all_reduce(counts, group=group)
-        mine = torch.zeros((1, per_q), dtype=torch.int32, device=device)
-        mine[:, :n_mine] = pred_mine
-        pred_all = torch.empty((world, 1, per_q), dtype=torch.int32, device=device)
-        dist.all_gather_into_tensor(pred_all, mine, group=group)
-        mark("counters_and_predictions")
-        return pred_all.permute(1, 0, 2).reshape(1, world * per_q)[:, :nq], counts
-
-    def finish(q_src, lab_src, o_part):
-        """Zero-shot logits + alpha epilogue.  q_src / lab_src cover the queries [qlo, qhi) attention ran for.
-        Key-sharded ranks: one reduce-scatter sums the partial tiles and hands every rank ITS query slice, which it
-        finishes alone (searcher.exchange_partials / ClipSearcher._search_sharded).  Query-sharded ranks finish
-        their own slice, no exchange.  Either way predictions are all-gathered and the counters all-reduced."""
-        if not shard_keys:
-            z = ops.zero_shot_logits(q_src, True, searcher.text, t_split=searcher.text_split)
-            mark("zero_shot")
-            res = ops.epilogue(z, o_part, [ALPHA], labels=lab_src)   # sums the unmerged key-split tiles as it reads
-            mark("epilogue")
-            launches["n"] += 3                      # split-normalise + tensor-core GEMM (zero-shot logits), epilogue
-            counts = torch.stack([res["top1"], res["top5"]])
-            if world == 1:
-                return res["pred"], counts
-            return gather_results(res["pred"], counts, nq_attn)
-        if o_part.dim() == 3:
-            o_part = ops.merge_partials(o_part)
-            launches["n"] += 1
-            mark("merge_splits")
-        o_mine, slo, shi = exchange_partials(o_part, group)
-        mark("reduce_scatter")
-        z = ops.zero_shot_logits(q_src[:, slo:shi], True, searcher.text, t_split=searcher.text_split)
-        mark("zero_shot")
-        res = ops.epilogue(z, o_mine, [ALPHA], labels=lab_src[slo:shi].contiguous())
-        mark("epilogue")
-        launches["n"] += 3
-        return gather_results(res["pred"], torch.stack([res["top1"], res["top5"]]), shi - slo)
-
-    q_attn = q_bank[:, qlo:qhi] if shard_queries else q_bank          # strided view: the kernels take strides
-    lab_attn = labels_dev[qlo:qhi].contiguous() if shard_queries else labels_dev
-
-    def step_device(time_attn=None):
-        """Inputs resident in HBM."""
-        mark("start")
-        qn = ops.normalize_cast(q_attn, True)
-        mark("normalize_queries")
-        if time_attn is not None:
-            time_attn[0].record(stream)
-        part = attn(qn, False)
-        if time_attn is not None:
-            time_attn[1].record(stream)
-        mark("attention")
-        launches["n"] += 2
-        pred, counts = finish(q_attn, lab_attn, part if splits > 1 else part[0])
-        return {"pred": pred, "top1": counts[0], "top5": counts[1]}
+    def step_device():
+        """Inputs resident in HBM: one call of the public API, ClipSearcher.search."""
+        r = searcher.search(q_bank, [BETA], [ALPHA], labels=labels_dev, want_cache_logits=False, blocks=blocks)[0]
+        return {"pred": r["pred"], "top1": r["top1"], "top5": r["top5"]}
 
     # e2e: queries and labels come from pinned host memory every step and the predictions + counters go back.  Every
-    # rank copies only ITS query slice over PCIe (1/N of the bank); key-sharded ranks, which need every query, then
-    # all-gather the normalised fp16 rows over NVLink.  The host->device copy of step i+1 is issued on a side stream
-    # while step i computes (two device buffers), as a serving loop would; the first copy is fully exposed.
+    # rank copies only ITS query slice over its own PCIe link (1/N of the bank); key-sharded ranks, which need every
+    # query, all-gather the normalised fp16 rows over NVLink inside search(query_shard=True).  The host->device copy
+    # of step i+1 is issued on a side stream while step i computes (two device buffers), as a serving loop would; the
+    # first copy of the timed region is fully exposed.
     copy_stream = torch.cuda.Stream(device=device)
     elo, ehi = query_slice(nq, rank, world)
-    n_e2e = ehi - elo
     q_host_mine = q_host[:, elo:ehi].contiguous().pin_memory() if world > 1 else q_host
     lab_host_mine = labels_host[elo:ehi].contiguous().pin_memory() if world > 1 else labels_host
     q_bufs = [torch.empty_like(q_host_mine, device=device) for _ in range(2)]
@@ -356,8 +289,6 @@ def run_ours(args):
             lab_bufs[i % 2].copy_(lab_host_mine, non_blocking=True)
             copy_done[i % 2].record(copy_stream)
 
-    d_pad = ops.pad_dim(dim, ops.OP_DTYPE)
-
     def step_e2e(i, n_steps):
         """Host buffers in, host result out: H2D of the query slice, D2H of predictions + counters."""
         if i == 0:
@@ -365,23 +296,10 @@ def run_ours(args):
         if i + 1 < n_steps:
             start_copy(i + 1)                       # buffer (i+1) % 2 was last read by step i-1, which has completed
         torch.cuda.current_stream().wait_event(copy_done[i % 2])
-        q_dev, lab = q_bufs[i % 2], lab_bufs[i % 2]
-        qn = ops.normalize_cast(q_dev, True)
-        if shard_keys:                              # every rank needs every query: all-gather the normalised rows
-            qn_pad = qn if n_e2e == per_q else torch.cat([qn, qn.new_zeros((per_q - n_e2e, d_pad))])
-            qn_all = torch.empty((world * per_q, d_pad), dtype=qn.dtype, device=device)
-            dist.all_gather_into_tensor(qn_all, qn_pad, group=group)
-            part = attn(qn_all[:nq], False)
-            o_part = ops.merge_partials(part) if splits > 1 else part[0]
-            o_mine, slo, shi = exchange_partials(o_part, group)
-            z = ops.zero_shot_logits(q_dev, True, searcher.text, t_split=searcher.text_split)
-            res = ops.epilogue(z, o_mine, [ALPHA], labels=lab)
-            pred, counts = gather_results(res["pred"], torch.stack([res["top1"], res["top5"]]), shi - slo)
-        else:
-            part = attn(qn, False)
-            pred, counts = finish(q_dev, lab, part if splits > 1 else part[0])
-        pred = pred.to("cpu", non_blocking=True)
-        counts = counts.to("cpu", non_blocking=True)
+        r = searcher.search(q_bufs[i % 2], [BETA], [ALPHA], labels=lab_bufs[i % 2], want_cache_logits=False,
+                            query_shard=nq if world > 1 else False, blocks=blocks)[0]
+        pred = r["pred"].to("cpu", non_blocking=True)
+        counts = torch.stack([r["top1"], r["top5"]]).to("cpu", non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return pred, counts
 
@@ -401,17 +319,18 @@ def run_ours(args):
     for _ in range(args.warmup):
         res = step_device()
     sync_all()
-    launches["n"] = 0
-    attn_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    searcher.gpu_launches = 0
+    searcher.events = []                                   # (name, start, end) CUDA events on the launching streams
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0.record(stream)
     for i in range(args.steps):
-        res = step_device(attn_events[i])
+        res = step_device()
     ev1.record(stream)
     sync_all()
     clocks = sampler.stop()
+    events, searcher.events = searcher.events, None
     if os.environ.get("SC_ATTN_CLKPROBE"):                 # experiments builds: clock seen by the attention CTAs
         try:
             import ctypes
@@ -422,8 +341,12 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             clocks["attn_cta_mhz"] = str(exc)
     total_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    attn_ms = sum(a.elapsed_time(b) for a, b in attn_events) / args.steps
-    gpu_launches = launches["n"]
+    phase_ms = {}
+    for name, e0, e1 in events:
+        phase_ms[name] = phase_ms.get(name, 0.0) + e0.elapsed_time(e1) / args.steps
+    attn_ms = phase_ms["attention"]                        # per step: the sum over the step's attention launches
+    n_attn_launches = sum(1 for name, _, _ in events if name == "attention") // args.steps
+    gpu_launches = searcher.gpu_launches
     top1 = int(res["top1"][0])
     pred_timed = res["pred"][0].clone()
 
@@ -438,18 +361,7 @@ def run_ours(args):
     sync_all()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_top1 = int(counts[0][0])
-
-    phases = None
-    if args.phases:                                        # untimed extra steps, decomposed with events on the stream
-        acc = {}
-        for _ in range(3):
-            phase_marks = []
-            step_device()
-            sync_all()
-            for (_, e0), (name, e1) in zip(phase_marks[:-1], phase_marks[1:]):
-                acc[name] = acc.get(name, 0.0) + e0.elapsed_time(e1) / 3
-        phase_marks = None
-        phases = {k: round(v, 4) for k, v in acc.items()}
+    phases = {k: round(v, 4) for k, v in phase_ms.items()} if args.phases else None
 
     # ---------------- output check of the step just timed (outside every timed region)
     check = None
@@ -510,7 +422,8 @@ def run_ours(args):
         "config": {"workload": args.workload, "description": desc, "n_queries": nq, "n_keys": nk, "dim": dim,
                    "n_classes": n_classes, "beta": BETA, "alpha": ALPHA,
                    "values": "hard (one-hot of argmax L)" if soft_scale is None else f"softmax({soft_scale:.6f} * L) (SoftmaxCacheStrategy, scale 0.1)",
-                   "sharding": sharding, "key_splits_per_gpu": splits, "accumulate": "fp32",
+                   "sharding": sharding, "key_splits_per_gpu": splits, "attention_launches_per_step": n_attn_launches,
+                   "accumulate": "fp32",
                    "l2": "inputs larger than L2: key bank = %.2f GB per GPU (+ %s)" % (
                        2 * n_local * dim / 1e9, "sorted by label" if not dense else "%.2f GB dense values" % (2 * n_local * c_pad / 1e9)),
                    "values_operand": "one-hot, label-sorted bank (W @ V = per-class segmented sum out of tensor memory)" if not dense else "dense Vt",
@@ -643,7 +556,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager fp16 reference expressions on the GPU")
     ap.add_argument("--no-parity-check", action="store_true")
-    ap.add_argument("--phases", action="store_true", help="add phases_ms: rank 0's per-phase device times of extra untimed steps")
+    ap.add_argument("--phases", action="store_true", help="add phases_ms: rank 0's per-phase device times inside the timed steps")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == "reference":

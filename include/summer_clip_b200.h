@@ -234,6 +234,15 @@ int sc_merge_softmax(const float* O_parts, const float* m_parts, const float* l_
 int sc_merge_partials(const float* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld,
                       float* out, int64_t ld_out, void* stream);
 
+/* The key-sharded exchange as ONE pass over peer memory: out[r, c] = sum_p parts[p][r * ld + c], where parts is a
+ * HOST array of n_parts <= 16 device pointers that may belong to OTHER GPUs of the node (peer-mapped over NVLink,
+ * e.g. the buffers of a symmetric-memory allocation): every rank reads the rows of its query slice straight out of
+ * every rank's partial tile — no staging copy, no NCCL kernel, no shared memory, so the pass runs beside the
+ * attention CTAs of the next query block.  The caller orders it after the peers' writes (a device-side barrier).
+ * Parts are added in index order: every rank computes bit-identical sums. */
+int sc_merge_peer_parts(const float* const* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld, float* out,
+                        int64_t ld_out, void* stream);
+
 /* Zero-shot logits Z = scale * normalise_cols(X)^T @ T in fp32 (image_attention.py:80-83; with
  * scale = 1 also the pseudo-label logits bank of save_image_outs.py:25).
  *   X element (d, n) at X[d*stride_d + n*stride_n]; T is [D, C] row-major with leading dim ldt. */

@@ -64,6 +64,7 @@ SIGNATURES = {
                                  c_float, c_int, c_void_p, c_int64, c_void_p]),
     "sc_attn_fwd_hard_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                        POINTER(c_float), c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "sc_merge_peer_parts": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "sc_merge_partials": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "sc_zero_shot_logits": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int64,
                                     c_int64, c_float, c_int, c_void_p, c_int64, c_void_p]),

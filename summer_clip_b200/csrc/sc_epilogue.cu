@@ -334,9 +334,73 @@ void launch_epilogue_reg(unsigned blocks, cudaStream_t st, const float* Z, int64
                                                            labels, out_logits, pred, top1, top5);
 }
 
+// The same sum over tiles that live at UNRELATED addresses: the partial tiles of the key-sharded ranks, read in
+// place from every peer's memory over NVLink (peer-mapped pointers; the caller orders the read after the peers'
+// writes).  Parts are added in index order on every rank, so all ranks agree bit for bit.  16-byte loads when the
+// shapes allow; every part of a vector is in flight before the adds (~2 us of NVLink latency per dependent load).
+constexpr int kMaxPeerParts = 16;
+struct PeerParts {
+  const float* p[kMaxPeerParts];
+};
+
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+merge_peers_kernel(PeerParts parts, int n_parts, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ out,
+                   int64_t ld_out) {
+  if (kVec) {
+    const int64_t c4 = cols / 4, total = rows * c4;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = e / c4, c = (e - r * c4) * 4;
+      float4 v[kMaxPeerParts];
+#pragma unroll
+      for (int p = 0; p < kMaxPeerParts; ++p)
+        if (p < n_parts) v[p] = *reinterpret_cast<const float4*>(parts.p[p] + r * ld + c);
+      float4 s = v[0];
+#pragma unroll
+      for (int p = 1; p < kMaxPeerParts; ++p)
+        if (p < n_parts) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+      *reinterpret_cast<float4*>(out + r * ld_out + c) = s;
+    }
+  } else {
+    const int64_t total = rows * cols;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = e / cols, c = e - r * cols;
+      float s = parts.p[0][r * ld + c];
+      for (int p = 1; p < n_parts; ++p) s += parts.p[p][r * ld + c];
+      out[r * ld_out + c] = s;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int sc_merge_peer_parts(const float* const* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld, float* out,
+                        int64_t ld_out, void* stream) {
+  SC_REQUIRE(parts && out, SC_EINVAL, "sc_merge_peer_parts: null pointer");
+  SC_REQUIRE(n_parts >= 1 && n_parts <= kMaxPeerParts, SC_ESHAPE, "sc_merge_peer_parts: n_parts=%d must be in [1, %d]",
+             n_parts, kMaxPeerParts);
+  SC_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && ld_out >= cols, SC_ESHAPE, "sc_merge_peer_parts: bad shape");
+  if (rows * cols == 0) return SC_OK;
+  PeerParts pp;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(out);
+  for (int p = 0; p < kMaxPeerParts; ++p) {
+    pp.p[p] = parts[p < n_parts ? p : 0];
+    SC_REQUIRE(pp.p[p] != nullptr, SC_EINVAL, "sc_merge_peer_parts: null part pointer");
+    bits |= reinterpret_cast<uintptr_t>(pp.p[p]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0 && bits % 16 == 0;
+  const int64_t want = sc::ceil_div(rows * (vec ? cols / 4 : cols), 256);
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+  if (vec) merge_peers_kernel<true><<<blocks, 256, 0, st>>>(pp, n_parts, rows, cols, ld, out, ld_out);
+  else merge_peers_kernel<false><<<blocks, 256, 0, st>>>(pp, n_parts, rows, cols, ld, out, ld_out);
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
 
 int sc_merge_partials(const float* parts, int n_parts, int64_t rows, int64_t cols, int64_t ld,
                       float* out, int64_t ld_out, void* stream) {

@@ -346,11 +346,17 @@ def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float]
     return outs
 
 
+# A/B knob for experiments (read once): force the number of key splits of both attention kernels
+_SPLITS_OVERRIDE = int(os.environ.get("SUMMER_CLIP_B200_SPLITS", "0") or 0)
+
+
 def attn_hard_splits(Nq: int, Nks: int, device=None, bank: Optional[HardBank] = None) -> int:
     """Key splits of the segmented kernel.  With `bank` (gathered) the choice also charges every extra split the
     zeroing and reading back of its [Nq, n_classes] tile (sc_attn_hard_splits_for).  Deliberately independent of
     how many betas share the launch: the split count fixes the summation grouping, so a beta computed in a sweep
     stays bit-identical to the same beta computed alone."""
+    if _SPLITS_OVERRIDE > 0:
+        return max(1, min(_SPLITS_OVERRIDE, -(-Nks // 256)))
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
     if bank is not None and bank.rows is not None:
         return int(_lib.load().sc_attn_hard_splits_for(Nq, Nks, bank.rows.shape[1], _code(bank.rows), bank.n_classes, 1, sms))
@@ -358,6 +364,8 @@ def attn_hard_splits(Nq: int, Nks: int, device=None, bank: Optional[HardBank] = 
 
 
 def attn_splits(Nq: int, Nk: int, C_pad: int, device=None) -> int:
+    if _SPLITS_OVERRIDE > 0:
+        return max(1, min(_SPLITS_OVERRIDE, -(-Nk // 128)))
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
     return int(_lib.load().sc_attn_splits(Nq, Nk, C_pad, sms))
 
@@ -372,6 +380,23 @@ def merge_partials(parts: torch.Tensor, out: Optional[torch.Tensor] = None) -> t
     with torch.cuda.device(parts.device):
         check(_lib.load().sc_merge_partials(_ptr(parts), n_parts, rows, cols, cols, _ptr(out), out.stride(0),
                                             _stream()), "sc_merge_partials")
+    return out
+
+
+def merge_peer_parts(parts: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum of equally shaped fp32 [rows, cols] tiles that may live in OTHER GPUs' memory (peer-mapped views of a
+    symmetric-memory allocation): the key-sharded ranks' partial tiles, read in place over NVLink."""
+    rows, cols = parts[0].shape
+    for t in parts:
+        assert t.is_cuda and t.dtype == torch.float32 and t.shape == (rows, cols) and t.stride(1) == 1 and \
+            (rows <= 1 or t.stride(0) == parts[0].stride(0))
+    dev = out.device if out is not None else torch.device("cuda", torch.cuda.current_device())
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    arr = (ctypes.c_void_p * len(parts))(*[t.data_ptr() for t in parts])
+    with torch.cuda.device(dev):
+        check(_lib.load().sc_merge_peer_parts(arr, len(parts), rows, cols, parts[0].stride(0) if rows > 1 else cols, _ptr(out),
+                                              out.stride(0), _stream()), "sc_merge_peer_parts")
     return out
 
 

@@ -13,6 +13,7 @@ Reference call sites this engine implements: image_attention.py:48-70 (build_cac
 """
 from __future__ import annotations
 
+import os
 import typing as tp
 
 import torch
@@ -60,6 +61,24 @@ def exchange_partials(part: torch.Tensor, group: tp.Any) -> tp.Tuple[torch.Tenso
     return full[lo:hi], lo, hi
 
 
+class _PeerTiles:
+    """Partial-tile slots in symmetric memory (torch.distributed._symmetric_memory: one allocation per rank, mapped
+    into every peer over NVLink): rank r writes its partial tile of query block b into ITS slot b, and after a
+    device-side barrier every rank sums the rows of its query slice straight out of all ranks' slots
+    (ops.merge_peer_parts) — the key-sharded exchange without a collective kernel."""
+
+    def __init__(self, group: tp.Any, device: torch.device, n_slots: int, rows: int, cols: int) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.shape = (n_slots, rows, cols)
+        self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group=group.group_name)
+        self.views = [self.hdl.get_buffer(r, self.shape, torch.float32) for r in range(dist.get_world_size(group))]
+
+    def barrier(self, channel: int) -> None:
+        self.hdl.barrier(channel=channel)
+
+
 class ClipSearcher:
     def __init__(self, device: tp.Union[str, torch.device] = "cuda", op_dtype: tp.Optional[torch.dtype] = None,
                  group: tp.Optional[tp.Any] = None, shard: str = "keys") -> None:
@@ -93,6 +112,11 @@ class ClipSearcher:
         self.rowsum_col: tp.Optional[int] = None
         self.softmax = False                                 # temperature-softmax mode: `betas` are temperatures
         self.gpu_launches = 0                                # kernels of ours launched (bench bookkeeping)
+        self.events: tp.Optional[list] = None                # bench.py: set to [] to collect (name, start, end) CUDA events
+        # key-sharded exchange: "p2p" = peers' partial tiles read in place over NVLink (symmetric memory), "nccl" =
+        # reduce-scatter; None = p2p when the process group supports it (decided at the first sharded search)
+        self.exchange: tp.Optional[str] = os.environ.get("SUMMER_CLIP_B200_EXCHANGE") or None
+        self._peer_tiles: tp.Dict[tuple, _PeerTiles] = {}
 
     # ------------------------------------------------------------------ bank
     def set_text(self, text_features: torch.Tensor) -> None:
@@ -103,14 +127,16 @@ class ClipSearcher:
     def set_cache(self, cache_image_features: torch.Tensor, cache_image_outs: tp.Optional[torch.Tensor],
                   idx: tp.Optional[torch.Tensor] = None, *, feature_major: bool = True,
                   softmax_scale: tp.Optional[float] = None, labels: tp.Optional[torch.Tensor] = None,
-                  n_classes: tp.Optional[int] = None, softmax_normalize: bool = False) -> None:
+                  n_classes: tp.Optional[int] = None, softmax_normalize: bool = False, local_shard: bool = False) -> None:
         """Build the resident cache: K[:, idx] normalised/cast (image_attention.py:54-55 +
         cache_weights_strategy.py:20) and V = f(L[idx]) (cache_value_strategy.py).  With a process group the
         selected keys are sharded contiguously across ranks.  `labels` (gold, already per selected key)
         replaces argmax(L) (one-hot values only).
         `softmax_normalize=True` selects the temperature-softmax mode (north-star extension, no reference
         implementation): `search(betas=...)` then computes softmax_k(beta * A) @ V with a running row maximum
-        instead of the Tip-Adapter weights exp(-beta (1 - A)) @ V."""
+        instead of the Tip-Adapter weights exp(-beta (1 - A)) @ V.
+        `local_shard=True` (key-sharded groups): the tensors given ARE this rank's key shard already (a bank too
+        large to exist on one rank, or generated / loaded per rank); nothing is sliced."""
         if labels is not None and softmax_scale is not None:
             raise ValueError("set_cache: `labels` replace the argmax of one-hot values; softmax values are built from "
                              "cache_image_outs[idx]")
@@ -121,12 +147,18 @@ class ClipSearcher:
             n_sel = idx.numel()
         else:
             n_sel = n_total
-        lo, hi = shard_range(n_sel, self.rank, self.world) if self.shard == "keys" else (0, n_sel)
-        if (self.world > 1 and self.shard == "keys") or idx is not None:
+        slice_here = self.world > 1 and self.shard == "keys" and not local_shard
+        lo, hi = shard_range(n_sel, self.rank, self.world) if slice_here else (0, n_sel)
+        if slice_here or idx is not None:
             local_idx = idx[lo:hi] if idx is not None else torch.arange(lo, hi, device=self.device)
         else:
             local_idx = None
         self.n_keys_global, self.n_keys = n_sel, hi - lo
+        if local_shard and self.world > 1 and self.shard == "keys":
+            import torch.distributed as dist
+            total = torch.tensor([n_sel], dtype=torch.int64, device=self.device)
+            dist.all_reduce(total, group=self.group)
+            self.n_keys_global = int(total.item())
         if cache_image_outs is not None:
             outs = cache_image_outs.to(self.device, non_blocking=True)
             self.n_classes = outs.shape[1]
@@ -275,24 +307,60 @@ class ClipSearcher:
 
     def search(self, test_image_features: torch.Tensor, betas: tp.Sequence[float], alphas: tp.Sequence[float],
                labels: tp.Optional[torch.Tensor] = None, feature_major: bool = True, want_logits: bool = False,
-               want_pred: bool = True) -> tp.List[tp.Dict[str, tp.Any]]:
+               want_pred: bool = True, want_cache_logits: bool = True, query_shard: tp.Union[bool, int] = False,
+               blocks: tp.Optional[int] = None) -> tp.List[tp.Dict[str, tp.Any]]:
         """One pass of the hot path for a query bank: for every beta one fused attention launch, then one
         epilogue launch covering every alpha.  Returns one dict per beta with device tensors
-        pred [na, Nq], top1/top5 [na] (if labels), logits [na, Nq, C] (if requested), cache_logits."""
+        pred [na, Nq], top1/top5 [na] (if labels), logits [na, Nq, C] (if requested), cache_logits (if requested;
+        otherwise the key-split tiles go to the epilogue unmerged and no [Nq, C] sum is ever written).
+        Under a process group: `query_shard=True` (or the total query count) says that `test_image_features` /
+        `labels` hold only THIS rank's query slice (`query_slice(nq_total, rank, world)`, e.g. copied from host by each
+        rank on its own PCIe link);
+        `blocks` = query blocks of the key-sharded pipeline (None: chosen from the batch size)."""
         if self.world > 1:
-            return self._search_sharded(test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred)
+            return self._search_sharded(test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred,
+                                        query_shard, blocks)
         qn, z = self.prepare_queries(test_image_features, feature_major)
         if labels is not None:
             labels = labels.to(self.device, non_blocking=True)
         results = []
-        for beta, o in zip(betas, self.local_cache_logits_many(qn, betas)):
+        for beta, o in zip(betas, self._local_parts_many(qn, betas, merge=want_cache_logits)):
             res = ops.epilogue(z, o, alphas, labels=labels, want_logits=want_logits, want_pred=want_pred)
             self.gpu_launches += 1
             res["beta"] = float(beta)
-            res["cache_logits"] = o
+            res["cache_logits"] = o if want_cache_logits else None
             res["clip_logits"] = z
             results.append(res)
         return results
+
+    def _local_parts_many(self, qn: torch.Tensor, betas: tp.Sequence[float], merge: bool) -> tp.List[torch.Tensor]:
+        """This rank's cache logits per beta: merged [Nq, C], or (merge=False, Tip mode) the unmerged key-split
+        tiles [splits, Nq, C] that `ops.epilogue` / `ops.merge_partials` sum."""
+        if merge or self.softmax or self.n_keys == 0:
+            return self.local_cache_logits_many(qn, betas)
+        betas = [float(b) for b in betas]
+        nq = qn.shape[0]
+        t0 = self._mark()
+        if self.hard_bank is not None:
+            splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
+            outs = ops.attn_fwd_hard_multi(qn, self.hard_bank, betas, splits=splits, merge=False)
+            self.gpu_launches += -(-len(betas) // 4)
+        else:
+            splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
+            outs = [ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, self.n_classes, b, splits=splits, merge=False) for b in betas]
+            self.gpu_launches += len(betas)
+        self._mark("attention", t0)
+        return outs
+
+    # device-time bookkeeping for bench.py: (name, start event, end event) triples on the launching stream
+    def _mark(self, name: tp.Optional[str] = None, start: tp.Any = None):
+        if self.events is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        if name is not None and start is not None:
+            self.events.append((name, start, ev))
+        return ev
 
     def capture_search(self, test_image_features: torch.Tensor, betas: tp.Sequence[float], alphas: tp.Sequence[float],
                        labels: tp.Optional[torch.Tensor] = None, feature_major: bool = True, warmup: int = 3):
@@ -315,57 +383,248 @@ class ClipSearcher:
             results = self.search(q, betas, alphas, labels=labels, feature_major=feature_major)
         return graph, results
 
-    def _search_sharded(self, test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred):
-        """Key-sharded `search`: every rank scores ALL queries against its key shard, one reduce-scatter sums
-        the partial tiles and hands each rank its query slice, which it finishes alone (zero-shot logits,
-        alpha epilogue); predictions are all-gathered and the accuracy counters all-reduced, so every rank
-        returns the same pred / top1 / top5.  `logits`, `cache_logits`, `clip_logits` cover the rank's own
-        query slice [`lo`, `hi`)."""
+    def _search_sharded(self, test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred,
+                        query_shard=False, blocks=None):
+        """`search` under a process group.  Every rank returns the same pred / top1 / top5; `logits`, `cache_logits`,
+        `clip_logits` cover the rank's own rows only (a list of (lo, hi, tensor) pieces in `pieces`).
+
+        shard = "queries": every rank scores its query slice against the whole bank — no data-path collective.
+        shard = "keys": every rank scores ALL queries against its key shard; per query block one reduce-scatter sums
+        the partial tiles and hands each rank its slice of the block, which it finishes alone (zero-shot logits,
+        alpha epilogue).  The exchange and the finishing of block b run on a side stream UNDER the attention of
+        block b + 1, so only the last block's exchange is exposed (at 8 GPUs the reduce-scatter of a whole
+        50 000 x 1000 tile was 0.93 ms of a 12.5 ms step: profiles/r01g_bench_n8_phases.json).  Predictions are
+        all-gathered per block, the accuracy counters all-reduced once."""
         import torch.distributed as dist
-        q = test_image_features.to(self.device, non_blocking=True)
-        qn = ops.normalize_cast(q, feature_major=feature_major, op_dtype=self.op_dtype)
+        dev, world, rank = self.device, self.world, self.rank
+        q = test_image_features.to(dev, non_blocking=True)
+        n_given = q.shape[1] if feature_major else q.shape[0]
+        na = len(alphas)
+        t0 = self._mark()
+        qn_mine = ops.normalize_cast(q, feature_major=feature_major, op_dtype=self.op_dtype)
         self.gpu_launches += 1
-        nq = qn.shape[0]
-        lo, hi = query_slice(nq, self.rank, self.world)
-        per = -(-nq // self.world)
-        z = None
-        if self.text is not None and hi > lo:
-            q_mine = q[:, lo:hi] if feature_major else q[lo:hi]
-            z = ops.zero_shot_logits(q_mine, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
-            self.gpu_launches += 1
-        lab_mine = labels.to(self.device, non_blocking=True)[lo:hi].contiguous() if labels is not None else None
-        results = []
-        if self.shard == "queries":            # the whole bank is local: score my query slice, nothing to exchange
-            parts = self.local_cache_logits_many(qn[lo:hi], betas) if hi > lo else \
-                [torch.zeros((0, self.n_classes), dtype=torch.float32, device=self.device) for _ in betas]
-        elif self.softmax:                      # log-sum-exp merge of the (m, l, O) partials inside softmax_logits
-            parts = [o[lo:hi] for o in self.local_cache_logits_many(qn, betas)]
-        else:
-            parts = self.local_cache_logits_many(qn, betas)
-        for beta, o in zip(betas, parts):
-            if self.shard == "keys" and not self.softmax:
-                o, lo, hi = exchange_partials(o, self.group)
-            res = {"beta": float(beta), "lo": lo, "hi": hi, "pred": None, "top1": None, "top5": None, "logits": None}
-            na = len(alphas)
-            pred_all = torch.zeros((self.world, na, per), dtype=torch.int32, device=self.device)
-            if hi > lo:
-                r = ops.epilogue(z, o, alphas, labels=lab_mine, want_logits=want_logits, want_pred=want_pred)
-                self.gpu_launches += 1
-                res.update(logits=r["logits"], top1=r["top1"], top5=r["top5"])
-                mine = torch.zeros((na, per), dtype=torch.int32, device=self.device)
-                if want_pred:
-                    mine[:, : hi - lo] = r["pred"]
+        if query_shard:
+            if query_shard is True:
+                # the total is recovered from the ranks' row counts (one small all-reduce and a host sync; pass the
+                # total query count as `query_shard=nq_total` to avoid both)
+                sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+                sizes[rank] = n_given
+                dist.all_reduce(sizes, group=self.group)
+                sizes = sizes.tolist()
             else:
-                mine = torch.zeros((na, per), dtype=torch.int32, device=self.device)
-            if labels is not None:
-                counts = torch.stack([res["top1"], res["top5"]]) if res["top1"] is not None else \
-                    torch.zeros((2, na), dtype=torch.int32, device=self.device)
-                dist.all_reduce(counts, group=self.group)
-                res["top1"], res["top5"] = counts[0], counts[1]
+                sizes = [hi_ - lo_ for lo_, hi_ in (query_slice(int(query_shard), r, world) for r in range(world))]
+                assert sizes[rank] == n_given, "query_shard=nq_total: this rank must hold query_slice(nq_total, rank, world)"
+            nq = int(sum(sizes))
+            per = max(sizes)
+            my_lo = int(sum(sizes[:rank]))
+        else:
+            nq, per, my_lo = n_given, -(-n_given // world), None
+        lab = labels.to(dev, non_blocking=True).to(torch.int32) if labels is not None else None
+        results = [{"beta": float(b), "pred": None, "top1": None, "top5": None, "logits": None, "pieces": []} for b in betas]
+        counts = torch.zeros((len(betas), 2, na), dtype=torch.int32, device=dev)
+
+        if self.shard == "queries":
+            lo, hi = (my_lo, my_lo + n_given) if query_shard else query_slice(nq, rank, world)
+            q_mine = q if query_shard else (q[:, lo:hi] if feature_major else q[lo:hi])
+            qn = qn_mine if query_shard else qn_mine[lo:hi]
+            lab_mine = (lab if query_shard else lab[lo:hi].contiguous()) if lab is not None else None
+            self._mark("normalize_queries", t0)
+            z = None
+            if self.text is not None and hi > lo:
+                z = ops.zero_shot_logits(q_mine, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
+                self.gpu_launches += 1
+            parts = self._local_parts_many(qn, betas, merge=False) if hi > lo else [None] * len(betas)
+            preds = []
+            for bi, o in enumerate(parts):
+                mine = torch.zeros((na, per), dtype=torch.int32, device=dev)
+                if o is not None:
+                    r = ops.epilogue(z, o, alphas, labels=lab_mine, want_logits=want_logits, want_pred=want_pred)
+                    self.gpu_launches += 1
+                    if lab_mine is not None:
+                        counts[bi, 0], counts[bi, 1] = r["top1"], r["top5"]
+                    if want_pred:
+                        mine[:, : hi - lo] = r["pred"]
+                    results[bi]["pieces"].append((lo, hi, r["logits"], o, z))
+                preds.append(mine)
             if want_pred:
-                dist.all_gather_into_tensor(pred_all, mine, group=self.group)
-                res["pred"] = pred_all.permute(1, 0, 2).reshape(na, self.world * per)[:, :nq].contiguous()
-            res["cache_logits"] = o
-            res["clip_logits"] = z
-            results.append(res)
+                gathered = torch.empty((world, len(betas), na, per), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(gathered, torch.stack(preds), group=self.group)
+                for bi in range(len(betas)):
+                    if query_shard:
+                        results[bi]["pred"] = torch.cat([gathered[r, bi, :, : sizes[r]] for r in range(world)], dim=1)
+                    else:
+                        results[bi]["pred"] = gathered[:, bi].permute(1, 0, 2).reshape(na, world * per)[:, :nq].contiguous()
+        else:
+            # ---- key shards: all queries on every rank
+            if query_shard:
+                pad = qn_mine if n_given == per else torch.cat([qn_mine, qn_mine.new_zeros((per - n_given, qn_mine.shape[1]))])
+                allq = torch.empty((world * per, qn_mine.shape[1]), dtype=qn_mine.dtype, device=dev)
+                dist.all_gather_into_tensor(allq, pad, group=self.group)            # normalised rows over NVLink
+                qn = allq[:nq] if all(sz == per for sz in sizes[:-1]) else torch.cat([allq[r * per: r * per + sizes[r]] for r in range(world)])
+            else:
+                qn = qn_mine
+            self._mark("normalize_queries", t0)
+            if blocks is None:
+                blocks = 4 if (nq >= 16384 and not self.softmax) else 1
+            blocks = max(1, min(int(blocks), nq))
+            edges = [nq * b // blocks for b in range(blocks + 1)]
+            lab_all = self._all_labels(lab, query_shard, sizes if query_shard else None, per, nq)
+            main = torch.cuda.current_stream(dev)
+            side = self._side_stream()
+            bmax = max(edges[b + 1] - edges[b] for b in range(blocks))
+            nbeta = len(betas)
+            tiles = None if self.softmax else self._tiles_for("o", blocks * nbeta, bmax, self.n_classes)
+            # predictions and counters travel the same way: every rank writes its rows (as exact fp32 integers, zeros
+            # elsewhere) and its local counters into its own peer-mapped result tile; one summing pass over all
+            # ranks' tiles at the end is the all-gather of the predictions AND the all-reduce of the counters
+            rtile = self._tiles_for("r", nbeta, na, nq + 2) if tiles is not None else None
+            if rtile is not None:
+                rtile.buf.zero_()
+            keep = []                                   # tensors the side stream still reads: alive until the final join
+            preds = [torch.zeros((na, nq), dtype=torch.int32, device=dev) for _ in betas] if (want_pred and rtile is None) else None
+            for b in range(blocks):
+                b0, b1 = edges[b], edges[b + 1]
+                nb = b1 - b0
+                parts = self._local_parts_many(qn[b0:b1], betas, merge=False)
+                merged = []
+                tm = self._mark()
+                for bi, o in enumerate(parts):
+                    if self.softmax:
+                        merged.append(o)
+                    elif tiles is not None:             # the summed key-split tiles land in my slot of the peer-mapped buffer
+                        merged.append(ops.merge_partials(o if o.dim() == 3 else o[None], out=tiles.buf[b * nbeta + bi, :nb]))
+                        self.gpu_launches += 1
+                    else:
+                        merged.append(ops.merge_partials(o) if o.dim() == 3 and o.shape[0] > 1 else (o[0] if o.dim() == 3 else o))
+                        self.gpu_launches += int(o.dim() == 3 and o.shape[0] > 1)
+                self._mark("merge_splits", tm)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                keep.append((parts, merged))
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    ts = self._mark()
+                    slo, shi = query_slice(nb, rank, world)
+                    bper = -(-nb // world)
+                    glo, ghi = b0 + slo, b0 + shi          # my rows of this block, global numbering
+                    z = None
+                    if self.text is not None and ghi > glo:
+                        if query_shard:                     # the raw rows may live on another rank: use the normalised ones
+                            z = ops.zero_shot_logits(qn[glo:ghi], False, self.text, scale=100.0, normalize=False, t_split=self.text_split)
+                        else:
+                            z = ops.zero_shot_logits(q[:, glo:ghi] if feature_major else q[glo:ghi], feature_major, self.text,
+                                                     scale=100.0, normalize=True, t_split=self.text_split)
+                        self.gpu_launches += 1
+                    lab_mine = lab_all[glo:ghi].contiguous() if lab_all is not None else None
+                    if tiles is not None:
+                        tiles.barrier(b)                    # every rank's slots of block b are complete
+                    for bi, o in enumerate(merged):
+                        if self.softmax:            # already merged over the key shards (log-sum-exp merge, softmax_logits)
+                            o_mine = o[slo:shi]
+                        elif tiles is not None:
+                            o_mine = None
+                            if shi > slo:
+                                o_mine = ops.merge_peer_parts([v[b * nbeta + bi, slo:shi] for v in tiles.views])
+                                self.gpu_launches += 1
+                        else:
+                            o_mine, _, _ = exchange_partials(o, self.group)
+                        r = None
+                        if ghi > glo:
+                            r = ops.epilogue(z, o_mine, alphas, labels=lab_mine, want_logits=want_logits, want_pred=want_pred)
+                            self.gpu_launches += 1
+                            if lab_mine is not None:
+                                counts[bi, 0] += r["top1"]
+                                counts[bi, 1] += r["top5"]
+                            results[bi]["pieces"].append((glo, ghi, r["logits"], o_mine, z))
+                        if want_pred and rtile is not None:
+                            if r is not None:
+                                rtile.buf[bi, :, glo:ghi] = r["pred"]          # int32 -> exact fp32
+                        elif want_pred:
+                            mine = torch.zeros((na, bper), dtype=torch.int32, device=dev)
+                            if r is not None:
+                                mine[:, : shi - slo] = r["pred"]
+                            gathered = torch.empty((world, na, bper), dtype=torch.int32, device=dev)
+                            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+                            preds[bi][:, b0:b1] = gathered.permute(1, 0, 2).reshape(na, world * bper)[:, :nb]
+                            keep.append((gathered, mine))
+                        keep.append((o_mine, z, r))
+                    self._mark("exchange_and_finish", ts)
+            with torch.cuda.stream(side):
+                if rtile is not None:
+                    tf = self._mark()
+                    if lab is not None:
+                        rtile.buf[:, :, nq:] = counts.permute(0, 2, 1)          # [nbeta, na, 2] local counters
+                    rtile.barrier(blocks)               # every rank's result tile is complete
+                    for bi in range(nbeta):
+                        total = ops.merge_peer_parts([v[bi] for v in rtile.views]).to(torch.int32)     # [na, nq + 2]
+                        self.gpu_launches += 1
+                        if want_pred:
+                            results[bi]["pred"] = total[:, :nq]
+                        if lab is not None:
+                            results[bi]["top1"], results[bi]["top5"] = total[:, nq].contiguous(), total[:, nq + 1].contiguous()
+                    rtile.barrier(blocks + 1)           # nobody rewrites a tile (next search) while a peer still reads it
+                    self._mark("gather_results", tf)
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            if preds is not None:
+                for bi in range(nbeta):
+                    results[bi]["pred"] = preds[bi]
+            del keep
+            if rtile is not None:
+                lab = None                              # counters already summed over the ranks
+        if lab is not None:
+            dist.all_reduce(counts, group=self.group)
+            for bi in range(len(betas)):
+                results[bi]["top1"], results[bi]["top5"] = counts[bi, 0], counts[bi, 1]
+        for res in results:                                   # single-piece conveniences (one block / query shards)
+            if len(res["pieces"]) == 1:
+                res["lo"], res["hi"], res["logits"], res["cache_logits"], res["clip_logits"] = res["pieces"][0]
         return results
+
+    def _tiles_for(self, kind: str, n_slots: int, rows: int, cols: int) -> tp.Optional[_PeerTiles]:
+        """The peer-mapped tile slots of this kind ("o" partial cache logits, "r" results) and shape, or None when the
+        exchange is NCCL's.  Collective: every rank calls it with the same shape (the first call per shape allocates
+        and exchanges handles; a new shape replaces the previous allocation of its kind)."""
+        import torch.distributed as dist
+        if self.exchange == "nccl":
+            return None
+        key = (kind, n_slots, rows, cols)
+        if key not in self._peer_tiles:
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            tiles = None
+            try:
+                if dist.get_backend(self.group) != "nccl":
+                    raise RuntimeError("symmetric memory needs the NCCL group of one node")
+                tiles = _PeerTiles(self.group, self.device, n_slots, rows, cols)
+            except Exception:  # noqa: BLE001  (no peer mapping on this system: fall back to the collective)
+                if self.exchange == "p2p":
+                    raise
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self.exchange = "nccl"
+                return None
+            self._peer_tiles = {k: v for k, v in self._peer_tiles.items() if k[0] != kind}
+            self._peer_tiles[key] = tiles
+        return self._peer_tiles[key]
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._side
+
+    def _all_labels(self, lab, query_shard, sizes, per, nq):
+        """Labels of ALL queries on this rank (key shards finish rows that another rank brought in)."""
+        if lab is None or not query_shard:
+            return lab
+        cached = getattr(self, "_lab_all_cache", None)
+        if cached is not None and cached[0] is lab:
+            return cached[1]
+        import torch.distributed as dist
+        pad = lab if lab.numel() == per else torch.cat([lab, lab.new_zeros(per - lab.numel())])
+        allv = torch.empty(self.world * per, dtype=lab.dtype, device=self.device)
+        dist.all_gather_into_tensor(allv, pad, group=self.group)
+        out = allv[:nq] if all(sz == per for sz in sizes[:-1]) else torch.cat([allv[r * per: r * per + sizes[r]] for r in range(self.world)])
+        self._lab_all_cache = (lab, out)
+        return out

@@ -1,4 +1,6 @@
-"""2-rank NCCL check of the key-sharded ClipSearcher.search against the single-rank result (run under torchrun)."""
+"""N-rank NCCL check of the sharded ClipSearcher.search (key shards with the query-blocked overlap pipeline, query
+shards, per-rank query slices, the temperature-softmax (m, l, O) merge) against the single-rank result and the
+oracle.  Run under torchrun:  python -m torch.distributed.run --nproc-per-node 2 tests/checks/check_sharded.py"""
 import os
 import sys
 
@@ -7,13 +9,31 @@ import torch
 import torch.distributed as dist
 
 from oracle import clip_search_oracle as orc
-from summer_clip_b200.searcher import ClipSearcher
+from summer_clip_b200.searcher import ClipSearcher, query_slice
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 ok = True
+BETAS = [5.5, 0.1, 1.0, 3.5, 11.5]                 # one-hot banks: a 4-beta launch + a 1-beta launch
+ALPHAS = [0.5, 2.0]
+
+
+def compare(gots, refs, what):
+    """every rank: same pred / counts as the single-rank search; logits of its own pieces equal."""
+    e, same_pred, same_cnt, rows = 0.0, True, True, 0
+    for got, r in zip(gots, refs):
+        for lo, hi, logits, _, _ in got["pieces"]:
+            e = max(e, (logits - r["logits"][:, lo:hi]).abs().max().item() / r["logits"].abs().max().item())
+            rows += hi - lo
+        same_pred &= got["pred"].shape == r["pred"].shape and bool((got["pred"] == r["pred"]).float().mean() > 0.999)
+        same_cnt &= bool((got["top1"] - r["top1"]).abs().max() <= 1) and bool((got["top5"] - r["top5"]).abs().max() <= 1)
+    good = e < 1e-4 and same_pred and same_cnt
+    print(f"rank {rank} {what}: rows={rows // len(gots)} rel_err={e:.2e} pred={same_pred} counts={same_cnt} {'OK' if good else 'FAIL'}", flush=True)
+    return good
+
+
 for nq, hard in ((1001, True), (512, True), (777, False)):
     banks = orc.synthetic_banks(nq, 5000, 256, 300, seed=5, sigma=0.5, sigma_text=0.8, shared=3.0)
     Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
@@ -22,30 +42,40 @@ for nq, hard in ((1001, True), (512, True), (777, False)):
     single = ClipSearcher(dev)
     single.set_text(T)
     single.set_cache(K, L, **kw)
-    BETAS = [5.5, 0.1, 1.0, 3.5, 11.5]                 # one-hot banks: a 4-beta launch + a 1-beta launch
-    refs = single.search(Q, BETAS, [0.5, 2.0], labels=labels, want_logits=True)
-    ref = refs[0]
+    refs = single.search(Q, BETAS, ALPHAS, labels=labels, want_logits=True)
     V = orc.hard_values(L.float()) if hard else orc.softmax_values(L.float(), orc.CLIP_SCALE, 0.1)
     want = orc.searcher_logits(orc.zero_shot_logits(Q.float(), T.float()), orc.image_attention(Q, K, V, 5.5), 0.5)
-    e0 = (ref["logits"][0].cpu() - want).abs().max().item() / want.abs().max().item()
+    e0 = (refs[0]["logits"][0].cpu() - want).abs().max().item() / want.abs().max().item()
     print(f"rank {rank} nq={nq} hard={hard}: single-rank result vs oracle rel_err={e0:.2e}", flush=True)
     ok &= e0 < 2e-3
+    lo, hi = query_slice(nq, rank, world)
     for shard in ("keys", "queries"):
         sharded = ClipSearcher(dev, group=dist.group.WORLD, shard=shard)
         sharded.set_text(T)
         sharded.set_cache(K, L, **kw)
-        gots = sharded.search(Q, BETAS, [0.5, 2.0], labels=labels, want_logits=True)
-        e, same_pred, same_cnt = 0.0, True, True
-        for got, r in zip(gots, refs):
-            lo, hi = got["lo"], got["hi"]
-            e = max(e, (got["logits"] - r["logits"][:, lo:hi]).abs().max().item() / r["logits"].abs().max().item())
-            same_pred &= bool((got["pred"] == r["pred"]).float().mean() > 0.999) and got["pred"].shape == r["pred"].shape
-            same_cnt &= bool((got["top1"] - r["top1"]).abs().max() <= 1) and bool((got["top5"] - r["top5"]).abs().max() <= 1)
-        got = gots[0]
-        good = e < 1e-4 and same_pred and same_cnt and got["pred"].shape == ref["pred"].shape
-        ok &= good
-        print(f"rank {rank} nq={nq} hard={hard} shard={shard}: slice=[{lo},{hi}) rel_err={e:.2e} pred={same_pred} "
-              f"counts={same_cnt} {'OK' if good else 'FAIL'}", flush=True)
+        for blocks in ((1, 3) if shard == "keys" else (None,)):
+            gots = sharded.search(Q, BETAS, ALPHAS, labels=labels, want_logits=True, blocks=blocks)
+            ok &= compare(gots, refs, f"nq={nq} hard={hard} shard={shard} blocks={blocks}")
+        # every rank brings only ITS query slice (sharded host->device copy)
+        gots = sharded.search(Q[:, lo:hi].contiguous(), BETAS, ALPHAS, labels=labels[lo:hi].contiguous(), want_logits=True,
+                              query_shard=True, blocks=2 if shard == "keys" else None)
+        ok &= compare(gots, refs, f"nq={nq} hard={hard} shard={shard} query_shard")
+
+# temperature-softmax mode: (m, l, O) partials of the key shards merged by log-sum-exp
+for hard in (True, False):
+    banks = orc.synthetic_banks(600, 4000, 256, 50, seed=6, sigma=2.0, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    sm = ClipSearcher(dev, group=dist.group.WORLD, shard="keys")
+    sm.set_text(T.float())
+    sm.set_cache(K, L, softmax_normalize=True, softmax_scale=None if hard else 2.0)
+    got = sm.search(Q, [100.0], [1.0], labels=banks["test_labels"], want_logits=True)[0]
+    V = orc.hard_values(L.float()) if hard else torch.softmax(2.0 * L.float(), dim=1)
+    ref = orc.softmax_attention(Q.float(), K.float(), V, 100.0)
+    e = max((o.cpu() - ref[lo_:hi_]).abs().max().item() for lo_, hi_, _, o, _ in got["pieces"])
+    good = e <= 2e-3
+    ok &= good
+    print(f"rank {rank} softmax mode tau=100 hard={hard}: max-abs vs oracle {e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+
 dist.barrier()
 print(f"rank {rank} SHARDED {'OK' if ok else 'FAIL'}", flush=True)
 dist.destroy_process_group()
