@@ -166,6 +166,17 @@ int sc_hard_bank_layout(const int16_t* labels16, int64_t n_keys, int32_t n_class
                         void* workspace, size_t ws_bytes, void* stream);
 int sc_gather_rows(const void* src, int64_t n_src, int64_t row_bytes, const int64_t* perm, int64_t n_out,
                    void* dst, void* stream);
+/* The one-pass alternative to normalise + sc_gather_rows: inv[k] = sorted position of original key k (-1 if the
+ * layout dropped it), and — when rows != NULL — zero rows at the padding positions of the sorted bank
+ * rows [n_sorted_rows, row_bytes]; sc_normalize_scatter then writes every key's normalised row straight to
+ * dst[dst_row[o]] (dst_row = inv, or inv gathered by the selection idx), so the bank crosses HBM once. */
+int sc_hard_bank_inverse(const int64_t* perm, int64_t n_sorted_rows, int64_t n_keys, int64_t* inv, void* rows,
+                         int64_t row_bytes, void* stream);
+/* sc_normalize_cast with a scattered destination: output o (o < n_out) is written to row dst_row[o] of dst
+ * (skipped when dst_row[o] < 0).  Same sources, types and arithmetic as sc_normalize_cast. */
+int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
+                         const int64_t* idx, int64_t n_out, const int64_t* dst_row, void* dst, int dst_dtype,
+                         int64_t D_pad, int normalize, void* stream);
 
 /* sc_attn_fwd for one-hot cache values on a LABEL-SORTED key bank (same result as sc_attn_fwd on
  * Vt = one_hot(label)^T; the sum over keys does not depend on their order):
@@ -262,6 +273,16 @@ int sc_normalize_split(const void* src, int src_dtype, int64_t D, int64_t N, int
                        int64_t stride_n, void* hi, void* lo, int64_t D_pad, int normalize, void* stream);
 int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
                      int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream);
+
+/* Pseudo-labels WITHOUT the logits bank (save_image_outs.py:25 fused with cache_strategy.py:67-70 / :79-81): the
+ * rows of L = scale * A @ B^T (A = split(normalised image features) [M, D_pad], B = split(T^T) [C, D_pad], as for
+ * sc_gemm_split_nt: fp32-accurate on fp16 tensor cores) are reduced inside the kernel to what sc_rowconf returns,
+ *     label[m] = first argmax_c L[m, c],   conf[m] = max_c L[m, c]  (SC_CONF_RAW)
+ *                                          conf[m] = max_c softmax(prob_scale * L[m, :])  (SC_CONF_PROB),
+ * so that the [M, C] bank (5 GB fp32 at ImageNet scale) is never written or read.  Feed sc_topk_per_class. */
+int sc_rowconf_from_split(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t C,
+                          int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
+                          void* stream);
 
 /* Epilogue (image_attention.py:111-112, clip_searcher/utils.py:15-21, tip_adapter/utils.py:10-15):
  * for every alpha a: out = Z + O * alpha  (O optionally divided by rowsum[q] first), prediction =

@@ -18,6 +18,51 @@ from .. import ops
 from .utils import load_labels
 
 
+class LazyLogitsBank:
+    """Stand-in for the `[N, C]` zero-shot logits bank `image_outs = normalise(K)^T @ T` (save_image_outs.py:25) that
+    is never materialised: the confidence-ranked strategies only need (confidence, label) per
+    row, which the fused GEMM + row-scan kernel produces straight from the features (`ops.rowconf_from_features`);
+    rows of selected keys (cache-quality statistics, soft cache values) are computed on demand for those keys only.
+    Pass it to `select` / `build_cache` wherever the reference passes `image_outs`."""
+
+    def __init__(self, image_features: torch.Tensor, text_features: torch.Tensor) -> None:
+        self.image_features, self.text_features = image_features, text_features      # [D, N], [D, C]
+        self._t_split = ops.text_split(text_features.float().contiguous())
+        self._conf: tp.Dict[tuple, tp.Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    @property
+    def shape(self) -> tp.Tuple[int, int]:
+        return (self.image_features.shape[1], self.text_features.shape[1])
+
+    @property
+    def device(self) -> torch.device:
+        return self.image_features.device
+
+    def rowconf(self, scale: float = 1.0, prob: bool = False) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        key = (float(scale), bool(prob))
+        if key not in self._conf:
+            self._conf[key] = ops.rowconf_from_features(self.image_features, True, self.text_features, prob=prob,
+                                                        prob_scale=scale, t_split=self._t_split)
+        return self._conf[key]
+
+    def __getitem__(self, idx: torch.Tensor) -> torch.Tensor:
+        """L[idx]: fp32 [n_sel, C] logits of the selected keys only."""
+        return ops.zero_shot_logits(self.image_features[:, idx], True, self.text_features, scale=1.0, normalize=True,
+                                    t_split=self._t_split)
+
+    def dense(self, chunk: int = 1 << 16) -> torch.Tensor:
+        """The whole bank after all (strategies that index it by gold label need it): chunked tensor-core GEMM."""
+        n = self.shape[0]
+        return torch.cat([ops.zero_shot_logits(self.image_features[:, s:s + chunk], True, self.text_features, scale=1.0,
+                                               normalize=True, t_split=self._t_split) for s in range(0, n, chunk)])
+
+
+def _rowconf(image_outs, scale: float = 1.0, prob: bool = False):
+    if isinstance(image_outs, LazyLogitsBank):
+        return image_outs.rowconf(scale=scale, prob=prob)
+    return ops.rowconf(image_outs, scale=scale, prob=prob)
+
+
 class CacheStrategy(ABC):
     @abstractmethod
     def transform(self, image_features: torch.Tensor, image_outs: torch.Tensor) \
@@ -48,7 +93,7 @@ class ThresholdStrategy(IndexedCacheStrategy):
         self.use_softmax = use_softmax
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        max_probs, _ = ops.rowconf(image_outs, scale=1.0, prob=self.use_softmax)
+        max_probs, _ = _rowconf(image_outs, scale=1.0, prob=self.use_softmax)
         confidence_mask = (max_probs >= self.threshold)
         return confidence_mask.nonzero().squeeze(1)
 
@@ -67,7 +112,7 @@ class TopKStrategy(IndexedCacheStrategy):
         self.topk = topk
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        image_logits, label_preds = ops.rowconf(image_outs, prob=False)
+        image_logits, label_preds = _rowconf(image_outs, prob=False)
         return select_topk_per_label(label_preds, image_logits, self.topk, image_outs.shape[1])
 
 
@@ -80,7 +125,7 @@ class TopKProbStrategy(IndexedCacheStrategy):
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
         # softmax(image_outs * scale) never materialised: its row max is 1 / sum_c exp(scale (l_c - l_max))
-        image_probs, label_preds = ops.rowconf(image_outs, scale=self.scale, prob=True)
+        image_probs, label_preds = _rowconf(image_outs, scale=self.scale, prob=True)
         return select_topk_per_label(label_preds, image_probs, self.topk, image_outs.shape[1])
 
 
@@ -91,6 +136,8 @@ class TopKPerGoldStrategy(IndexedCacheStrategy):
         self.cache_labels = cache_labels if cache_labels is not None else load_labels(cache_dataset)
 
     def _gold_logits(self, image_outs: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        if isinstance(image_outs, LazyLogitsBank):
+            image_outs = image_outs.dense()
         cache_labels = self.cache_labels.to(image_outs.device)
         labels_indexes = cache_labels.long().unsqueeze(dim=0).t()
         return cache_labels, image_outs.gather(1, labels_indexes).squeeze(dim=1).float()
@@ -109,6 +156,8 @@ class TopKPerGoldProbStrategy(IndexedCacheStrategy):
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
         # softmax(scale * l)[gold] = exp(scale * l_gold - scale * l_max) * max-prob, from two row scans
+        if isinstance(image_outs, LazyLogitsBank):
+            image_outs = image_outs.dense()
         max_prob, _ = ops.rowconf(image_outs, scale=self.scale, prob=True)
         max_raw, _ = ops.rowconf(image_outs, prob=False)
         cache_labels, gold_raw = self.topk_strategy._gold_logits(image_outs)
@@ -156,5 +205,5 @@ class PerPredClassRandomSampleStrategy(IndexedCacheStrategy):
         self.topk = topk
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        _, label_preds = ops.rowconf(image_outs, prob=False)
+        _, label_preds = _rowconf(image_outs, prob=False)
         return select_k_random_per_label(label_preds, self.topk)

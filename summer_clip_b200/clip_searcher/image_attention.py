@@ -26,7 +26,7 @@ from ..searcher import ClipSearcher
 from ..utils import hydra_utils
 from ..utils.config import Config, compose
 from ..utils.log_utils import JsonLinesLogger
-from .cache_strategy import CacheStrategy, IndexedCacheStrategy
+from .cache_strategy import CacheStrategy, IndexedCacheStrategy, LazyLogitsBank
 from .cache_value_strategy import GoldCacheValues, HardCacheStrategy, SoftmaxCacheStrategy
 from .cache_weights_strategy import FusedWeights, NormalizedBank
 from .utils import TensorsNumpySaver, compute_accuracy
@@ -77,13 +77,22 @@ class ImageAttention:
     def setup_model(self) -> None:
         self.searcher = ClipSearcher(self.device)
         self.test_image_features = _load_tensor(self.cfg.data.image_features_path, self.device)
+        text = None
         if self.cfg.data.get("clip_logits_path"):
             self.clip_logits = _load_tensor(self.cfg.data.clip_logits_path, self.device).float().contiguous()
         else:
-            self.clip_logits = self.compute_clip_logits(_load_tensor(self.cfg.data.text_features_path, self.device))
+            text = _load_tensor(self.cfg.data.text_features_path, self.device)
+            self.clip_logits = self.compute_clip_logits(text)
         self.test_q_norm = ops.normalize_cast(self.test_image_features, feature_major=True)
         self.origin_cache_image_features = _load_tensor(self.cfg.cache.image_features_path, self.device)
-        self.origin_cache_image_outs = _load_tensor(self.cfg.cache.image_outs_path, self.device)
+        if self.cfg.cache.get("image_outs_path"):
+            self.origin_cache_image_outs = _load_tensor(self.cfg.cache.image_outs_path, self.device)
+        else:
+            # no stored logits bank (cache.image_outs_path: null): pseudo-labels come straight from the features and
+            # the text classifier through the fused GEMM + row-scan kernel; the [N, C] bank is never written
+            if text is None:
+                text = _load_tensor(self.cfg.data.text_features_path, self.device)
+            self.origin_cache_image_outs = LazyLogitsBank(self.origin_cache_image_features, text)
         self.logger.log_info(f"original-data-size: {self.origin_cache_image_outs.shape[0]}")
 
     def setup(self) -> None:
@@ -138,6 +147,8 @@ class ImageAttention:
         n_q = self.test_labels.shape[0]
         q_bank = NormalizedBank(self.test_q_norm)
         for cache_strategy_cfg in self.cfg.cache_strategies.values():
+            if cache_strategy_cfg is None:            # a group switched off on the command line (`...group=null`)
+                continue
             for cache_strategy, cache_strategy_params in hydra_utils.instantiate_all(
                     cache_strategy_cfg, inject=self._strategy_inject(cache_strategy_cfg)):
                 k_bank, (outs, idx, gold), cache_info = self.build_cache(
@@ -150,6 +161,12 @@ class ImageAttention:
                 for vi, (value_strategy, value_params) in enumerate(values_grid):
                     if gold is not None:
                         value_cache[vi] = self._gold_values(value_strategy, gold, outs.shape[1])
+                    elif isinstance(outs, LazyLogitsBank):
+                        if isinstance(value_strategy, HardCacheStrategy):       # argmax labels from the fused row scan
+                            pred = outs.rowconf()[1]
+                            value_cache[vi] = GoldCacheValues(outs.shape[1]).transform(pred if idx is None else pred[idx])
+                        else:
+                            value_cache[vi] = value_strategy.transform(outs.dense() if idx is None else outs[idx])
                     elif isinstance(value_strategy, (HardCacheStrategy, SoftmaxCacheStrategy)):
                         value_cache[vi] = value_strategy.transform(outs, idx=idx)
                     else:

@@ -60,6 +60,10 @@ struct SParams {
   long long ldz;
   int n_cols;                // valid columns of Z (rows of B)
   float scale;
+  // kRowConf: per-row confidence / label of scale * S (sc_rowconf_from_features)
+  float* conf;
+  int* label;
+  int conf_prob;             // 0: conf = row max; 1: conf = max softmax(prob_scale * row) = 1 / sum exp2(c1[0] (v - max))
 };
 
 struct Bars {
@@ -94,6 +98,8 @@ enum : int {
   kSoftmax = 2,   // temperature softmax over the keys with a RUNNING ROW MAXIMUM: per class the
                   // log2-sum-exp of tau * S over its keys (the (m, l) pair in one float)            -> LSE[q, class]
   kRowMax = 3,    // max_k S[q, k] over the valid keys (pre-pass of the dense-values softmax mode)   -> rowmax[q]
+  kRowConf = 4,   // split-fp16 GEMM (3 operand passes, as kGemmOut) whose rows are reduced on the fly to
+                  // (confidence, first argmax): pseudo-labels without writing the logits bank        -> conf[m], label[m]
 };
 
 // kGemm = false: the attention kernel described above.  kGemm = true: the same TMA ring / pair-UMMA / TMEM
@@ -127,7 +133,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int nd = p.n_dchunks;
   constexpr bool kF8 = (kOp == SC_E4M3);
   constexpr int kChunkElems = kF8 ? 2 * kBK : kBK;      // elements in a 128-byte operand row
-  constexpr bool kGemm = (kKind == kGemmOut);
+  constexpr bool kGemm = (kKind == kGemmOut || kKind == kRowConf);      // split-fp16 operands, 3 passes per S tile
   constexpr int kPasses = kGemm ? 3 : 1;      // operand passes accumulated into one S tile
 
 #ifdef SC_ATTN_TIMING_EXPERIMENTS
@@ -240,7 +246,60 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ===================================================== exp + segmented sum warps: thread = query
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    if constexpr (kGemm) {
+    if constexpr (kKind == kRowConf) {
+      // ---- logits never leave the SM: thread = image row; running first-argmax over the class columns (strictly
+      // greater replaces, so equal values keep the smaller class like torch.max) and, for the softmax confidence,
+      // an online sum of exp2(c1 (v - running max)) rescaled whenever the maximum grows
+      const int qg = q0 + row;
+      float best = -INFINITY, m_run = -1e30f, acc = 0.f;
+      int bidx = 0;
+      const float c1 = p.c1[0];
+#pragma unroll 1
+      for (int st = 0; st < nsteps; ++st) {
+        const int b = st & 1;
+        mbar_wait(smem_u32(&bars->s_full[b]), (st >> 1) & 1);
+        tc_fence_after();
+        const int n0 = (s0 + st) * kStepKeys;
+#pragma unroll 1
+        for (int cc = 0; cc < kStepKeys / 32; ++cc) {
+          const int nb = n0 + cc * 32;
+          if (nb >= p.n_cols) break;
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + lane_addr + b * 256 + cc * 32, rg);
+          tmem_ld_wait();
+          const int nvalid = min(32, p.n_cols - nb);
+          float cm = -1e30f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = (j < nvalid) ? __uint_as_float(rg[j]) * p.scale : -INFINITY;
+            if (v > best) { best = v; bidx = nb + j; }
+            cm = fmaxf(cm, v);
+          }
+          if (p.conf_prob) {
+            const float mn = fmaxf(m_run, cm);
+            acc *= ex2_approx(c1 * (m_run - mn));
+            m_run = mn;
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = ex2_approx(c1 * (__uint_as_float(rg[j]) * p.scale - mn));
+              sacc += (j < nvalid) ? e : 0.f;
+            }
+            acc += sacc;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
+          else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), 0);
+        }
+      }
+      if (qg < p.Nq) {
+        p.conf[qg] = p.conf_prob ? 1.0f / acc : best;
+        p.label[qg] = bidx;
+      }
+    } else if constexpr (kGemm) {
       // ---- GEMM mode: Z[q, n] = scale * S[q, n]; thread = output row, 32 consecutive columns per TMEM load
       const int qg = q0 + row;
       float* zrow = p.Z + static_cast<long long>(qg) * p.ldz;
@@ -617,7 +676,7 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
     if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
     if ((rc = make_tmap(&tmK, Ks, Nks, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;    // 128 keys x 64 d
   }
-  SParams p;
+  SParams p = {};
   p.Nq = static_cast<int>(Nq);
   p.n_dchunks = static_cast<int>(D_pad / (f8 ? 2 * kBK : kBK));
   // e4m3 operands are stored as SC_E4M3_SCALE * x: S comes back scaled by its square
@@ -684,6 +743,44 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   return rc2;
 }
 
+// (conf, label) per row of scale * A @ B^T for split-fp16 operands, the logits never written: the kGemmOut pipeline
+// with ALL column steps of a row tile in one work item and the row reduction in the consumer warps.
+int rowconf_fused_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
+                         const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                         int64_t D_pad, float scale, float prob_scale, int prob, float* conf, int* label, cudaStream_t st) {
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  int rc;
+  if ((rc = make_tmap(&tmA, Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmA2, Al, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmB, Bh, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmB2, Bl, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
+  SParams p = {};
+  p.Nq = static_cast<int>(M);
+  p.n_dchunks = static_cast<int>(D_pad / kBK);
+  p.steps_total = static_cast<int>(ceil_div(N, kStepKeys));
+  p.splits = 1;
+  for (int bi = 0; bi < 4; ++bi) p.c1[bi] = p.c0[bi] = 0.f;
+  p.c1[0] = prob_scale * 1.4426950408889634f;
+  p.o_beta_stride = 0;
+  p.gcls = nullptr;
+  p.kbits = nullptr;
+  p.O = nullptr;
+  p.ldo = 0;
+  p.dbg = 0;
+  p.clk = nullptr;
+  p.pf_dist = 0;
+  p.Z = nullptr;
+  p.ldz = 0;
+  p.n_cols = static_cast<int>(N);
+  p.scale = scale;
+  p.conf = conf;
+  p.label = label;
+  p.conf_prob = prob;
+  dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), 1u);
+  SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_rowconf_from_split: too many row tiles; chunk the rows");
+  return launch_seg<SC_F16, kRowConf, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
+}
+
 // rowmax[q] = max over the Nk keys of Qn[q].Kn[k] (any key order; rows past Nk are never counted): GEMM-1 of the
 // attention kernel with a max instead of the exponential sum.  Pre-pass of the dense-values softmax mode, which
 // needs the exact row maximum before it rounds weights to 16 bits (sc_attn_fwd_shifted).
@@ -701,7 +798,7 @@ int attn_rowmax_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int6
     if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;
     if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;
   }
-  SParams p;
+  SParams p = {};
   p.Nq = static_cast<int>(Nq);
   p.n_dchunks = static_cast<int>(D_pad / (f8 ? 2 * kBK : kBK));
   p.steps_total = static_cast<int>(ceil_div(Nk, kStepKeys));
@@ -738,7 +835,7 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   if ((rc = make_tmap(&tmA2, Al, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
   if ((rc = make_tmap(&tmB, Bh, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
   if ((rc = make_tmap(&tmB2, Bl, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
-  SParams p;
+  SParams p = {};
   p.Nq = static_cast<int>(M);
   p.n_dchunks = static_cast<int>(D_pad / kBK);
   p.steps_total = static_cast<int>(ceil_div(N, kStepKeys));

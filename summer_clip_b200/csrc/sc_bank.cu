@@ -148,6 +148,24 @@ gather_rows_kernel(const uint4* __restrict__ src, int64_t n_src, const int64_t* 
   }
 }
 
+// inverse of the bank permutation (original key -> sorted position; -1 for keys the layout dropped) and zero rows
+// for the padding positions of the sorted bank: what a normalise pass needs to write each key's row straight to its
+// sorted place (sc_normalize_scatter), instead of a second pass over the bank (sc_gather_rows).
+__global__ void __launch_bounds__(256)
+bank_inverse_kernel(const int64_t* __restrict__ perm, int64_t n_sorted_rows, int64_t n_keys, int64_t* __restrict__ inv,
+                    uint4* __restrict__ rows, int64_t row_vecs) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); j < n_sorted_rows; j += warps) {
+    const int64_t k = perm[j];
+    if (k >= 0) {
+      if (lane == 0 && k < n_keys) inv[k] = j;
+    } else if (rows != nullptr) {
+      for (int64_t v = lane; v < row_vecs; v += 32) rows[j * row_vecs + v] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -182,6 +200,23 @@ int sc_hard_bank_layout(const int16_t* labels16, int64_t n_keys, int32_t n_class
     bank_scatter_kernel<<<static_cast<unsigned>(n_chunks), 32, 0, st>>>(labels16, n_keys, n_classes, w.counts, w.seg_start,
                                                                         perm, group_class);
   bank_bits_kernel<<<static_cast<unsigned>(sc::ceil_div(capacity / 32, 256)), 256, 0, st>>>(perm, capacity / 32, key_bits);
+  SC_CUDA(cudaGetLastError());
+  return SC_OK;
+}
+
+int sc_hard_bank_inverse(const int64_t* perm, int64_t n_sorted_rows, int64_t n_keys, int64_t* inv, void* rows,
+                         int64_t row_bytes, void* stream) {
+  SC_REQUIRE(perm && inv, SC_EINVAL, "sc_hard_bank_inverse: null pointer");
+  SC_REQUIRE(n_sorted_rows >= 0 && n_keys >= 0 && (rows == nullptr || (row_bytes > 0 && row_bytes % 16 == 0)), SC_ESHAPE,
+             "sc_hard_bank_inverse: bad shape");
+  SC_REQUIRE(reinterpret_cast<uintptr_t>(rows) % 16 == 0, SC_EALIGN, "sc_hard_bank_inverse: rows must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_keys > 0) SC_CUDA(cudaMemsetAsync(inv, 0xff, static_cast<size_t>(n_keys) * sizeof(int64_t), st));     // -1: dropped
+  if (n_sorted_rows == 0) return SC_OK;
+  const int64_t want = sc::ceil_div(n_sorted_rows, 8);
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+  bank_inverse_kernel<<<blocks, 256, 0, st>>>(perm, n_sorted_rows, n_keys, inv, static_cast<uint4*>(rows),
+                                              rows ? row_bytes / 16 : 0);
   SC_CUDA(cudaGetLastError());
   return SC_OK;
 }

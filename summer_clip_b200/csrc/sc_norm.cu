@@ -15,7 +15,7 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d,
                       int64_t stride_n, const int64_t* __restrict__ idx, int64_t n_out,
-                      TO* __restrict__ dst, int64_t D_pad, int normalize) {
+                      TO* __restrict__ dst, int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
   __shared__ float tile[64][33];
   __shared__ float red[8][32];
   __shared__ float inv_norm[32];
@@ -72,8 +72,9 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
       const int r = ty + 8 * j;            // strip column -> output row
       const int64_t o = n0 + r;
       if (o < n_out) {
+        const int64_t orow = dst_row ? dst_row[o] : o;      // scattered output (the label-sorted bank); < 0 = dropped
         const int d = 2 * tx;
-        sc::store2<TO>(dst + o * D_pad + d0 + d, tile[d][r], tile[d + 1][r]);
+        if (orow >= 0) sc::store2<TO>(dst + orow * D_pad + d0 + d, tile[d][r], tile[d + 1][r]);
       }
     }
     __syncthreads();
@@ -90,7 +91,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
 template <typename T, typename TO>
 __global__ void __launch_bounds__(512)
 norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d, TO* __restrict__ dst,
-                  int64_t D_pad, int normalize) {
+                  int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
   extern __shared__ uint16_t strip[];            // [32 columns][pitch]: column-major, pitch = D_even + 2 halves
   __shared__ float red[16][32];
   __shared__ float inv_s[32];
@@ -135,8 +136,10 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
   // phase B: warp w writes the output rows of columns w and w + 16; lane handles the pair d = d0 + 2 lane, +1
   // (one 4-byte shared load, one 4-byte global store: 128 contiguous bytes per warp)
   for (int c = warp; c < 32; c += 16) {
-    const int64_t o = n0 + c;
+    int64_t o = n0 + c;
     if (o >= N) continue;
+    if (dst_row != nullptr) o = dst_row[o];      // scattered output (the label-sorted bank); < 0 = dropped key
+    if (o < 0) continue;
     const float inv = inv_s[c];
     const uint32_t* col32 = reinterpret_cast<const uint32_t*>(strip + c * pitch);
     TO* orow = dst + o * D_pad;
@@ -156,11 +159,11 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
 
 template <typename T, typename TO>
 int launch_norm_strip(const void* src, int64_t D, int64_t N, int64_t stride_d, void* dst, int64_t D_pad, int normalize,
-                      cudaStream_t st) {
+                      const int64_t* dst_row, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(32) * ((D + 1) / 2 * 2 + 2) * 2;
   SC_CUDA(cudaFuncSetAttribute(norm_strip_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   norm_strip_kernel<T, TO><<<static_cast<unsigned>(sc::ceil_div(N, 32)), 512, smem, st>>>(
-      static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize);
+      static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize, dst_row);
   return SC_OK;
 }
 
@@ -169,11 +172,13 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_n,
                  const int64_t* __restrict__ idx, int64_t n_out, TO* __restrict__ dst,
-                 int64_t D_pad, int normalize) {
+                 int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
   const int lane = threadIdx.x & 31;
-  const int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (o >= n_out) return;
   const int64_t n = idx ? idx[o] : o;
+  if (dst_row != nullptr) o = dst_row[o];
+  if (o < 0) return;
   const bool ok = (n >= 0 && n < N);
   const T* row = src + (ok ? n : 0) * stride_n;
   float nrm = 1.f;
@@ -347,10 +352,9 @@ extern "C" int sc_normalize_split(const void* src, int src_dtype, int64_t D, int
   return SC_OK;
 }
 
-extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N,
-                                 int64_t stride_d, int64_t stride_n, const int64_t* idx,
-                                 int64_t n_out, void* dst, int dst_dtype, int64_t D_pad,
-                                 int normalize, void* stream) {
+static int normalize_impl(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
+                          const int64_t* idx, int64_t n_out, void* dst, int dst_dtype, int64_t D_pad, int normalize,
+                          const int64_t* dst_row, void* stream) {
   SC_REQUIRE(src && dst, SC_EINVAL, "sc_normalize_cast: null pointer");
   SC_REQUIRE(D > 0 && N >= 0 && n_out >= 0, SC_ESHAPE, "sc_normalize_cast: bad shape");
   SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE,
@@ -365,8 +369,8 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
       static_cast<size_t>(D) * 33 * 2 <= 200 * 1024) {
     int rc = SC_OK;
     SC_DISPATCH_OP8(dst_dtype, TO, {
-      if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
-      else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, st);
+      if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, st);
+      else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, st);
     });
     if (rc != SC_OK) return rc;
   } else if (stride_d == 1 && stride_n != 1) {
@@ -375,7 +379,7 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_rows_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_n, idx, n_out,
-                            static_cast<TO*>(dst), D_pad, normalize)));
+                            static_cast<TO*>(dst), D_pad, normalize, dst_row)));
     });
   } else {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
@@ -383,11 +387,27 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_transpose_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,
-                            static_cast<TO*>(dst), D_pad, normalize)));
+                            static_cast<TO*>(dst), D_pad, normalize, dst_row)));
     });
   }
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int64_t N,
+                                 int64_t stride_d, int64_t stride_n, const int64_t* idx,
+                                 int64_t n_out, void* dst, int dst_dtype, int64_t D_pad,
+                                 int normalize, void* stream) {
+  return normalize_impl(src, src_dtype, D, N, stride_d, stride_n, idx, n_out, dst, dst_dtype, D_pad, normalize, nullptr,
+                        stream);
+}
+
+extern "C" int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
+                                    int64_t stride_n, const int64_t* idx, int64_t n_out, const int64_t* dst_row,
+                                    void* dst, int dst_dtype, int64_t D_pad, int normalize, void* stream) {
+  SC_REQUIRE(dst_row != nullptr, SC_EINVAL, "sc_normalize_scatter: null dst_row");
+  return normalize_impl(src, src_dtype, D, N, stride_d, stride_n, idx, n_out, dst, dst_dtype, D_pad, normalize, dst_row,
+                        stream);
 }
 
 extern "C" int sc_mean_normalize_rows(const void* src, int dtype, int64_t E, int64_t N, int64_t D, int64_t stride_e,

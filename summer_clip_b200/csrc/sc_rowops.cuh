@@ -2,6 +2,8 @@
 #pragma once
 #include "sc_common.cuh"
 
+#include <type_traits>
+
 namespace sc {
 
 // value/index pair ordered like torch.max(dim=1): larger value wins, NaN is largest, and among
@@ -35,6 +37,33 @@ __device__ __forceinline__ float max_nan(float a, float b) {
   return d;
 }
 
+// exp(t) for t <= 0 as one multiply and one MUFU: ex2.approx(t * log2(e)).  Against expf this differs by ~1e-7
+// relative on the terms that matter (|t| < 1), far inside the 2e-6 the selection goldens allow, and costs 2
+// instructions instead of ~8 — the PROB row scan was bound by them, not by HBM.
+__device__ __forceinline__ float exp_neg_fast(float t) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t * 1.4426950408889634f));
+  return y;
+}
+
+// packed max of two 16-bit pairs that PROPAGATES NaN (one instruction per two elements)
+template <typename T>
+__device__ __forceinline__ uint32_t max_nan_x2(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t max_nan_x2<__half>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <>
+__device__ __forceinline__ uint32_t max_nan_x2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <>
+__device__ __forceinline__ uint32_t max_nan_x2<float>(uint32_t a, uint32_t) { return a; }   // never used
+
 // Register-resident row of at most 32 * NV 16-byte vectors (one warp per row).  load(): every lane issues all
 // of its 16-byte loads before the first use.  argmax(): two cheap passes over the fp32 copy in registers —
 // max.NaN for the value (1 instruction per element), then "last hit in reverse order" for the FIRST index at
@@ -64,12 +93,28 @@ struct RegRow {
 
   __device__ __forceinline__ MaxIdx argmax() const {
     float mx = __int_as_float(0xff800000);   // -inf
+    if constexpr (sizeof(T) == 2) {
+      // 16-bit storage: the maximum is exact in the storage type, so take it pairwise there (0.5 instructions per
+      // element); -inf in both halves is the identity (absent vectors were loaded as zeros: skip them)
+      uint32_t m2 = std::is_same<T, __half>::value ? 0xfc00fc00u : 0xff80ff80u;        // a pair of -inf (fp16 / bf16)
 #pragma unroll
-    for (int u = 0; u < NV; ++u)
-      if (has(u)) {
+      for (int u = 0; u < NV; ++u)
+        if (has(u)) {
+          m2 = max_nan_x2<T>(m2, v[u].x);
+          m2 = max_nan_x2<T>(m2, v[u].y);
+          m2 = max_nan_x2<T>(m2, v[u].z);
+          m2 = max_nan_x2<T>(m2, v[u].w);
+        }
+      const T* pair = reinterpret_cast<const T*>(&m2);
+      mx = max_nan(to_f32<T>(pair[0]), to_f32<T>(pair[1]));
+    } else {
 #pragma unroll
-        for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
-      }
+      for (int u = 0; u < NV; ++u)
+        if (has(u)) {
+#pragma unroll
+          for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (mx != mx) {                           // a NaN in the row (warp-uniform): exact ordered compare
@@ -103,7 +148,7 @@ struct RegRow {
     for (int u = 0; u < NV; ++u)
       if (has(u)) {
 #pragma unroll
-        for (int t = 0; t < kN; ++t) s += expf(__fmul_rn(x(u, t), scale) - tmax);
+        for (int t = 0; t < kN; ++t) s += exp_neg_fast(__fmul_rn(x(u, t), scale) - tmax);
       }
     return warp_sum(s);
   }
@@ -159,13 +204,13 @@ __device__ __forceinline__ float row_expsum(const T* __restrict__ row, int64_t C
       uint4 raw = __ldg(vrow + j);
       const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-      for (int t = 0; t < kN; ++t) s += expf(__fmul_rn(to_f32<T>(e[t]), scale) - tmax);
+      for (int t = 0; t < kN; ++t) s += exp_neg_fast(__fmul_rn(to_f32<T>(e[t]), scale) - tmax);
     }
     for (int64_t c = nv * kN + lane; c < C; c += 32)
-      s += expf(__fmul_rn(to_f32<T>(row[c]), scale) - tmax);
+      s += exp_neg_fast(__fmul_rn(to_f32<T>(row[c]), scale) - tmax);
   } else {
     for (int64_t c = lane; c < C; c += 32)
-      s += expf(__fmul_rn(to_f32<T>(row[c]), scale) - tmax);
+      s += exp_neg_fast(__fmul_rn(to_f32<T>(row[c]), scale) - tmax);
   }
   return warp_sum(s);
 }

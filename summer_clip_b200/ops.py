@@ -133,6 +133,28 @@ def rowconf(L: torch.Tensor, scale: float = 1.0, prob: bool = False) -> Tuple[to
     return conf, label
 
 
+def rowconf_from_features(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scale: float = 1.0,
+                          prob: bool = False, prob_scale: float = 1.0,
+                          t_split: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`rowconf(scale * normalise(X)^T @ T, scale=prob_scale, prob=prob)` without materialising the logits bank:
+    (confidence fp32 [N], predicted label int32 [N]) straight from the image features X ([D, N] if feature_major)
+    and the text classifier T [D, C] — save_image_outs.py:25 fused with TopK[Prob]Strategy's row scan."""
+    _cuda(X, "X"), _cuda(T, "T")
+    xh, xl = normalize_split(X, feature_major, normalize=True)
+    th, tl = t_split if t_split is not None else text_split(T)
+    N, D_pad = xh.shape
+    C = th.shape[0]
+    conf = torch.empty(N, dtype=torch.float32, device=X.device)
+    label = torch.empty(N, dtype=torch.int32, device=X.device)
+    if N == 0:
+        return conf, label
+    with torch.cuda.device(X.device):
+        check(_lib.load().sc_rowconf_from_split(_ptr(xh), _ptr(xl), _ptr(th), _ptr(tl), N, C, D_pad, float(scale),
+                                                float(prob_scale), SC_CONF_PROB if prob else SC_CONF_RAW, _ptr(conf),
+                                                _ptr(label), _stream()), "sc_rowconf_from_split")
+    return conf, label
+
+
 def topk_per_class(conf: torch.Tensor, label: torch.Tensor, n_classes: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(int64 [C, k] row indices, most confident first, -1 padded; int32 [C] counts)."""
     _cuda(conf, "conf"), _cuda(label, "label")
@@ -256,6 +278,44 @@ class HardBank:
                                              _ptr(self.perm), n_out, _ptr(rows), _stream()), "sc_gather_rows")
         self.rows = rows
         return self
+
+
+def hard_bank_build(labels: torch.Tensor, n_classes: int, feats: torch.Tensor, feature_major: bool,
+                    idx: Optional[torch.Tensor] = None, normalize: bool = True,
+                    op_dtype: Optional[torch.dtype] = None) -> HardBank:
+    """The label-sorted bank straight from the RAW feature bank in one pass over it: layout from the labels, then
+    every selected key's normalised row is written directly to its sorted position (sc_hard_bank_inverse +
+    sc_normalize_scatter) — no intermediate normalised bank and no gather pass (normalize_cast + HardBank.gather
+    move the bank through HBM twice).  `labels`: one per selected key (int16 from hard_labels, or any int type);
+    `idx`: the selected columns / rows of `feats` (None = all)."""
+    _cuda(feats, "feats")
+    bank = hard_bank_layout(labels, n_classes)
+    n_keys = bank.n_keys
+    if feature_major:
+        D, N = feats.shape
+        stride_d, stride_n = feats.stride()
+    else:
+        N, D = feats.shape
+        stride_n, stride_d = feats.stride()
+    if idx is not None:
+        idx = _cuda(idx, "idx").to(torch.int64).contiguous()
+        assert idx.numel() == n_keys
+    else:
+        assert N == n_keys
+    op_dtype = _op(op_dtype, allow_e4m3=True)
+    D_pad = pad_dim(D, op_dtype)
+    n_rows = bank.perm.numel()
+    rows = torch.empty((n_rows, D_pad), dtype=op_dtype, device=feats.device)
+    inv = torch.empty(max(n_keys, 1), dtype=torch.int64, device=feats.device)
+    lib = _lib.load()
+    with torch.cuda.device(feats.device):
+        check(lib.sc_hard_bank_inverse(_ptr(bank.perm), n_rows, n_keys, _ptr(inv), _ptr(rows), D_pad * rows.element_size(),
+                                       _stream()), "sc_hard_bank_inverse")
+        if n_keys > 0:
+            check(lib.sc_normalize_scatter(_ptr(feats), _code(feats), D, N, stride_d, stride_n, _ptr(idx), n_keys, _ptr(inv),
+                                           _ptr(rows), _code(rows), D_pad, int(normalize), _stream()), "sc_normalize_scatter")
+    bank.rows = rows
+    return bank
 
 
 def hard_bank_layout(labels: torch.Tensor, n_classes: int) -> HardBank:

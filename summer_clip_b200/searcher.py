@@ -174,18 +174,19 @@ class ClipSearcher:
         self.rowsum_col = self.n_classes if (softmax_normalize and not hard) else None
         if self.n_keys == 0:
             return
-        self.k_norm = ops.normalize_cast(feats, feature_major=feature_major, idx=local_idx, op_dtype=self.op_dtype)
-        self.gpu_launches += 1
         local_labels = labels.to(self.device)[lo:hi].contiguous() if labels is not None else None
         if hard:
             # one-hot values: W @ V is a per-class segmented row sum; sort the keys by label once and let the
-            # kernel sum the exponentials per class straight out of tensor memory (sc_attn_fwd_hard)
+            # kernel sum the exponentials per class straight out of tensor memory (sc_attn_fwd_hard).  The bank is
+            # built in ONE pass over the raw features: labels -> layout -> normalised rows written to sorted places.
             labels16 = ops.hard_labels(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
                                        labels=local_labels)
-            self.hard_bank = ops.hard_bank_layout(labels16[: self.n_keys], self.n_classes).gather(self.k_norm)
-            self.k_norm = None
-            self.gpu_launches += 1
+            self.hard_bank = ops.hard_bank_build(labels16[: self.n_keys], self.n_classes, feats, feature_major,
+                                                 idx=local_idx, op_dtype=self.op_dtype)
+            self.gpu_launches += 6
             return
+        self.k_norm = ops.normalize_cast(feats, feature_major=feature_major, idx=local_idx, op_dtype=self.op_dtype)
+        self.gpu_launches += 1
         self.vt = ops.values_prepare(outs, self.n_classes, idx=None if local_labels is not None else local_idx,
                                      labels=local_labels, softmax_scale=softmax_scale, ones_row=softmax_normalize,
                                      op_dtype=self.op_dtype)

@@ -427,3 +427,70 @@ def test_headline_launch_is_bitwise_repeatable(ops):
     first = ops.attn_fwd(Qn[:512].contiguous(), Kn, Vt, nk, c, 5.5, splits=2, merge=False).clone()
     for _ in range(9):
         assert torch.equal(ops.attn_fwd(Qn[:512].contiguous(), Kn, Vt, nk, c, 5.5, splits=2, merge=False), first)
+
+
+def test_one_pass_sorted_bank_build_equals_normalise_then_gather(ops):
+    """ops.hard_bank_build (layout -> inverse permutation -> normalised rows scattered to their sorted places, one
+    pass over the raw bank) == normalize_cast + hard_bank_layout + gather, bit for bit, for every source layout the
+    normalise kernels have (16-bit feature-major strip kernel, fp32 transpose kernel, row-major, with a gather)."""
+    g = torch.Generator().manual_seed(11)
+    for dtype, fm, n, d, use_idx in ((torch.float16, True, 3001, 1024, False), (torch.float32, True, 777, 96, False),
+                                     (torch.float16, False, 900, 128, False), (torch.float16, True, 2000, 256, True),
+                                     (torch.bfloat16, True, 65, 64, False)):
+        x = torch.randn((d, n) if fm else (n, d), generator=g).to(dtype).cuda()
+        idx = torch.randperm(n, generator=g)[: n // 2].cuda() if use_idx else None
+        nk = idx.numel() if use_idx else n
+        labels = torch.randint(-1, 38, (nk,), generator=g).int().cuda()            # -1 and 37 are dropped keys
+        want = ops.hard_bank_layout(labels, 37).gather(ops.normalize_cast(x, fm, idx=idx))
+        got = ops.hard_bank_build(labels, 37, x, fm, idx=idx)
+        assert got.n_sorted == want.n_sorted and torch.equal(got.perm, want.perm) and torch.equal(got.gcls, want.gcls)
+        assert torch.equal(got.rows.view(torch.int16), want.rows.view(torch.int16)), (dtype, fm, n, d, use_idx)
+
+
+def test_pseudo_labels_without_the_logits_bank(ops, golden_dir, tmp_path):
+    """(confidence, label) straight from features + text classifier (sc_rowconf_from_split: the
+    split-fp16 GEMM with the row scan in its consumer warps; L is never written) == the row scan of the stored bank,
+    and the selected indices equal the REFERENCE's TopKProbStrategy output on the golden banks, bit for bit."""
+    from summer_clip_b200.clip_searcher.cache_strategy import LazyLogitsBank, TopKProbStrategy, TopKStrategy
+    att = np.load(golden_dir / "image_attention.npz")
+    K, T, L = (torch.from_numpy(att[n]).cuda() for n in ("cache_image_features", "text_features", "cache_image_outs"))
+    lazy = LazyLogitsBank(K, T)
+    conf, label = lazy.rowconf()
+    conf_ref, label_ref = ops.rowconf(L)
+    assert torch.equal(label, label_ref)
+    torch.testing.assert_close(conf, conf_ref, rtol=0, atol=5e-7)
+    conf_p, label_p = lazy.rowconf(scale=orc.CLIP_SCALE, prob=True)
+    conf_p_ref, _ = ops.rowconf(L, scale=orc.CLIP_SCALE, prob=True)
+    assert torch.equal(label_p, label_ref)
+    torch.testing.assert_close(conf_p, conf_p_ref, rtol=2e-4, atol=0)          # exp(100 * 5e-7) - 1 = 5e-5 per term
+    idx = TopKProbStrategy(4, orc.CLIP_SCALE).select(K, lazy)
+    assert np.array_equal(idx.cpu().numpy(), att["cache_idx"])
+    assert np.array_equal(TopKStrategy(4).select(K, lazy).cpu().numpy(), TopKStrategy(4).select(K, L).cpu().numpy())
+    torch.testing.assert_close(lazy[idx], L[idx], rtol=0, atol=5e-7)
+    # ragged larger shape: 1000 classes (4 column steps), rows not a multiple of the 256-row tile, fp16 features
+    g = torch.Generator().manual_seed(12)
+    banks = orc.synthetic_banks(8, 3001, 512, 1000, seed=12, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    Kb, Tb = banks["cache_image_features"].cuda(), banks["text_features"].cuda()
+    conf, label = ops.rowconf_from_features(Kb, True, Tb)
+    Lb = orc.normalize_columns(banks["cache_image_features"].float()).t() @ banks["text_features"].float()
+    ref_conf, ref_label = Lb.max(dim=1)
+    torch.testing.assert_close(conf.cpu(), ref_conf, rtol=0, atol=1e-6)
+    agree = (label.cpu() == ref_label).float().mean().item()
+    assert agree >= 0.999, agree                                               # a flipped label needs a top-2 gap < 1e-6
+    # the sweep driver with cache.image_outs_path = null: same records as with the stored bank
+    from summer_clip_b200.clip_searcher.image_attention import run
+    small = orc.synthetic_banks(300, 2000, 128, 30, seed=53, sigma=0.5, sigma_text=0.8, shared=3.0)
+    p = _write_banks(tmp_path, small)
+    accs = {}
+    for mode in ("stored", "lazy"):
+        over = [f"data.image_features_path={p['test_image_features']}", f"data.text_features_path={p['text_features']}",
+                f"data.labels_path={p['test_labels']}", f"cache.image_features_path={p['cache_image_features']}",
+                f"cache.image_outs_path={p['cache_image_outs'] if mode == 'stored' else 'null'}", "cache.labels_path=null",
+                "cache.alpha=[1.0]", "cache_weights_strategy.beta=[5.5]", f"run_dir={tmp_path / mode}",
+                "cache_strategies.topk.topk=[4]", "cache_strategies.topk_prob.topk=[8]"]
+        for grp in ("topk_per_gold", "topk_prob_per_gold", "per_pred_class_random", "per_gold_class_random", "global_random"):
+            over.append(f"cache_strategies.{grp}=null")
+        run(over)
+        recs = [json.loads(line) for line in (tmp_path / mode / "image_attention.log").read_text().splitlines()]
+        accs[mode] = [(r["cache_strategy"]["_target_"], r["acc1"], r["acc5"]) for r in recs if r.get("type") == "searcher_result"]
+    assert len(accs["stored"]) == 3 and accs["stored"] == accs["lazy"]
