@@ -458,23 +458,23 @@ def test_pseudo_labels_without_the_logits_bank(ops, golden_dir, tmp_path):
     conf, label = lazy.rowconf()
     conf_ref, label_ref = ops.rowconf(L)
     assert torch.equal(label, label_ref)
-    torch.testing.assert_close(conf, conf_ref, rtol=0, atol=5e-7)
+    torch.testing.assert_close(conf, conf_ref, rtol=0, atol=3e-6)            # fp32 accumulation order of a D-long dot product
     conf_p, label_p = lazy.rowconf(scale=orc.CLIP_SCALE, prob=True)
     conf_p_ref, _ = ops.rowconf(L, scale=orc.CLIP_SCALE, prob=True)
     assert torch.equal(label_p, label_ref)
-    torch.testing.assert_close(conf_p, conf_p_ref, rtol=2e-4, atol=0)          # exp(100 * 5e-7) - 1 = 5e-5 per term
+    torch.testing.assert_close(conf_p, conf_p_ref, rtol=1e-3, atol=0)          # exp(100 * 3e-6) - 1 = 3e-4 per term
     idx = TopKProbStrategy(4, orc.CLIP_SCALE).select(K, lazy)
     assert np.array_equal(idx.cpu().numpy(), att["cache_idx"])
     assert np.array_equal(TopKStrategy(4).select(K, lazy).cpu().numpy(), TopKStrategy(4).select(K, L).cpu().numpy())
-    torch.testing.assert_close(lazy[idx], L[idx], rtol=0, atol=5e-7)
+    torch.testing.assert_close(lazy[idx], L[idx], rtol=0, atol=3e-6)
     # ragged larger shape: 1000 classes (4 column steps), rows not a multiple of the 256-row tile, fp16 features
     g = torch.Generator().manual_seed(12)
     banks = orc.synthetic_banks(8, 3001, 512, 1000, seed=12, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
     Kb, Tb = banks["cache_image_features"].cuda(), banks["text_features"].cuda()
     conf, label = ops.rowconf_from_features(Kb, True, Tb)
-    Lb = orc.normalize_columns(banks["cache_image_features"].float()).t() @ banks["text_features"].float()
+    Lb = orc.normalize_columns(banks["cache_image_features"].double()).t() @ banks["text_features"].double()
     ref_conf, ref_label = Lb.max(dim=1)
-    torch.testing.assert_close(conf.cpu(), ref_conf, rtol=0, atol=1e-6)
+    torch.testing.assert_close(conf.cpu().double(), ref_conf, rtol=0, atol=5e-6)       # 22-bit operands, fp32 accumulate
     agree = (label.cpu() == ref_label).float().mean().item()
     assert agree >= 0.999, agree                                               # a flipped label needs a top-2 gap < 1e-6
     # the sweep driver with cache.image_outs_path = null: same records as with the stored bank
