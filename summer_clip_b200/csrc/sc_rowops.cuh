@@ -65,11 +65,15 @@ template <>
 __device__ __forceinline__ uint32_t max_nan_x2<float>(uint32_t a, uint32_t) { return a; }   // never used
 
 // Register-resident row of at most 32 * NV 16-byte vectors (one warp per row).  load(): every lane issues all
-// of its 16-byte loads before the first use.  argmax(): two cheap passes over the fp32 copy in registers —
-// max.NaN for the value (1 instruction per element), then "last hit in reverse order" for the FIRST index at
-// which it occurs (2 per element) — instead of the ~20-instruction ordered compare per element of
-// sc::better(); rows that contain a NaN (the max comes back NaN) take the exact path.  Semantics are those
-// of row_argmax / torch.max(dim=1): larger value wins, NaN is largest, equal values -> smaller index.
+// of its 16-byte loads before the first use; vectors past the end of the row are filled with -inf, which is the
+// identity of every pass below (never the maximum unless the whole row is -inf, never equal to a finite
+// maximum, exp(scale * -inf - tmax) = 0 for scale > 0), so the passes run without per-vector predicates.
+// argmax(): max.NaN for the value (packed pairs for 16-bit storage: 0.5 instructions per element), then "last hit
+// in reverse order" for the FIRST index at which it occurs (3 per element) — instead of the ~20-instruction
+// ordered compare per element of sc::better(); rows that contain a NaN (the max comes back NaN) take the exact
+// path.  Semantics are those of row_argmax / torch.max(dim=1): larger value wins, NaN is largest, equal values
+// -> smaller index.  argmax_expsum(): the index pass and sum_c exp(scale l_c - scale l_max) in ONE pass over the
+// registers (one conversion per element).
 template <typename T, int NV>
 struct RegRow {
   static constexpr int kN = 16 / sizeof(T);
@@ -77,79 +81,106 @@ struct RegRow {
   int nv;        // 16-byte vectors in the row
   int lane;
 
+  static __device__ __forceinline__ uint32_t ninf_word() {
+    return sizeof(T) == 4 ? 0xff800000u : (std::is_same<T, __half>::value ? 0xfc00fc00u : 0xff80ff80u);
+  }
   __device__ __forceinline__ void load(const T* __restrict__ row, int nv_, int lane_) {
     nv = nv_;
     lane = lane_;
     const uint4* vrow = reinterpret_cast<const uint4*>(row);
+    const uint32_t ni = ninf_word();
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       const int j = lane + 32 * u;
-      v[u] = (j < nv) ? __ldg(vrow + j) : make_uint4(0u, 0u, 0u, 0u);
+      v[u] = (j < nv) ? __ldg(vrow + j) : make_uint4(ni, ni, ni, ni);
     }
   }
-  __device__ __forceinline__ bool has(int u) const { return lane + 32 * u < nv; }
   __device__ __forceinline__ int col(int u, int t) const { return (lane + 32 * u) * kN + t; }
   __device__ __forceinline__ float x(int u, int t) const { return to_f32<T>(reinterpret_cast<const T*>(&v[u])[t]); }
 
-  __device__ __forceinline__ MaxIdx argmax() const {
+  // row maximum, NaN-propagating, reduced over the warp
+  __device__ __forceinline__ float max_value() const {
     float mx = __int_as_float(0xff800000);   // -inf
     if constexpr (sizeof(T) == 2) {
-      // 16-bit storage: the maximum is exact in the storage type, so take it pairwise there (0.5 instructions per
-      // element); -inf in both halves is the identity (absent vectors were loaded as zeros: skip them)
-      uint32_t m2 = std::is_same<T, __half>::value ? 0xfc00fc00u : 0xff80ff80u;        // a pair of -inf (fp16 / bf16)
+      uint32_t m2 = ninf_word();             // the maximum is exact in the storage type: take it pairwise there
 #pragma unroll
-      for (int u = 0; u < NV; ++u)
-        if (has(u)) {
-          m2 = max_nan_x2<T>(m2, v[u].x);
-          m2 = max_nan_x2<T>(m2, v[u].y);
-          m2 = max_nan_x2<T>(m2, v[u].z);
-          m2 = max_nan_x2<T>(m2, v[u].w);
-        }
+      for (int u = 0; u < NV; ++u) {
+        m2 = max_nan_x2<T>(m2, v[u].x);
+        m2 = max_nan_x2<T>(m2, v[u].y);
+        m2 = max_nan_x2<T>(m2, v[u].z);
+        m2 = max_nan_x2<T>(m2, v[u].w);
+      }
       const T* pair = reinterpret_cast<const T*>(&m2);
       mx = max_nan(to_f32<T>(pair[0]), to_f32<T>(pair[1]));
     } else {
 #pragma unroll
-      for (int u = 0; u < NV; ++u)
-        if (has(u)) {
+      for (int u = 0; u < NV; ++u) {
 #pragma unroll
-          for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
-        }
+        for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (mx != mx) {                           // a NaN in the row (warp-uniform): exact ordered compare
-      MaxIdx m{0.f, -1};
+    return mx;
+  }
+  // exact ordered compare for rows that contain a NaN (warp-uniform slow path)
+  __device__ __forceinline__ MaxIdx argmax_exact() const {
+    MaxIdx m{0.f, -1};
 #pragma unroll
-      for (int u = 0; u < NV; ++u)
-        if (has(u)) {
+    for (int u = 0; u < NV; ++u)
+      if (lane + 32 * u < nv) {
 #pragma unroll
-          for (int t = 0; t < kN; ++t)
-            if (better(x(u, t), col(u, t), m)) { m.v = x(u, t); m.i = col(u, t); }
-        }
-      return warp_argmax(m);
-    }
+        for (int t = 0; t < kN; ++t)
+          if (better(x(u, t), col(u, t), m)) { m.v = x(u, t); m.i = col(u, t); }
+      }
+    return warp_argmax(m);
+  }
+  __device__ __forceinline__ MaxIdx argmax() const {
+    const float mx = max_value();
+    if (mx != mx) return argmax_exact();
     int idx = 0x7fffffff;
 #pragma unroll
-    for (int u = NV - 1; u >= 0; --u)
-      if (has(u)) {
+    for (int u = NV - 1; u >= 0; --u) {
 #pragma unroll
-        for (int t = kN - 1; t >= 0; --t) idx = (x(u, t) == mx) ? col(u, t) : idx;
-      }
+      for (int t = kN - 1; t >= 0; --t) idx = (x(u, t) == mx) ? col(u, t) : idx;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
     return MaxIdx{mx, idx};
   }
-
-  // sum_c exp(scale * l_c - tmax): same terms and summation order as row_expsum (lane partials in vector
-  // order, then the xor tree)
+  // argmax() plus sum_c exp(scale * l_c - scale * l_max) (scale > 0) in one pass over the registers.  The sum
+  // runs in reverse vector order within a lane, then the xor tree.
+  __device__ __forceinline__ MaxIdx argmax_expsum(float scale, float& sum) const {
+    const float mx = max_value();
+    if (mx != mx) {
+      sum = mx;
+      return argmax_exact();
+    }
+    const float tmax = __fmul_rn(mx, scale);
+    int idx = 0x7fffffff;
+    float s = 0.f;
+#pragma unroll
+    for (int u = NV - 1; u >= 0; --u) {
+#pragma unroll
+      for (int t = kN - 1; t >= 0; --t) {
+        const float xv = x(u, t);
+        idx = (xv == mx) ? col(u, t) : idx;
+        s += exp_neg_fast(__fmul_rn(xv, scale) - tmax);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+    sum = warp_sum(s);
+    return MaxIdx{mx, idx};
+  }
+  // sum_c exp(scale * l_c - tmax), scale > 0
   __device__ __forceinline__ float expsum(float scale, float tmax) const {
     float s = 0.f;
 #pragma unroll
-    for (int u = 0; u < NV; ++u)
-      if (has(u)) {
+    for (int u = NV - 1; u >= 0; --u) {
 #pragma unroll
-        for (int t = 0; t < kN; ++t) s += exp_neg_fast(__fmul_rn(x(u, t), scale) - tmax);
-      }
+      for (int t = kN - 1; t >= 0; --t) s += exp_neg_fast(__fmul_rn(x(u, t), scale) - tmax);
+    }
     return warp_sum(s);
   }
 };

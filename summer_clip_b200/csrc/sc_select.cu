@@ -64,9 +64,16 @@ rowconf_reg_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, fl
     for (int i = 0; i < kRows; ++i) {
       const int64_t r = r0 + i * warps_per_grid;
       if (r < N) {
-        const MaxIdx m = row[i].argmax();
-        float cf = m.v;
-        if (mode == SC_CONF_PROB) cf = 1.0f / row[i].expsum(scale, __fmul_rn(m.v, scale));
+        MaxIdx m;
+        float cf;
+        if (mode == SC_CONF_PROB) {
+          float sum;
+          m = row[i].argmax_expsum(scale, sum);
+          cf = 1.0f / sum;
+        } else {
+          m = row[i].argmax();
+          cf = m.v;
+        }
         if (lane == 0) {
           conf[r] = cf;
           label[r] = m.i;
@@ -261,7 +268,7 @@ int launch_rowconf(const void* L, int64_t N, int64_t C, int64_t ld, float scale,
   const int64_t want = sc::ceil_div(N, 8);
   const unsigned blocks = static_cast<unsigned>(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
   constexpr int NV = (sizeof(T) == 4) ? 8 : 4;          // 32 lanes * NV vectors * kN elements = 1024
-  if (vec && C % kN == 0 && C / kN <= 32 * NV)
+  if (vec && C % kN == 0 && C / kN <= 32 * NV && (mode != SC_CONF_PROB || scale > 0.f))
     rowconf_reg_kernel<T, NV><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, scale, mode, conf, label);
   else if (vec)
     rowconf_kernel<T, true><<<blocks, 256, 0, st>>>(static_cast<const T*>(L), N, C, ld, scale, mode, conf, label);

@@ -23,6 +23,12 @@ for dtype in (torch.float16, torch.float32):
 bank = torch.randn(dim, n, device=dev, dtype=torch.float16)
 for _ in range(2):
     kn = ops.normalize_cast(bank, True)
-    layout = ops.hard_bank_layout(lab16[:n], c).gather(kn)
+    layout = ops.hard_bank_layout(lab16[:n], c).gather(kn)                 # two passes over the bank (round 1)
+    built = ops.hard_bank_build(lab16[:n], c, bank, True)                  # one pass: rows scattered to sorted places
+del kn, layout
+L = (0.25 + 0.02 * torch.randn(n, c, generator=g, device=dev)).half()
+for _ in range(2):
+    vt = ops.values_prepare(L, c, softmax_scale=10.0)                      # SoftmaxCacheStrategy values, transposed
+    vh = ops.values_prepare(L, c)                                          # dense one-hot values
 torch.cuda.synchronize()
-print("ok", idx.numel(), layout.n_sorted)
+print("ok", idx.numel(), built.n_sorted)
