@@ -494,3 +494,74 @@ def test_pseudo_labels_without_the_logits_bank(ops, golden_dir, tmp_path):
         recs = [json.loads(line) for line in (tmp_path / mode / "image_attention.log").read_text().splitlines()]
         accs[mode] = [(r["cache_strategy"]["_target_"], r["acc1"], r["acc5"]) for r in recs if r.get("type") == "searcher_result"]
     assert len(accs["stored"]) == 3 and accs["stored"] == accs["lazy"]
+
+
+def test_kernels_stay_inside_their_output_buffers(ops):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02h_sanitizer_memcheck.log), so out-of-bounds WRITES
+    are hunted with canaries instead: every output of the attention-family entry points is a window of a larger
+    buffer whose guard zones (before, after, and the unused tail of every padded row) must come back untouched, on
+    shapes that are ragged against every tile size; the results inside the windows are checked as well."""
+    import ctypes
+    from summer_clip_b200 import _lib
+    lib = _lib.load()
+    SENT = float.fromhex("0x1.234568p+100")
+    nq, nk, dim, c = 259, 2931, 192, 37
+    g = torch.Generator().manual_seed(13)
+    Qn = ops.normalize_cast(torch.randn(nq, dim, generator=g).cuda(), False)
+    Kn = ops.normalize_cast(torch.randn(nk, dim, generator=g).cuda() + 0.3, False)
+    labels = torch.randint(0, c, (nk,), generator=g).int().cuda()
+    bank = ops.hard_bank_layout(labels, c).gather(Kn)
+    A = Qn.float() @ Kn.float().t()
+    onehot = torch.nn.functional.one_hot(labels.long(), c).float()
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())            # noqa: E731
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def guarded(rows, cols, ld, parts=1):
+        buf = torch.full((parts * rows * ld + 2 * 4096,), SENT, dtype=torch.float32, device="cuda")
+        win = buf[4096: 4096 + parts * rows * ld].view(parts, rows, ld)
+        return buf, win
+
+    def guards_ok(buf, win, cols):
+        inside = torch.zeros_like(buf, dtype=torch.bool)
+        inside[4096: 4096 + win.numel()].view_as(win)[:, :, :cols] = True
+        return bool((buf[~inside] == SENT).all())
+
+    ld = c + 5                                               # padded rows: columns c .. ld-1 must stay untouched
+    # segmented kernel, 3 key splits
+    buf, O = guarded(nq, c, ld, parts=3)
+    _lib.check(lib.sc_attn_fwd_hard(ptr(Qn), ptr(bank.rows), ptr(bank.gcls), ptr(bank.kbits), 0, nq, bank.n_sorted, Qn.shape[1],
+                                    c, 5.5, 3, ptr(O), ld, stream), "seg")
+    # the library zeroes the whole [splits, Nq, ldo] tile by contract (documented): only the outer guards apply
+    assert bool((buf[:4096] == SENT).all()) and bool((buf[4096 + O.numel():] == SENT).all())
+    torch.testing.assert_close(O[:, :, :c].sum(0), torch.exp(5.5 * (A - 1)) @ onehot, rtol=1e-4, atol=1e-5)
+    # softmax mode of the segmented kernel
+    buf, S = guarded(nq, c, ld, parts=2)
+    _lib.check(lib.sc_attn_softmax_hard(ptr(Qn), ptr(bank.rows), ptr(bank.gcls), ptr(bank.kbits), 0, nq, bank.n_sorted,
+                                        Qn.shape[1], c, 30.0, 2, ptr(S), ld, stream), "softmax seg")
+    assert bool((buf[:4096] == SENT).all()) and bool((buf[4096 + S.numel():] == SENT).all())
+    # dense kernel, 2 key splits, narrow class slices
+    Vt = ops.values_prepare(None, c, labels=labels)
+    buf, O = guarded(nq, c, ld, parts=2)
+    _lib.check(lib.sc_attn_fwd(ptr(Qn), ptr(Kn), ptr(Vt), 0, nq, nk, Qn.shape[1], c, Vt.shape[0], Vt.shape[1], 5.5, 2, ptr(O), ld,
+                               stream), "dense")
+    assert guards_ok(buf, O, c)
+    torch.testing.assert_close(O[:, :, :c].sum(0), torch.exp(5.5 * (A - 1)) @ onehot, rtol=3e-3, atol=3e-3)
+    # split-fp16 GEMM and the fused row scan
+    xh, xl = ops.normalize_split(torch.randn(nq, dim, generator=g).cuda(), False)
+    th, tl = ops.normalize_split(torch.randn(c, dim, generator=g).cuda(), False)
+    buf, Z = guarded(nq, c, ld)
+    _lib.check(lib.sc_gemm_split_nt(ptr(xh), ptr(xl), ptr(th), ptr(tl), nq, c, xh.shape[1], 1.0, ptr(Z), ld, stream), "gemm")
+    assert guards_ok(buf, Z, c)
+    want = (xh.float() + xl.float()) @ (th.float() + tl.float()).t()
+    torch.testing.assert_close(Z[0, :, :c], want, rtol=1e-5, atol=1e-5)
+    buf, cf = guarded(1, nq, nq + 3)
+    lb = torch.full((nq + 64,), -7, dtype=torch.int32, device="cuda")
+    _lib.check(lib.sc_rowconf_from_split(ptr(xh), ptr(xl), ptr(th), ptr(tl), nq, c, xh.shape[1], 1.0, 1.0, 0, ptr(cf), ptr(lb), stream),
+               "rowconf fused")
+    assert guards_ok(buf, cf, nq) and bool((lb[nq:] == -7).all())
+    assert torch.equal(lb[:nq].long(), want.argmax(1))
+    # row maximum pre-pass
+    buf, rm = guarded(1, nq, nq + 3)
+    _lib.check(lib.sc_attn_rowmax(ptr(Qn), ptr(Kn), 0, nq, nk, Qn.shape[1], ptr(rm), stream), "rowmax")
+    assert guards_ok(buf, rm, nq)
+    torch.testing.assert_close(rm[0, 0, :nq], A.amax(1), rtol=0, atol=2e-6)
