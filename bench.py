@@ -283,25 +283,47 @@ def run_ours(args):
     lab_bufs = [torch.empty_like(lab_host_mine, device=device) for _ in range(2)]
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
 
+    computed = [None, None]                        # per input buffer: the event after the search that read it last
+
     def start_copy(i):
         with torch.cuda.stream(copy_stream):
+            if computed[i % 2] is not None:
+                copy_stream.wait_event(computed[i % 2])      # the step that read this buffer last has finished
             q_bufs[i % 2].copy_(q_host_mine, non_blocking=True)
             lab_bufs[i % 2].copy_(lab_host_mine, non_blocking=True)
             copy_done[i % 2].record(copy_stream)
 
+    # results leave the same way: the device->host copy of step i's predictions and counters runs on a second copy
+    # stream into double-buffered pinned host buffers and is awaited one step later, under step i + 1's compute
+    out_stream = torch.cuda.Stream(device=device)
+    pred_host = [torch.empty((1, nq), dtype=torch.int32).pin_memory() for _ in range(2)]
+    cnt_host = [torch.empty((2, 1), dtype=torch.int32).pin_memory() for _ in range(2)]
+    out_done = [torch.cuda.Event(), torch.cuda.Event()]
+    out_keep = [None, None]
+
     def step_e2e(i, n_steps):
-        """Host buffers in, host result out: H2D of the query slice, D2H of predictions + counters."""
+        """Host buffers in, host result out: H2D of the query slice, D2H of predictions + counters, both double
+        buffered against the compute of the neighbouring steps.  Returns the host tensors of step i - 1 (complete)."""
         if i == 0:
             start_copy(0)
         if i + 1 < n_steps:
-            start_copy(i + 1)                       # buffer (i+1) % 2 was last read by step i-1, which has completed
+            start_copy(i + 1)                       # buffer (i+1) % 2 was last read by step i-1: the copy waits for it
         torch.cuda.current_stream().wait_event(copy_done[i % 2])
         r = searcher.search(q_bufs[i % 2], [BETA], [ALPHA], labels=lab_bufs[i % 2], want_cache_logits=False,
                             query_shard=nq if world > 1 else False, blocks=blocks)[0]
-        pred = r["pred"].to("cpu", non_blocking=True)
-        counts = torch.stack([r["top1"], r["top5"]]).to("cpu", non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return pred, counts
+        computed[i % 2] = torch.cuda.Event()
+        computed[i % 2].record(torch.cuda.current_stream())
+        with torch.cuda.stream(out_stream):
+            out_stream.wait_event(computed[i % 2])
+            pred_host[i % 2].copy_(r["pred"], non_blocking=True)
+            cnt_host[i % 2].copy_(torch.stack([r["top1"], r["top5"]]), non_blocking=True)
+            out_done[i % 2].record(out_stream)
+        out_keep[i % 2] = r                         # keep the device tensors alive until their copy has been awaited
+        if i > 0:
+            out_done[(i - 1) % 2].synchronize()     # step i-1's results are on the host now
+        if i + 1 == n_steps:
+            out_done[i % 2].synchronize()
+        return pred_host[i % 2], cnt_host[i % 2]
 
     def sync_all():
         if world > 1:
@@ -345,6 +367,12 @@ def run_ours(args):
     for name, e0, e1 in events:
         phase_ms[name] = phase_ms.get(name, 0.0) + e0.elapsed_time(e1) / args.steps
     attn_ms = phase_ms["attention"]                        # per step: the sum over the step's attention launches
+    attn_ms_ranks = [attn_ms]
+    if world > 1:                                          # the step ends with the slowest rank: report the spread
+        t = torch.zeros(world, dtype=torch.float64, device=device)
+        t[rank] = attn_ms
+        dist.all_reduce(t)
+        attn_ms_ranks = [round(v, 3) for v in t.tolist()]
     n_attn_launches = sum(1 for name, _, _ in events if name == "attention") // args.steps
     gpu_launches = searcher.gpu_launches
     top1 = int(res["top1"][0])
@@ -430,7 +458,8 @@ def run_ours(args):
                    "bank_build_ms": bank_build_ms, "bank_build_first_call_ms": bank_build_first_ms, "top1_count": top1},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                     "kernel": "sc_attn_seg_kernel" if not dense else "sc_attn_t_kernel", "kernel_ms": attn_ms, "algorithmic_flops_per_launch": flops,
+                     "kernel": "sc_attn_seg_kernel" if not dense else "sc_attn_t_kernel", "kernel_ms": attn_ms,
+                     "kernel_ms_per_rank": attn_ms_ranks, "algorithmic_flops_per_launch": flops,
                      "executed_flops_per_launch": executed, "dense_equivalent_tflops": dense_equiv,
                      "note": ("one-hot values: achieved/frac count the tensor-core FLOPs actually issued (GEMM-1; W @ one_hot is a segmented fp32 "
                               "sum, no GEMM-2 exists); dense_equivalent_tflops = 2*Nq*Nk*(D+C)/time is what a dense-V kernel would need for the "

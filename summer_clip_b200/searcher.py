@@ -113,6 +113,7 @@ class ClipSearcher:
         self.softmax = False                                 # temperature-softmax mode: `betas` are temperatures
         self.gpu_launches = 0                                # kernels of ours launched (bench bookkeeping)
         self.events: tp.Optional[list] = None                # bench.py: set to [] to collect (name, start, end) CUDA events
+        self.trace = bool(os.environ.get("SUMMER_CLIP_B200_TRACE"))   # finer marks inside the key-sharded pipeline
         # key-sharded exchange: "p2p" = peers' partial tiles read in place over NVLink (symmetric memory), "nccl" =
         # reduce-scatter; None = p2p when the process group supports it (decided at the first sharded search)
         self.exchange: tp.Optional[str] = os.environ.get("SUMMER_CLIP_B200_EXCHANGE") or None
@@ -483,42 +484,60 @@ class ClipSearcher:
                 rtile.buf.zero_()
             keep = []                                   # tensors the side stream still reads: alive until the final join
             preds = [torch.zeros((na, nq), dtype=torch.int32, device=dev) for _ in betas] if (want_pred and rtile is None) else None
+            # zero-shot logits of MY rows of every block, up front on the side stream: the tensor-core GEMM needs whole
+            # SMs (224 KB of shared memory) and would otherwise queue behind the attention CTAs of the next block
+            slices = []
+            for b in range(blocks):
+                slo, shi = query_slice(edges[b + 1] - edges[b], rank, world)
+                slices.append((edges[b] + slo, edges[b] + shi))
+            start = torch.cuda.Event()
+            start.record(main)
+            zs: tp.List[tp.Optional[torch.Tensor]] = [None] * blocks
+            with torch.cuda.stream(side):
+                side.wait_event(start)
+                if self.text is not None:
+                    for b, (glo, ghi) in enumerate(slices):
+                        if ghi <= glo:
+                            continue
+                        if query_shard:                     # the raw rows may live on another rank: use the normalised ones
+                            zs[b] = ops.zero_shot_logits(qn[glo:ghi], False, self.text, scale=100.0, normalize=False, t_split=self.text_split)
+                        else:
+                            zs[b] = ops.zero_shot_logits(q[:, glo:ghi] if feature_major else q[glo:ghi], feature_major, self.text,
+                                                         scale=100.0, normalize=True, t_split=self.text_split)
+                        self.gpu_launches += 2
+            t_last = None
             for b in range(blocks):
                 b0, b1 = edges[b], edges[b + 1]
                 nb = b1 - b0
                 parts = self._local_parts_many(qn[b0:b1], betas, merge=False)
-                merged = []
-                tm = self._mark()
-                for bi, o in enumerate(parts):
-                    if self.softmax:
-                        merged.append(o)
-                    elif tiles is not None:             # the summed key-split tiles land in my slot of the peer-mapped buffer
-                        merged.append(ops.merge_partials(o if o.dim() == 3 else o[None], out=tiles.buf[b * nbeta + bi, :nb]))
-                        self.gpu_launches += 1
-                    else:
-                        merged.append(ops.merge_partials(o) if o.dim() == 3 and o.shape[0] > 1 else (o[0] if o.dim() == 3 else o))
-                        self.gpu_launches += int(o.dim() == 3 and o.shape[0] > 1)
-                self._mark("merge_splits", tm)
-                ready = torch.cuda.Event()
+                t_last = self._mark()
+                ready = torch.cuda.Event(enable_timing=self.events is not None)
                 ready.record(main)
-                keep.append((parts, merged))
+                keep.append(parts)
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
                     ts = self._mark()
+                    # sum of the key-split tiles: beside the next block's attention (no shared memory: co-resident)
+                    merged = []
+                    for bi, o in enumerate(parts):
+                        if self.softmax:
+                            merged.append(o)
+                        elif tiles is not None:         # ... straight into my slot of the peer-mapped buffer
+                            merged.append(ops.merge_partials(o if o.dim() == 3 else o[None], out=tiles.buf[b * nbeta + bi, :nb]))
+                            self.gpu_launches += 1
+                        else:
+                            merged.append(ops.merge_partials(o) if o.dim() == 3 and o.shape[0] > 1 else (o[0] if o.dim() == 3 else o))
+                            self.gpu_launches += int(o.dim() == 3 and o.shape[0] > 1)
+                    keep.append(merged)
+                    tsub = self._mark(f"b{b}.merge_splits", ts) if self.trace else None
                     slo, shi = query_slice(nb, rank, world)
                     bper = -(-nb // world)
                     glo, ghi = b0 + slo, b0 + shi          # my rows of this block, global numbering
-                    z = None
-                    if self.text is not None and ghi > glo:
-                        if query_shard:                     # the raw rows may live on another rank: use the normalised ones
-                            z = ops.zero_shot_logits(qn[glo:ghi], False, self.text, scale=100.0, normalize=False, t_split=self.text_split)
-                        else:
-                            z = ops.zero_shot_logits(q[:, glo:ghi] if feature_major else q[glo:ghi], feature_major, self.text,
-                                                     scale=100.0, normalize=True, t_split=self.text_split)
-                        self.gpu_launches += 1
+                    z = zs[b]
                     lab_mine = lab_all[glo:ghi].contiguous() if lab_all is not None else None
                     if tiles is not None:
                         tiles.barrier(b)                    # every rank's slots of block b are complete
+                    tsub = self._mark(f"b{b}.barrier", tsub) if self.trace else None
                     for bi, o in enumerate(merged):
                         if self.softmax:            # already merged over the key shards (log-sum-exp merge, softmax_logits)
                             o_mine = o[slo:shi]
@@ -527,6 +546,7 @@ class ClipSearcher:
                             if shi > slo:
                                 o_mine = ops.merge_peer_parts([v[b * nbeta + bi, slo:shi] for v in tiles.views])
                                 self.gpu_launches += 1
+                                tsub = self._mark(f"b{b}.peer_merge", tsub) if self.trace else None
                         else:
                             o_mine, _, _ = exchange_partials(o, self.group)
                         r = None
@@ -537,6 +557,7 @@ class ClipSearcher:
                                 counts[bi, 0] += r["top1"]
                                 counts[bi, 1] += r["top5"]
                             results[bi]["pieces"].append((glo, ghi, r["logits"], o_mine, z))
+                            tsub = self._mark(f"b{b}.epilogue", tsub) if self.trace else None
                         if want_pred and rtile is not None:
                             if r is not None:
                                 rtile.buf[bi, :, glo:ghi] = r["pred"]          # int32 -> exact fp32
@@ -550,6 +571,8 @@ class ClipSearcher:
                             keep.append((gathered, mine))
                         keep.append((o_mine, z, r))
                     self._mark("exchange_and_finish", ts)
+                    if self.events is not None:             # attention-of-block-done -> block finished, per block
+                        self._mark(f"block{b}_ready_to_finished", ready)
             with torch.cuda.stream(side):
                 if rtile is not None:
                     tf = self._mark()
@@ -568,6 +591,7 @@ class ClipSearcher:
                 done = torch.cuda.Event()
                 done.record(side)
             main.wait_event(done)
+            self._mark("tail_after_last_attention", t_last)
             if preds is not None:
                 for bi in range(nbeta):
                     results[bi]["pred"] = preds[bi]
