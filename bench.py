@@ -258,7 +258,7 @@ def run_ours(args):
     blocks = (int(os.environ["SC_BENCH_BLOCKS"]) if os.environ.get("SC_BENCH_BLOCKS") else None) if shard_keys else None
     nq_launch = nq_attn // (blocks or 4) if shard_keys else nq_attn        # queries per attention launch
     splits = ops.attn_hard_splits(nq_launch, searcher.hard_bank.n_sorted, device, bank=searcher.hard_bank) if searcher.hard_bank is not None \
-        else ops.attn_splits(nq_launch, n_local, c_pad, device)
+        else ops.attn_splits(nq_launch, n_local, c_pad, device, D_pad=ops.pad_dim(dim))
 
     q_host = q_bank.cpu().pin_memory()
     labels_host = labels.cpu().pin_memory()

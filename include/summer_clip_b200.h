@@ -121,6 +121,10 @@ int sc_values_prepare(const void* L, int dtype, int64_t N, int64_t C, int64_t ld
  * (sc_merge_partials).  splits >= 1 partitions the key tiles so that small query batches still
  * fill the GPU; splits = 0 lets the library choose (query with sc_attn_splits). */
 int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count);
+/* ... and with L2 blocking (what splits = 0 uses): for banks larger than L2 scored by several waves of query tiles the
+ * key range of a split is sized so that its K + Vt bytes stay L2-resident while every query tile passes over it
+ * (work items launch split-major); costs one [Nq, ldo] fp32 partial tile per split. */
+int sc_attn_splits_for(int64_t Nq, int64_t Nk, int64_t D_pad, int64_t C_pad, int sm_count);
 int sc_attn_fwd(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,
                 int64_t D_pad, int64_t n_cols, int64_t C_pad, int64_t Nk_pad, float beta,
                 int splits, float* O, int64_t ldo, void* stream);

@@ -38,6 +38,7 @@ SIGNATURES = {
     "sc_values_prepare": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int,
                                   c_float, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
     "sc_attn_splits": (c_int, [c_int64, c_int64, c_int64, c_int]),
+    "sc_attn_splits_for": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "sc_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                             c_float, c_int, c_void_p, c_int64, c_void_p]),
     "sc_attn_fwd_shifted": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int64,

@@ -124,6 +124,30 @@ int64_t sc_pad_classes(int64_t C) {
   return n_class_slices(C) * class_slice(C);
 }
 
+int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count);
+
+// Key splits of the dense-values kernel with L2 blocking: work items are launched split-major (blockIdx.z slowest), so
+// while the query tiles pass over one key range its K and Vt bytes are read from DRAM once and then served by L2 —
+// if they fit.  Query-tile clusters that start at different times (every wave after the first) otherwise stream the
+// bank on their own schedule and the DRAM traffic grows ~15x (measured: profiles/r02n_dense_dram_vs_splits.log).
+// Block = 64 MB (half of the 126 MB L2: the two dies cache a line both read twice).  Measured at 12.5k queries x
+// 1.28M keys: 5 / 40 / 80 / 160 / 320 splits -> 150 / 126 / 41 / 10 / 10 GB of DRAM reads and 76.6 / 73.2 / 70.7 / 72.6 /
+// 79.4 ms: smaller blocks read less but pay more per-item prologue and one more [Nq, C] partial tile each.
+int sc_attn_splits_for(int64_t Nq, int64_t Nk, int64_t D_pad, int64_t C_pad, int sm_count) {
+  const int base = sc_attn_splits(Nq, Nk, C_pad, sm_count);
+  if (Nq <= 0 || Nk <= 0 || D_pad <= 0 || C_pad <= 0) return base;
+  if (sm_count <= 0) sm_count = 148;
+  const int64_t clusters = sc::ceil_div(Nq, kBM);                                   // query tiles
+  const int64_t resident = sm_count / (n_class_slices(C_pad) >= 4 ? 4 : 2);        // clusters in flight
+  const double bank_bytes = static_cast<double>(Nk) * static_cast<double>(D_pad + C_pad) * 2.0;
+  if (clusters < 2 * resident || bank_bytes <= 48.0e6) return base;                 // one wave, or the bank fits anyway
+  const int64_t tiles = sc::ceil_div(Nk, kBN);
+  int64_t want = static_cast<int64_t>(bank_bytes / 64.0e6) + 1;
+  if (want > tiles) want = tiles;
+  if (want > 65535) want = 65535;
+  return want > base ? static_cast<int>(want) : base;
+}
+
 int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count) {
   if (Nq <= 0 || Nk <= 0 || C_pad <= 0) return 1;
   if (sm_count <= 0) sm_count = 148;
@@ -290,7 +314,7 @@ int sc_attn_fwd_shifted(const void* Qn, const void* Kn, const void* Vt, int op_d
     int dev = 0, sms = 148;
     SC_CUDA(cudaGetDevice(&dev));
     SC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    splits = sc_attn_splits(Nq, Nk, C_pad, sms);
+    splits = sc_attn_splits_for(Nq, Nk, D_pad, C_pad, sms);
   }
   SC_REQUIRE(splits <= tiles_total && splits <= 65535, SC_ESHAPE,
              "sc_attn_fwd: splits=%d exceeds the %lld key tiles", splits, (long long)tiles_total);

@@ -13,10 +13,13 @@
 // weight slots shrink to 16 KB and the operand ring grows to 6 stages.  (Measured on the non-transposed
 // pair kernel: the 32 KB x 3 exchange per tile sits on a serial chain with single-buffered slots and
 // costs ~75 ms of a 309 ms pass.)
-// The fused probe+issue loops of sc_attn_seg.cu (sc_ptx.cuh: umma4_cg2_probe / tma2_cg2_probe) were tried here too:
-// they cut the cycle count by 10 % but the kernel already sits at the board's power limit with the tensor pipe
-// half idle, so the clock fell from 1.96 to 1.55 GHz and the pass got slower (297 -> 337-342 ms, same GPU, same
-// call: profiles/r01e_ab_dense_kernels.log).  This file keeps the plain wait-then-issue loops.
+// What bounds it: tensor memory.  A 128-query x 1000-class fp32 accumulator is 1000 TMEM columns, so
+// the classes are sliced over 4 CTAs and GEMM-1 tiles are N = 128 wide (96 B/cycle/SM of operand traffic instead of
+// the segmented kernel's 64), 80 KB of shared memory go to the weight slots and the 6-stage ring holds 144 KB
+// against the ~195 KB that 78 B/cycle x a ~2500-cycle slot turnaround asks for; the tensor pipe is active 43 % of
+// the cycles (ncu, profiles/r02m_*), the board sits at its 1 kW cap at ~1.75 GHz.  What moved the time this round:
+// L2-blocked key splits (the key range of a work item is chosen so that its K + Vt bytes stay L2-resident while
+// every query tile passes over it: DRAM 150 -> 10 GB per 12.5k queries, 327 -> 300 ms), not issue-loop tuning.
 #include "sc_common.cuh"
 #include "sc_ptx.cuh"
 
@@ -31,9 +34,9 @@ constexpr int kBQ = 128;             // queries per cluster tile (UMMA N)
 constexpr int kBN = 128;             // keys per tile = TMEM lanes of S^T
 constexpr int kBK = 64;              // 16-bit elements per swizzled smem row
 constexpr int kSub = 24576;          // one 64-wide K chunk: Kn chunk 16 KB + Qn half 8 KB
-// A ring stage holds CPS (1 or 2) K chunks for GEMM-1 / the Vt boxes of CPS 128-class blocks for GEMM-2.
-// CPS = 2 halves the barrier round trips (measured: on-chip time 250 -> 165 ms) but leaves only 3 stages in
-// flight against ~2 us of loaded TMA latency (full pass 296 -> 321 ms); CPS = 1 is the default.
+// A ring stage holds one K chunk + Q half for GEMM-1, or the Vt box of one 128-class block for GEMM-2.  (Two chunks
+// per stage halved the barrier round trips — on-chip time 250 -> 165 ms in round 1 — but left 3 stages in flight
+// against ~2 us of loaded TMA latency: full pass 296 -> 321 ms.)
 constexpr int kHalf = 16384;         // half of a weight tile: [128 keys x 64 queries] MN-major SW128
 constexpr int kThreads = 192;
 constexpr int kExpThreads = 128;
@@ -53,8 +56,8 @@ struct TParams {
   int n_mb;         // 128-class blocks per CTA = ceil(slice / 128)
   int tiles_total;
   int splits;
-  int dbg;          // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit0/1/2 skip Q/V/K loads,
-                    // 3 exp math, 4/5 GEMM-1/2 MMAs, 6 shrink the exchange to 1 KB
+  int dbg;          // SC_ATTN_TIMING_EXPERIMENTS builds only (wrong results): bit 3 skips the exp math, bit 6 shrinks
+                    // the exchange to 1 KB
   float c1, c0, o_scale;
   const float* row_shift;   // nullable [Nq]: weights exp(beta (A - row_shift[q])) instead of exp(beta (A - 1))
   float* O;
@@ -91,12 +94,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <bool kF16, int NPAIR, int CPS>
+template <bool kF16, int NPAIR, bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
 sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const TParams p) {
   constexpr int CS = 2 * NPAIR;                                            // cluster size
-  constexpr int kStage = CPS * kSub;
+  constexpr int kStage = kSub;
   constexpr int NS = (kSmemPayload - (CS + 1) * kHalf) / kStage;           // 6 (CS=4) / 7 (CS=2) stages
   static_assert(NS <= kMaxStages && NS >= 2, "ring depth");
   extern __shared__ uint8_t smem_raw[];
@@ -161,13 +164,42 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t xbytes = (p.dbg & 64) ? 1024u : static_cast<uint32_t>(kHalf);   // exchange unit
 
+  // The TMA-producer and MMA-issuer loops below are single-thread issue loops with 256 cycles of UMMA work per ring
+  // stage; a plain wait-then-issue loop costs ~270 (try_wait on a completed barrier 117 cycles + 4 UMMA issues of ~36).
+  // Like the segmented kernel they use the fused probe helpers of sc_ptx.cuh: the non-blocking test of the NEXT ring
+  // slot's barrier rides inside this stage's issue block, and a blocking wait happens only when that probe failed.
+  // `kFused` = false (the default) keeps the plain wait-then-issue loops; SC_ATTN_T_FUSED=1 selects the fused ones.
+  // (An L2 prefetch of the next rounds' key tiles was tried as well: 354 -> 437 ms, profiles/r02k_dense_knobs.log.)
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; warp-uniform, elected issue)
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, ready = 0;
     const uint32_t full0 = smem_u32(&bars->full[0]);
     const uint32_t full0c = mapa(full0, leader);
     const uint32_t empty0 = smem_u32(&bars->empty[0]);
+    const uint32_t tx_g1 = is_leader ? 2u * (16384u + 8192u) : 0u;        // both CTAs' bytes land on the leader's barrier
+    const uint32_t tx_g2 = is_leader ? 2u * 16384u : 0u;
+    // one stage: wait for the slot (unless the previous stage's probe already saw it free), issue, probe the next slot
+    auto stage_load = [&](const CUtensorMap* m0, int x0, int y0, const CUtensorMap* m1, int x1, int y1, uint32_t on1,
+                          uint32_t tx) {
+      if (!ready) mbar_wait(empty0 + stage * 8, phase ^ 1u);
+      const bool wrap = (stage + 1 == NS);
+      const uint32_t dst = ring0 + stage * kStage;
+      if (kFused) {
+        ready = __all_sync(0xffffffffu,
+                           tma2_cg2_probe(dst, m0, x0, y0, 1u, dst + 16384, m1, x1, y1, on1, full0c + stage * 8,
+                                          full0 + stage * 8, tx, 0u, empty0 + (wrap ? 0 : stage + 1) * 8,
+                                          (wrap ? phase ^ 1u : phase) ^ 1u));
+      } else {
+        if (elect_one()) {
+          if (tx) mbar_arrive_expect_tx(full0 + stage * 8, tx);
+          tma_load_2d_cg2(dst, m0, full0c + stage * 8, x0, y0);
+          if (on1) tma_load_2d_cg2(dst + 16384, m1, full0c + stage * 8, x1, y1);
+        }
+        __syncwarp();
+      }
+      if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+    };
     auto load_v_round = [&](int rr) {
 #pragma unroll 1
       for (int src = 0; src < CS; ++src) {
@@ -176,22 +208,8 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll 1
         for (int c = 0; c < kBN / kBK; ++c) {
 #pragma unroll 1
-          for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
-            const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
-            mbar_wait(empty0 + stage * 8, phase ^ 1u);
-            if (elect_one()) {
-              if (p.dbg & 2) {
-                if (is_leader) mbar_arrive(full0 + stage * 8);
-              } else {
-                if (is_leader) mbar_arrive_expect_tx(full0 + stage * 8, 2u * 16384u * static_cast<uint32_t>(nblk));
-                for (int u = 0; u < nblk; ++u)
-                  tma_load_2d_cg2(ring0 + stage * kStage + u * kSub, &tmV, full0c + stage * 8,
-                                  (t0 + i) * kBN + c * kBK, c0 + (mb0 + u) * 128);     // my classes x 64 keys
-              }
-            }
-            __syncwarp();
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
-          }
+          for (int mb = 0; mb < n_mb; ++mb)                                            // my classes x 64 keys
+            stage_load(&tmV, (t0 + i) * kBN + c * kBK, c0 + mb * 128, &tmV, 0, 0, 0u, tx_g2);
         }
       }
     };
@@ -200,24 +218,8 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (r * CS + pair_first < T) {
         const int krow = (t0 + r * CS + static_cast<int>(rank)) * kBN;   // my key tile (may be past the split: unused)
 #pragma unroll 1
-        for (int d = 0; d < nd; d += CPS) {
-          const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
-          mbar_wait(empty0 + stage * 8, phase ^ 1u);
-          if (elect_one()) {
-            const uint32_t kb = (p.dbg & 4) ? 0u : 16384u, qb = (p.dbg & 1) ? 0u : 8192u;
-            if (is_leader) {
-              if (kb + qb) mbar_arrive_expect_tx(full0 + stage * 8, 2u * (kb + qb) * static_cast<uint32_t>(nsub));
-              else mbar_arrive(full0 + stage * 8);
-            }
-            for (int u = 0; u < nsub; ++u) {
-              const uint32_t dst = ring0 + stage * kStage + u * kSub;
-              if (kb) tma_load_2d_cg2(dst, &tmK, full0c + stage * 8, (d + u) * kBK, krow);                  // 128 keys
-              if (qb) tma_load_2d_cg2(dst + 16384, &tmQ, full0c + stage * 8, (d + u) * kBK, q0 + h * 64);   // 64 queries
-            }
-          }
-          __syncwarp();
-          if (++stage == NS) { stage = 0; phase ^= 1u; }
-        }
+        for (int d = 0; d < nd; ++d)                                     // 128 keys x 64 d  +  64 queries x 64 d
+          stage_load(&tmK, d * kBK, krow, &tmQ, d * kBK, q0 + h * 64, 1u, tx_g1);
       }
       if (r > 0) load_v_round(r - 1);
     }
@@ -233,13 +235,37 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (is_leader) {
       // ===================================================== MMA issuer for the pair
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, ready = 0;
       const uint32_t idesc1 = umma_idesc_16b(256, kBQ, kF16);                 // A, B K-major
       const uint32_t idesc2 = umma_idesc_16b(256, kBQ, kF16) | (1u << 16);    // B (P^T) MN-major
       const uint32_t tmem_o = tmem_base + kColO;
       const uint32_t full0 = smem_u32(&bars->full[0]);
       const uint32_t empty0 = smem_u32(&bars->empty[0]);
       const uint32_t pempty = smem_u32(&bars->p_empty);
+      // one stage of 4 UMMAs (K = 16 each): A advances 32 bytes per instruction, B by b_step descriptor units
+      auto stage_mma = [&](uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint64_t b_step, uint32_t idesc,
+                           uint32_t acc0, uint32_t bar2, uint16_t mask2, uint32_t flag2) {
+        if (!ready) mbar_wait(full0 + stage * 8, phase);
+        tc_fence_after();
+        const bool wrap = (stage + 1 == NS);
+        if (kFused) {
+          ready = __all_sync(0xffffffffu,
+                             umma4_cg2_probe<false>(d_tmem, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc,
+                                                    b_desc + b_step, b_desc + 2 * b_step, b_desc + 3 * b_step, idesc, acc0,
+                                                    1u, empty0 + stage * 8, pair_mask, bar2, mask2, flag2,
+                                                    full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
+        } else {
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_ss2(d_tmem, a_desc + 2 * k, b_desc + b_step * k, idesc, (k != 0 || acc0) ? 1u : 0u);
+            umma_commit2_mcast(empty0 + stage * 8, pair_mask);
+            if (flag2) umma_commit2_mcast(bar2, mask2);
+          }
+          __syncwarp();
+        }
+        if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
+      };
       auto gemm2_round = [&](int rr) {
 #pragma unroll 1
         for (int src = 0; src < CS; ++src) {
@@ -254,28 +280,12 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
 #pragma unroll 1
           for (int c = 0; c < kBN / kBK; ++c) {
+            const uint64_t b_desc = umma_desc_k128(slot0 + src * kHalf + c * 8192);              // P^T rows 64c..
 #pragma unroll 1
-            for (int mb0 = 0; mb0 < n_mb; mb0 += CPS) {
-              const int nblk = (n_mb - mb0) < CPS ? (n_mb - mb0) : CPS;
-              mbar_wait(full0 + stage * 8, phase);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t b_desc = umma_desc_k128(slot0 + src * kHalf + c * 8192);            // P^T rows 64c..
-                for (int u = 0; u < nblk; ++u) {
-                  const uint64_t a_desc = umma_desc_k128(ring0 + stage * kStage + u * kSub);       // Vt box, K-major
-#pragma unroll
-                  for (int k = 0; k < kBK / 16; ++k)       // A: +32 B per 16 keys; B: +16 key rows = +2048 B
-                    if (!(p.dbg & 32))
-                      umma_ss2(tmem_o + (mb0 + u) * 128, a_desc + 2 * k, b_desc + 128 * k, idesc2,
-                               (i | c | k) != 0 ? 1u : 0u);
-                }
-                umma_commit2_mcast(empty0 + stage * 8, pair_mask);
-                if (c == kBN / kBK - 1 && mb0 + CPS >= n_mb)      // this pair is done with source src's tile
-                  umma_commit2_mcast(pempty, static_cast<uint16_t>(1u << src));
-              }
-              __syncwarp();
-              if (++stage == NS) { stage = 0; phase ^= 1u; }
-            }
+            for (int mb = 0; mb < n_mb; ++mb)            // A: Vt box, K-major; B: +16 key rows = +2048 B per instruction
+              stage_mma(tmem_o + mb * 128, umma_desc_k128(ring0 + stage * kStage), b_desc, 128, idesc2,
+                        (i | c) != 0 ? 1u : 0u, pempty, static_cast<uint16_t>(1u << src),
+                        (c == kBN / kBK - 1 && mb == n_mb - 1) ? 1u : 0u);     // last stage: this pair is done with src's tile
           }
         }
       };
@@ -287,26 +297,12 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait(smem_u32(&bars->s_empty[sb]), ((own >> 1) & 1) ^ 1u);
           tc_fence_after();
           const uint32_t tmem_s = tmem_base + sb * 128;
+          const uint32_t sfull = smem_u32(&bars->s_full[sb]);
 #pragma unroll 1
-          for (int d = 0; d < nd; d += CPS) {
-            const int nsub = (nd - d) < CPS ? (nd - d) : CPS;
-            mbar_wait(full0 + stage * 8, phase);
-            tc_fence_after();
-            if (elect_one()) {
-              for (int u = 0; u < nsub; ++u) {
-                const uint32_t a_addr = ring0 + stage * kStage + u * kSub;
-                const uint64_t a_desc = umma_desc_k128(a_addr);              // K chunk (my 128 keys)
-                const uint64_t b_desc = umma_desc_k128(a_addr + 16384);      // Q half (64 queries)
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)
-                  if (!(p.dbg & 16))
-                    umma_ss2(tmem_s, a_desc + 2 * k, b_desc + 2 * k, idesc1, (d | u | k) != 0 ? 1u : 0u);
-              }
-              umma_commit2_mcast(empty0 + stage * 8, pair_mask);
-              if (d + CPS >= nd) umma_commit2_mcast(smem_u32(&bars->s_full[sb]), pair_mask);
-            }
-            __syncwarp();
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          for (int d = 0; d < nd; ++d) {
+            const uint32_t a_addr = ring0 + stage * kStage;                   // K chunk (my 128 keys) | Q half (64 queries)
+            stage_mma(tmem_s, umma_desc_k128(a_addr), umma_desc_k128(a_addr + 16384), 2, idesc1, d != 0 ? 1u : 0u, sfull,
+                      pair_mask, d == nd - 1 ? 1u : 0u);
           }
           ++own;
         }
@@ -443,10 +439,10 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // 16-bit row-major [rows, cols]; box = [box_rows x 64 cols], SW128 (own copy: box shapes differ per kernel)
-template <bool kF16, int NPAIR, int CPS>
+template <bool kF16, int NPAIR, bool kFused>
 int launch_t(dim3 grid, cudaStream_t st, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
              const TParams& p) {
-  auto kernel = sc_attn_t_kernel<kF16, NPAIR, CPS>;
+  auto kernel = sc_attn_t_kernel<kF16, NPAIR, kFused>;
   SC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -499,10 +495,11 @@ int attn_t_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, 
 #endif
   dim3 grid(static_cast<unsigned>(n_slices), static_cast<unsigned>(ceil_div(Nq, kBQ)), static_cast<unsigned>(splits));
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_attn_fwd: too many query tiles; chunk the queries");
-  // tuning knob, read once per process: K chunks per ring stage
-  static const int cps = [] { const char* env = std::getenv("SC_ATTN_T_CHUNKS"); return (env && std::atoi(env) == 2) ? 2 : 1; }();
+  // tuning knob, read once per process: fused probe+issue loops (SC_ATTN_T_FUSED=1; default off — measured equal
+  // within noise once the kernel sits at the power cap: profiles/r02l_dense_knobs.log)
+  static const bool fused = [] { const char* env = std::getenv("SC_ATTN_T_FUSED"); return env && std::atoi(env) != 0; }();
 #define SC_T_LAUNCH(F, NPV)                                                                       \
-  (cps == 2 ? launch_t<F, NPV, 2>(grid, st, tmQ, tmK, tmV, p) : launch_t<F, NPV, 1>(grid, st, tmQ, tmK, tmV, p))
+  (fused ? launch_t<F, NPV, true>(grid, st, tmQ, tmK, tmV, p) : launch_t<F, NPV, false>(grid, st, tmQ, tmK, tmV, p))
   if (n_slices == 2) {
     rc = f16 ? SC_T_LAUNCH(true, 1) : SC_T_LAUNCH(false, 1);
   } else {

@@ -423,11 +423,19 @@ def attn_hard_splits(Nq: int, Nks: int, device=None, bank: Optional[HardBank] = 
     return int(_lib.load().sc_attn_hard_splits(Nq, Nks, sms))
 
 
-def attn_splits(Nq: int, Nk: int, C_pad: int, device=None) -> int:
+def attn_splits(Nq: int, Nk: int, C_pad: int, device=None, D_pad: int = 0) -> int:
+    """Key splits of the dense-values kernel; with `D_pad` the choice is L2-blocked (sc_attn_splits_for)."""
     if _SPLITS_OVERRIDE > 0:
         return max(1, min(_SPLITS_OVERRIDE, -(-Nk // 128)))
     sms = torch.cuda.get_device_properties(device or torch.cuda.current_device()).multi_processor_count
+    if D_pad > 0:
+        return int(_lib.load().sc_attn_splits_for(Nq, Nk, D_pad, C_pad, sms))
     return int(_lib.load().sc_attn_splits(Nq, Nk, C_pad, sms))
+
+
+# fp32 partial tiles of one dense-values launch are bounded by chunking the queries (an L2-blocked launch has ~80 key
+# splits at the ImageNet size: 16 GB of [splits, Nq, C] tiles for 50 000 x 1000, which is allowed in one piece)
+_MAX_PARTIAL_BYTES = 20 << 30
 
 
 def merge_partials(parts: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -473,7 +481,19 @@ def attn_fwd(Qn: torch.Tensor, Kn: torch.Tensor, Vt: torch.Tensor, n_keys: int, 
     assert Kn.shape[1] == D_pad and Kn.shape[0] >= n_keys
     C_pad, Nk_pad = Vt.shape
     if splits <= 0:
-        splits = attn_splits(Nq, n_keys, C_pad, Qn.device)
+        splits = attn_splits(Nq, n_keys, C_pad, Qn.device, D_pad=D_pad)
+    if merge and splits > 1 and splits * Nq * n_cols * 4 > _MAX_PARTIAL_BYTES:
+        # query chunks of whole 128-row tiles whose partial tiles fit the bound; each chunk re-reads the bank once
+        rows = _MAX_PARTIAL_BYTES // (splits * n_cols * 4)
+        wave = 128 * max(1, torch.cuda.get_device_properties(Qn.device).multi_processor_count // 4)   # one wave of clusters
+        rows = max(128, rows // wave * wave if rows >= wave else rows // 128 * 128)
+        out = torch.empty((Nq, n_cols), dtype=torch.float32, device=Qn.device)
+        for s0 in range(0, Nq, rows):
+            s1 = min(Nq, s0 + rows)
+            part = attn_fwd(Qn[s0:s1], Kn, Vt, n_keys, n_cols, beta, splits=splits, merge=False,
+                            row_shift=row_shift[s0:s1].contiguous() if row_shift is not None else None)
+            merge_partials(part, out=out[s0:s1])
+        return out
     O = torch.empty((splits, Nq, n_cols), dtype=torch.float32, device=Qn.device)
     if row_shift is not None:
         row_shift = _cuda(row_shift, "row_shift")

@@ -237,8 +237,6 @@ class ClipSearcher:
                     splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
                 part = ops.attn_fwd_hard(qn, self.hard_bank, beta, splits=splits)
             else:
-                if splits <= 0:
-                    splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
                 part = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, n_cols, beta, splits=splits, merge=True)
             self.gpu_launches += 1 + int(splits > 1)
         else:
@@ -262,9 +260,8 @@ class ClipSearcher:
             self.gpu_launches += 3
             return ops.softmax_partials(lse)
         rowmax = ops.attn_rowmax(qn, self.k_norm, self.n_keys)
-        splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
-        o = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, c + 1, tau, splits=splits, merge=True, row_shift=rowmax)
-        self.gpu_launches += 4 + int(splits > 1)
+        o = ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, c + 1, tau, merge=True, row_shift=rowmax)
+        self.gpu_launches += 5
         out, m, l = ops.merge_softmax(o[None, :, :c], rowmax[None], o[None, :, c].contiguous(),
                                       m_scale=float(tau) * 1.4426950408889634, normalize=False)
         return out, m, l
@@ -347,10 +344,9 @@ class ClipSearcher:
             splits = ops.attn_hard_splits(nq, self.hard_bank.n_sorted, self.device, bank=self.hard_bank)
             outs = ops.attn_fwd_hard_multi(qn, self.hard_bank, betas, splits=splits, merge=False)
             self.gpu_launches += -(-len(betas) // 4)
-        else:
-            splits = ops.attn_splits(nq, self.n_keys, self.vt.shape[0], self.device)
-            outs = [ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, self.n_classes, b, splits=splits, merge=False) for b in betas]
-            self.gpu_launches += len(betas)
+        else:       # dense values: L2-blocked key splits, summed per query chunk inside attn_fwd (bounded partial tiles)
+            outs = [ops.attn_fwd(qn, self.k_norm, self.vt, self.n_keys, self.n_classes, b, merge=True) for b in betas]
+            self.gpu_launches += 2 * len(betas)
         self._mark("attention", t0)
         return outs
 
