@@ -59,6 +59,9 @@ const char* sc_last_error(void);
 int64_t sc_pad_dim(int64_t D);          /* multiple of 64 */
 int64_t sc_pad_dim_op(int64_t D, int op_dtype);  /* row length for an operand type: 128-byte chunks (64 16-bit / 128 e4m3) */
 int64_t sc_pad_keys(int64_t Nk);        /* multiple of 8  */
+int64_t sc_pad_queries(int64_t Nq);     /* multiple of 256: rows the QUERY operand of sc_attn_fwd_hard[_multi], sc_attn_softmax_hard
+                                           and sc_attn_rowmax must have allocated (rows Nq .. pad-1: any finite values, e.g.
+                                           zeros; they are read, never written or reported) */
 int64_t sc_pad_classes(int64_t C);      /* n_slices * slice width (2 or 4k slices; width a multiple of 16, <= 256) */
 int64_t sc_class_slice(int64_t C);      /* slice width the kernel uses for C classes */
 
@@ -188,6 +191,8 @@ int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, int64_t N, i
  * With one-hot values W @ V is a per-class segmented row sum of the weights.  The caller permutes the
  * normalised bank once so that keys of one class are adjacent and every class segment starts on a 16-key
  * boundary (padding rows: anything finite, e.g. zeros):
+ *   Qn          [sc_pad_queries(Nq), D_pad]   the normalised queries in whole 256-row tiles (rows >= Nq: finite padding;
+ *                                             a partly out-of-bounds TMA box costs a single-tile launch 30 % of its HBM rate);
  *   Ks          [Nks, D_pad]                  the permuted, padded bank (op_dtype);
  *   group_class int16  [ceil(Nks/256) * 16]   class of every 16-key group, -1 = no real key in it;
  *   key_bits    uint32 [ceil(Nks/256) * 8]    bit j of word w = 1 iff sorted key 32 w + j is a real key

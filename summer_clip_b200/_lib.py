@@ -24,6 +24,7 @@ SIGNATURES = {
     "sc_pad_dim": (c_int64, [c_int64]),
     "sc_pad_dim_op": (c_int64, [c_int64, c_int]),
     "sc_pad_keys": (c_int64, [c_int64]),
+    "sc_pad_queries": (c_int64, [c_int64]),
     "sc_pad_classes": (c_int64, [c_int64]),
     "sc_class_slice": (c_int64, [c_int64]),
     "sc_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,

@@ -165,6 +165,7 @@ int sc_attn_splits(int64_t Nq, int64_t Nk, int64_t C_pad, int sm_count) {
   return best;
 }
 
+int64_t sc_pad_queries(int64_t Nq) { return sc::round_up(Nq > 0 ? Nq : 1, 2 * kBM); }
 int64_t sc_pad_labels(int64_t Nk) { return sc::round_up(Nk > 0 ? Nk : 1, kBN); }
 
 int sc_attn_hard_supported(int64_t n_classes) { return (n_classes > 0 && n_classes <= 32767) ? 1 : 0; }

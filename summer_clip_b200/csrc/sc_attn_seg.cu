@@ -669,11 +669,15 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
   CUtensorMap tmQ, tmK;
   int rc;
   const bool f8 = (op_dtype == SC_E4M3), f16 = (op_dtype == SC_F16);
+  // The query operand is mapped over WHOLE 256-row tiles (the caller allocates sc_pad_queries(Nq) rows): a TMA box
+  // that is partly out of bounds is filled row by row and a single-tile launch then streams the bank at 3.7 instead
+  // of 5.5 TB/s (measured, tools/probes/probe_small_batch.py: 1 query 0.64 -> 0.49 ms, 8 queries 0.71 -> 0.47 ms)
+  const int64_t nq_rows = round_up(Nq, 2 * kBQ);
   if (f8) {                                                                                 // 128 rows x 128 e4m3
-    if ((rc = make_tmap_u8(&tmQ, Qn, Nq, D_pad, D_pad, kBQ)) != SC_OK) return rc;
+    if ((rc = make_tmap_u8(&tmQ, Qn, nq_rows, D_pad, D_pad, kBQ)) != SC_OK) return rc;
     if ((rc = make_tmap_u8(&tmK, Ks, Nks, D_pad, D_pad, kBKeys)) != SC_OK) return rc;
   } else {
-    if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;        // 128 queries x 64 d
+    if ((rc = make_tmap(&tmQ, Qn, nq_rows, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;   // 128 queries x 64 d
     if ((rc = make_tmap(&tmK, Ks, Nks, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;    // 128 keys x 64 d
   }
   SParams p = {};
@@ -791,11 +795,12 @@ int attn_rowmax_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int6
   CUtensorMap tmQ, tmK;
   int rc;
   const bool f8 = (op_dtype == SC_E4M3), f16 = (op_dtype == SC_F16);
+  const int64_t nq_rows = round_up(Nq, 2 * kBQ);          // whole query tiles, as in attn_seg_launch
   if (f8) {
-    if ((rc = make_tmap_u8(&tmQ, Qn, Nq, D_pad, D_pad, kBQ)) != SC_OK) return rc;
+    if ((rc = make_tmap_u8(&tmQ, Qn, nq_rows, D_pad, D_pad, kBQ)) != SC_OK) return rc;
     if ((rc = make_tmap_u8(&tmK, Kn, Nk, D_pad, D_pad, kBKeys)) != SC_OK) return rc;
   } else {
-    if ((rc = make_tmap(&tmQ, Qn, Nq, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;
+    if ((rc = make_tmap(&tmQ, Qn, nq_rows, D_pad, D_pad, kBQ, f16)) != SC_OK) return rc;
     if ((rc = make_tmap(&tmK, Kn, Nk, D_pad, D_pad, kBKeys, f16)) != SC_OK) return rc;
   }
   SParams p = {};

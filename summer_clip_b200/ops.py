@@ -61,6 +61,23 @@ def pad_dim(D: int, op_dtype: Optional[torch.dtype] = None) -> int:
     return int(_lib.load().sc_pad_dim(D))
 
 
+def pad_queries(Nq: int) -> int:
+    return int(_lib.load().sc_pad_queries(Nq))
+
+
+def _tile_padded(Qn: torch.Tensor) -> torch.Tensor:
+    """Qn with at least sc_pad_queries(Nq) rows ALLOCATED behind its first row (what `normalize_cast` returns, and any
+    row slice that is not at the end of such a tensor); otherwise a zero-padded copy."""
+    Nq, D_pad = Qn.shape
+    need = (pad_queries(Nq) * D_pad + Qn.storage_offset()) * Qn.element_size()
+    if Qn.is_contiguous() and Qn.untyped_storage().nbytes() >= need:
+        return Qn
+    buf = torch.empty((pad_queries(Nq), D_pad), dtype=Qn.dtype, device=Qn.device)
+    buf[Nq:].view(torch.uint8).zero_()
+    buf[:Nq].copy_(Qn)
+    return buf[:Nq]
+
+
 def pad_keys(Nk: int) -> int:
     return int(_lib.load().sc_pad_keys(Nk))
 
@@ -91,7 +108,13 @@ def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Ten
     op_dtype = _op(op_dtype if out is None else out.dtype, allow_e4m3=True)
     D_pad = pad_dim(D, op_dtype)
     if out is None:
-        out = torch.empty((n_out, D_pad), dtype=op_dtype, device=x.device)
+        # whole 256-row tiles are allocated (zero padding rows) and the first n_out rows returned: the attention
+        # kernels map their query operand over whole tiles (sc_pad_queries)
+        rows = pad_queries(n_out)
+        buf = torch.empty((rows, D_pad), dtype=op_dtype, device=x.device)
+        if rows > n_out:
+            buf[n_out:].view(torch.uint8).zero_()
+        out = buf[:n_out]
     else:
         assert out.is_cuda and out.is_contiguous() and out.shape[1] == D_pad and out.shape[0] >= n_out
         # the library writes through the raw pointer: tell torch, so that caches keyed on the tensor's version
@@ -358,6 +381,7 @@ def attn_fwd_hard(Qn: torch.Tensor, bank: HardBank, beta: float, splits: int = 0
     Ks = bank.rows
     assert Ks is not None, "HardBank.gather(k_norm) must be called first"
     assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16, E4M3) and Ks.is_contiguous() and Qn.is_contiguous()
+    Qn = _tile_padded(Qn)
     Nq, D_pad = Qn.shape
     assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
     n_classes = bank.n_classes
@@ -385,6 +409,7 @@ def attn_fwd_hard_multi(Qn: torch.Tensor, bank: HardBank, betas: Sequence[float]
     Ks = bank.rows
     assert Ks is not None, "HardBank.gather(k_norm) must be called first"
     assert Ks.dtype == Qn.dtype and Qn.dtype in (torch.float16, torch.bfloat16, E4M3) and Ks.is_contiguous() and Qn.is_contiguous()
+    Qn = _tile_padded(Qn)
     Nq, D_pad = Qn.shape
     assert Ks.shape[1] == D_pad and Ks.shape[0] >= bank.n_sorted
     n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)
@@ -513,6 +538,7 @@ def attn_rowmax(Qn: torch.Tensor, Kn: torch.Tensor, n_keys: int) -> torch.Tensor
     """fp32 [Nq]: max_k Qn[q].Kn[k] over the first n_keys rows of Kn (tensor-core pass, nothing materialised)."""
     _cuda(Qn, "Qn"), _cuda(Kn, "Kn")
     assert Qn.dtype == Kn.dtype and Qn.is_contiguous() and Kn.is_contiguous() and Kn.shape[1] == Qn.shape[1]
+    Qn = _tile_padded(Qn)
     out = torch.empty(Qn.shape[0], dtype=torch.float32, device=Qn.device)
     with torch.cuda.device(Qn.device):
         check(_lib.load().sc_attn_rowmax(_ptr(Qn), _ptr(Kn), _code(Qn), Qn.shape[0], int(n_keys), Qn.shape[1], _ptr(out),
@@ -527,6 +553,7 @@ def attn_softmax_hard(Qn: torch.Tensor, bank: HardBank, tau: float, splits: int 
     Ks = bank.rows
     assert Ks is not None, "HardBank.gather(k_norm) must be called first"
     assert Ks.dtype == Qn.dtype and Ks.is_contiguous() and Qn.is_contiguous() and Ks.shape[1] == Qn.shape[1]
+    Qn = _tile_padded(Qn)
     Nq, D_pad = Qn.shape
     n_classes, n_sorted = bank.n_classes, max(bank.n_sorted, 1)
     if splits <= 0:
