@@ -25,6 +25,8 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+LATENCY_BATCHES = (1, 8, 64, 256, 1024, 4096)
+
 WORKLOADS = {
     # name: (Nq, Nk, D, C, description)
     "imagenet_rn50": (50000, 1281167, 1024, 1000, "cfg3 ImageNet CLIP-search RN50: 50k val x 1.28M train keys x 1024-d, 1000 classes, hard values, beta=5.5, alpha=1"),
@@ -32,6 +34,7 @@ WORKLOADS = {
     "tip_imagenet_16shot": (50000, 16000, 1024, 1000, "cfg2 Tip-Adapter ImageNet 16-shot cache head"),
     "sun397": (19850, 19850, 1024, 397, "cfg1 SUN397-shaped image attention"),
     "tiny": (2048, 16384, 256, 100, "smoke-sized"),
+    "latency": (4096, 1281167, 1024, 1000, "cfg5 online classification latency: query batch 1-4096 against the 1.28M-key RN50 bank"),
 }
 BETA, ALPHA = 5.5, 1.0
 
@@ -487,6 +490,102 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_latency(args):
+    """`--workload latency` (BASELINE.json configs[4]): host-observed latency of ClipSearcher.search for query batches
+    of 1 .. 4096 against the resident 1.28M-key bank (queries on the device, predictions copied back), eager and
+    replayed from a CUDA graph; N > 1 ranks shard the keys.  One JSON line; `value` = graph-replayed p50 at batch 64."""
+    import torch
+    import torch.distributed as dist
+
+    from summer_clip_b200 import build as _build
+    from summer_clip_b200.searcher import ClipSearcher, shard_range
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CLIP-search path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    if rank == 0:
+        _build.build_library()
+    if world > 1:
+        dist.barrier()
+    nq, nk, dim, n_classes, desc = WORKLOADS["latency"]
+    lo, hi = shard_range(nk, rank, world) if world > 1 else (0, nk)
+    q_bank, k_bank, outs, text, labels = make_banks(torch, nq, lo, hi, dim, n_classes, seed=5, device=dev)
+    s = ClipSearcher(dev, group=group, shard="keys")
+    s.set_text(text)
+    s.set_cache(k_bank, outs, local_shard=world > 1)
+    del k_bank, outs
+    bank_bytes = 2.0 * dim * (s.hard_bank.n_sorted if s.hard_bank is not None else (hi - lo))
+    iters = max(10, args.steps * 4)
+    rows = []
+
+    def timed(fn):
+        lat = []
+        for _ in range(iters + 3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = sorted(lat[3:])
+        return lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))], out
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for b in LATENCY_BATCHES:
+        qb, lab = q_bank[:, :b].contiguous(), labels[:b].contiguous()
+        p50, p99, pred = timed(lambda: s.search(qb, [BETA], [ALPHA], labels=lab)[0]["pred"].cpu())
+        g50 = g99 = None
+        same = None
+        try:
+            graph, gres = s.capture_search(qb, [BETA], [ALPHA], labels=lab)
+
+            def replay():
+                graph.replay()
+                return gres[0]["pred"].cpu()
+
+            g50, g99, gpred = timed(replay)
+            same = bool((gpred == pred).all())
+            del graph, gres
+        except Exception as exc:  # noqa: BLE001
+            same = f"{type(exc).__name__}: {exc}"[:120]
+        if world > 1:
+            t = torch.tensor([p50, p99, g50 if g50 is not None else -1.0, g99 if g99 is not None else -1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p50, p99 = float(t[0]), float(t[1])
+            g50, g99 = (float(t[2]), float(t[3])) if g50 is not None else (None, None)
+        best = g50 if g50 is not None else p50
+        rows.append({"batch": b, "p50_ms": round(p50, 4), "p99_ms": round(p99, 4), "graph_p50_ms": None if g50 is None else round(g50, 4),
+                     "graph_p99_ms": None if g99 is None else round(g99, 4), "graph_same_pred": same,
+                     "queries_per_s": b / (best * 1e-3), "bank_gbs_per_gpu": bank_bytes / (best * 1e-3) / 1e9})
+    clocks = sampler.stop()
+    if rank == 0:
+        peaks = read_peaks()
+        at64 = next(r for r in rows if r["batch"] == 64)
+        v = at64["graph_p50_ms"] if at64["graph_p50_ms"] is not None else at64["p50_ms"]
+        out = {"metric": "clip_search_latency_p50_ms", "value": v, "unit": "ms", "n_gpus": world, "steps": iters, "warmup": 3,
+               "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+               "data": "synthetic",
+               "config": {"workload": "latency", "description": desc, "n_keys": nk, "dim": dim, "n_classes": n_classes, "beta": BETA,
+                          "alpha": ALPHA, "value_is": "p50 of a CUDA-graph replay of ClipSearcher.search at batch 64, predictions copied to the host",
+                          "sharding": f"key-sharded x{world}" if world > 1 else "single GPU"},
+               "latency": rows,
+               "roofline": {"bound": "hbm", "achieved": at64["bank_gbs_per_gpu"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": at64["bank_gbs_per_gpu"] / peaks["hbm_gbs"], "traffic": None,
+                            "note": "bank bytes of this GPU's shard / host-observed p50 at batch 64 (includes launch latency and the D2H of the predictions)"},
+               "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 CPU_SAMPLE = (1024, 131072)       # queries x keys of the bounded CPU sample, the same in both arms
 
 
@@ -590,6 +689,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "latency":
+        run_latency(args)
     else:
         run_ours(args)
 

@@ -215,16 +215,29 @@ class ClipSearcher:
         return True
 
     # ------------------------------------------------------------------ queries
-    def prepare_queries(self, test_image_features: torch.Tensor, feature_major: bool = True):
-        """H2D (if needed) + normalise/cast + zero-shot logits.  Returns (Qn, Z or None)."""
+    def prepare_queries(self, test_image_features: torch.Tensor, feature_major: bool = True, overlap: bool = False):
+        """H2D (if needed) + normalise/cast + zero-shot logits.  Returns (Qn, Z or None[, event]).  `overlap`: the
+        zero-shot GEMM (independent of the attention) is issued on the side stream FIRST — it takes a handful of SMs
+        for ~10 us while the attention CTAs fill the rest — and the third return value is the event the consumer
+        of Z must wait for (small batches: ~20 us less on a 0.5 ms search)."""
         q = test_image_features.to(self.device, non_blocking=True)
+        z, evz = None, None
+        if self.text is not None and overlap:
+            main, side = torch.cuda.current_stream(self.device), self._side_stream()
+            start = torch.cuda.Event()
+            start.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(start)
+                z = ops.zero_shot_logits(q, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
+                evz = torch.cuda.Event()
+                evz.record(side)
+            self.gpu_launches += 2
         qn = ops.normalize_cast(q, feature_major=feature_major, op_dtype=self.op_dtype)
         self.gpu_launches += 1
-        z = None
-        if self.text is not None:
+        if self.text is not None and not overlap:
             z = ops.zero_shot_logits(q, feature_major, self.text, scale=100.0, normalize=True, t_split=self.text_split)
-            self.gpu_launches += 1
-        return qn, z
+            self.gpu_launches += 2
+        return (qn, z, evz) if overlap else (qn, z)
 
     def local_cache_logits(self, qn: torch.Tensor, beta: float, splits: int = 0) -> torch.Tensor:
         """O_r = exp(-beta (1 - Qn Kn^T)) @ V over THIS rank's keys: fp32 [Nq, C]."""
@@ -319,11 +332,14 @@ class ClipSearcher:
         if self.world > 1:
             return self._search_sharded(test_image_features, betas, alphas, labels, feature_major, want_logits, want_pred,
                                         query_shard, blocks)
-        qn, z = self.prepare_queries(test_image_features, feature_major)
+        qn, z, evz = self.prepare_queries(test_image_features, feature_major, overlap=True)
         if labels is not None:
             labels = labels.to(self.device, non_blocking=True)
         results = []
-        for beta, o in zip(betas, self._local_parts_many(qn, betas, merge=want_cache_logits)):
+        parts = self._local_parts_many(qn, betas, merge=want_cache_logits)
+        if evz is not None:
+            torch.cuda.current_stream(self.device).wait_event(evz)
+        for beta, o in zip(betas, parts):
             res = ops.epilogue(z, o, alphas, labels=labels, want_logits=want_logits, want_pred=want_pred)
             self.gpu_launches += 1
             res["beta"] = float(beta)
