@@ -194,24 +194,35 @@ class ClipSearcher:
         self.gpu_launches += 2 + int(softmax_normalize)
 
     def save_bank(self, directory, key: str = ""):
-        """Write the resident label-sorted bank as a sidecar directory (bank_io.save_hard_bank)."""
+        """Write the resident cache as a sidecar directory (bank_io): the label-sorted bank of a one-hot cache, or the
+        normalised keys + transposed values of a dense-value cache."""
         from . import bank_io
-        if self.hard_bank is None:
-            raise ops._lib.SummerClipError("save_bank: only one-hot (label-sorted) caches have a sidecar format")
-        return bank_io.save_hard_bank(self.hard_bank, directory, key)
+        if self.hard_bank is not None:
+            return bank_io.save_hard_bank(self.hard_bank, directory, key)
+        if self.k_norm is None or self.vt is None:
+            raise ops._lib.SummerClipError("save_bank: no resident cache")
+        if self.softmax:
+            raise ops._lib.SummerClipError("save_bank: temperature-softmax caches are rebuilt from their sources")
+        return bank_io.save_dense_bank(self.k_norm, self.vt, self.n_keys, self.n_classes, directory, key)
 
     def load_bank(self, directory, key: tp.Optional[str] = None) -> bool:
-        """Make a sidecar bank resident instead of calling set_cache.  False (nothing changed) if it is absent or
-        was built for another key."""
+        """Make a sidecar bank resident instead of calling set_cache.  False (nothing changed) if it is absent, of
+        another operand type or was built for another key."""
         from . import bank_io
         bank = bank_io.load_hard_bank(directory, self.device, key)
-        if bank is None:
+        if bank is not None:
+            if bank.rows.dtype != self.op_dtype:
+                return False
+            self.hard_bank, self.k_norm, self.vt, self.rowsum_col, self.softmax = bank, None, None, None, False
+            self.n_keys = self.n_keys_global = bank.n_keys
+            self.n_classes = bank.n_classes
+            return True
+        dense = bank_io.load_dense_bank(directory, self.device, key)
+        if dense is None or dense[0].dtype != self.op_dtype:
             return False
-        if bank.rows.dtype != self.op_dtype:
-            return False
-        self.hard_bank, self.k_norm, self.vt, self.rowsum_col, self.softmax = bank, None, None, None, False
-        self.n_keys = self.n_keys_global = bank.n_keys
-        self.n_classes = bank.n_classes
+        self.k_norm, self.vt, self.n_keys, self.n_classes = dense
+        self.hard_bank, self.rowsum_col, self.softmax = None, None, False
+        self.n_keys_global = self.n_keys
         return True
 
     # ------------------------------------------------------------------ queries

@@ -565,3 +565,27 @@ def test_kernels_stay_inside_their_output_buffers(ops):
     _lib.check(lib.sc_attn_rowmax(ptr(Qn), ptr(Kn), 0, nq, nk, Qn.shape[1], ptr(rm), stream), "rowmax")
     assert guards_ok(buf, rm, nq)
     torch.testing.assert_close(rm[0, 0, :nq], A.amax(1), rtol=0, atol=2e-6)
+
+
+def test_dense_value_sidecar_and_streamed_load_vs_oracle(ops, tmp_path, monkeypatch):
+    """A SoftmaxCacheStrategy cache written by save_bank and streamed back (several pinned staging pieces) answers
+    like the oracle; so does a query-bank sidecar."""
+    from summer_clip_b200 import bank_io
+    from summer_clip_b200.searcher import ClipSearcher
+    monkeypatch.setattr(bank_io, "_STAGE_BYTES", 1 << 16)              # force many pieces through the two staging buffers
+    banks = orc.synthetic_banks(200, 2500, 256, 40, seed=88, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+    Q, K, L, T = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs", "text_features"))
+    a = ClipSearcher("cuda")
+    a.set_cache(K, L, softmax_scale=orc.CLIP_SCALE * 0.1)
+    a.save_bank(tmp_path / "bank", key="k")
+    b = ClipSearcher("cuda")
+    b.set_text(T.float())
+    assert not b.load_bank(tmp_path / "bank", key="other") and b.load_bank(tmp_path / "bank", key="k")
+    assert torch.equal(a.k_norm, b.k_norm) and torch.equal(a.vt, b.vt)
+    res = b.search(Q, [5.5], [1.0], want_logits=True)[0]
+    O = orc.image_attention(Q.float(), K.float(), orc.softmax_values(L.float(), orc.CLIP_SCALE, 0.1), 5.5)
+    assert_logits_match(res["logits"][0], orc.searcher_logits(orc.zero_shot_logits(Q.float(), T.float()), O, 1.0), "dense sidecar")
+    qn = ops.normalize_cast(Q.cuda(), True)
+    bank_io.save_query_bank(qn, tmp_path / "q", "q", clip_logits=res["clip_logits"])
+    q2, z2 = bank_io.load_query_bank(tmp_path / "q", "cuda", "q")
+    assert torch.equal(q2, qn) and torch.equal(z2, res["clip_logits"])

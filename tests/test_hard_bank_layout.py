@@ -71,3 +71,21 @@ def test_sidecar_round_trip(tmp_path):
     back8 = bank_io.load_hard_bank(d8, "cpu", key8)
     assert back8 is not None and back8.rows.dtype == torch.float8_e4m3fn and back8.rows.shape == bank.rows.shape
     assert torch.equal(back8.rows.view(torch.uint8), bank.rows.view(torch.uint8))
+
+
+def test_dense_and_query_sidecars_round_trip(tmp_path):
+    """bank_io: dense-value caches (keys + transposed values) and query banks (rows + zero-shot logits) survive
+    save -> load bit for bit; kinds and keys are not confused."""
+    from summer_clip_b200 import bank_io
+    g = torch.Generator().manual_seed(10)
+    k, vt = torch.randn(300, 64, generator=g).half(), torch.rand(48, 304, generator=g).half()
+    d = bank_io.save_dense_bank(k, vt, 300, 40, tmp_path / "dense", "k1")
+    back = bank_io.load_dense_bank(d, "cpu", "k1")
+    assert back is not None and back[2:] == (300, 40)
+    assert back[0].dtype == torch.float16 and torch.equal(back[0], k) and torch.equal(back[1], vt)
+    assert bank_io.load_dense_bank(d, "cpu", "k2") is None and bank_io.load_hard_bank(d, "cpu", "k1") is None
+    q, z = torch.randn(77, 64, generator=g).bfloat16(), torch.randn(77, 40, generator=g)
+    dq = bank_io.save_query_bank(q, tmp_path / "queries", "q1", clip_logits=z)
+    qb, zb = bank_io.load_query_bank(dq, "cpu", "q1")
+    assert qb.dtype == torch.bfloat16 and torch.equal(qb, q) and torch.equal(zb, z)
+    assert bank_io.load_query_bank(tmp_path / "dense", "cpu") is None
