@@ -16,6 +16,9 @@ PY
 }
 $TR bench.py --gpus $N --steps 10 --warmup 3 --phases > gpurun_out/${tag}_bench_n${N}_keys.json 2> gpurun_out/${tag}_bench_n${N}_keys.err; summ gpurun_out/${tag}_bench_n${N}_keys.json
 SUMMER_CLIP_B200_EXCHANGE=nccl SC_BENCH_BLOCKS=1 $TR bench.py --gpus $N --steps 10 --warmup 3 --phases --no-parity-check > gpurun_out/${tag}_bench_n${N}_keys_nccl_b1.json 2> gpurun_out/${tag}_bench_n${N}_keys_nccl_b1.err; summ gpurun_out/${tag}_bench_n${N}_keys_nccl_b1.json
-SC_BENCH_BLOCKS=2 $TR bench.py --gpus $N --steps 10 --warmup 3 --phases --no-parity-check > gpurun_out/${tag}_bench_n${N}_keys_b2.json 2> gpurun_out/${tag}_bench_n${N}_keys_b2.err; summ gpurun_out/${tag}_bench_n${N}_keys_b2.json
+$TR bench.py --gpus $N --workload latency > gpurun_out/${tag}_latency_n${N}.json 2> gpurun_out/${tag}_latency_n${N}.err; python -c "
+import json
+d=json.loads(open('gpurun_out/${tag}_latency_n${N}.json').read().strip().splitlines()[-1])
+print('latency', d['value'], [(r['batch'], r['p50_ms'], r['graph_p50_ms']) for r in d['latency']])" || tail -5 gpurun_out/${tag}_latency_n${N}.err
 $TR bench.py --gpus $N --steps 10 --warmup 3 --phases --shard queries > gpurun_out/${tag}_bench_n${N}_queries.json 2> gpurun_out/${tag}_bench_n${N}_queries.err; summ gpurun_out/${tag}_bench_n${N}_queries.json
 $TR bench.py --gpus $N --steps 5 --warmup 3 --phases --values softmax > gpurun_out/${tag}_bench_n${N}_keys_softvalues.json 2> gpurun_out/${tag}_bench_n${N}_keys_softvalues.err; summ gpurun_out/${tag}_bench_n${N}_keys_softvalues.json
