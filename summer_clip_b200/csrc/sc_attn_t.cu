@@ -399,7 +399,9 @@ sc_attn_t_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) {
         if (is_leader) mbar_arrive(smem_u32(&bars->s_empty[b]));
-        else mbar_arrive_cluster(smem_u32(&bars->s_empty[b]), leader);
+        else mbar_arrive_cluster_relaxed(smem_u32(&bars->s_empty[b]), leader);   // hands the S buffer back: publishes no
+                                                                                  // memory (the TMEM reads completed at
+                                                                                  // tcgen05.wait::ld), so no MEMBAR
       }
       if (has_tile) ++sent;
       ++own;

@@ -71,3 +71,59 @@ def test_host_rng_strategies_reproduce_the_reference_stream(strat, k):
     np.random.seed(42)
     got = PerGoldClassRandomSampleStrategy(k, cache_labels=gold).select(feats, outs).numpy()
     assert np.array_equal(got, strat[f"per_gold_random_{k}"])
+
+
+def test_hydra_defaults_composition_of_the_hot_path_config_tree():
+    """utils/config.compose: the defaults list of conf/image_attention.yaml (sibling configs, group: option,
+    group@package: option, nested /group, _self_), ${...} interpolation, key=value and group=option overrides."""
+    from pathlib import Path
+    from summer_clip_b200.utils.config import compose
+    conf = Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf"
+    cfg = compose(conf, "image_attention")
+    assert list(cfg.cache_strategies) == ["topk", "topk_prob", "topk_per_gold", "topk_prob_per_gold", "per_pred_class_random",
+                                          "per_gold_class_random", "global_random", "all_logits"]
+    assert cfg.cache_value_strategy["_target_"].endswith("HardCacheStrategy")
+    assert cfg.cache_weights_strategy.beta == [0.1, 1.0, 1.5, 3.5, 5.5, 7.5, 9.5, 11.5]
+    assert cfg.dataset_name == "sun397" and cfg.prompting == cfg.dataset_cfg.prompting          # nested /prompting lands in dataset_cfg
+    assert cfg.data.image_features_path == cfg.saved_paths.image_features["SUN397_tip_test-RN50"]
+    assert cfg.cache.dataset.split == "train" and cfg.dataset.split == "test" and cfg.cache.dataset.dataset == "sun397"
+    assert cfg.cache_strategies.topk_per_gold.cache_dataset == [cfg.cache.dataset]              # ${cache.dataset} keeps its type
+    assert cfg.meta.random_state == 42 and cfg.cache.alpha[-1] == 4.0
+    over = compose(conf, "image_attention", ["cache_value_strategy=softmax_cache", "img_attn_dataset@dataset_cfg=imagenet",
+                                             "cache.alpha=[1.0]", "cache_strategies.topk.topk=[16]", "run_dir=/tmp/x"])
+    assert over.cache_value_strategy.scale == [0.1, 1.0, 10.0, 20.0] and over.dataset_name == "imagenet"
+    assert over.cache.image_outs_path == over.saved_paths.logits["ImageNet_train-RN50-tip_adapter"]
+    assert over.cache.alpha == [1.0] and over.cache_strategies.topk.topk == [16] and over.run_dir == "/tmp/x"
+    tip = compose(conf, "tip_adapter_imagenet", ["search_step=[20,5]"])
+    assert tip.search_scale == [7, 3] and tip.search_step == [20, 5] and tip.init_beta == 5.5 and tip.shots == 16
+    assert compose(conf, "tip_adapter").search_scale == [20, 10]
+
+
+def test_reference_yaml_tree_composes_unmodified():
+    """The reference's own conf/ directory (dev container only) through the same composer: same key structure as the
+    package's tree apart from the four file inputs this path adds."""
+    from pathlib import Path
+    from summer_clip_b200.utils.config import compose
+    ref = Path("/root/reference/summer_clip/conf")
+    if not ref.exists():
+        pytest.skip("reference tree not present (GPU box)")
+    ours = compose(Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf", "image_attention")
+    theirs = compose(ref, "image_attention")
+
+    def keys(d, pre=""):
+        out = set()
+        for k, v in d.items():
+            out.add(pre + k)
+            if isinstance(v, dict) and not pre.startswith(("saved_paths", "hydra")):
+                out |= keys(v, pre + k + ".")
+        return out
+    skip = ("saved_paths.", "hydra.")
+    a = {k for k in keys(ours) if not k.startswith(skip)}
+    b = {k for k in keys(theirs) if not k.startswith(skip)}
+    assert b <= a and a - b == {"cache.labels_path", "data.clip_logits_path", "data.labels_path", "data.text_features_path"}
+    assert theirs.cache_strategies.topk_prob == ours.cache_strategies.topk_prob
+    assert theirs.cache.alpha == ours.cache.alpha and theirs.cache_weights_strategy == ours.cache_weights_strategy
+    for name in ("tip_adapter", "tip_adapter_imagenet"):
+        t, o = compose(ref, name), compose(Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf", name)
+        for k in ("search_hp", "search_scale", "search_step", "init_beta", "init_alpha", "dataset", "shots", "backbone", "augment_epoch"):
+            assert t[k] == o[k], (name, k)
