@@ -1,7 +1,7 @@
 """BASELINE.json config 1 as the reference runs it: the default image_attention sweep (conf/image_attention.yaml)
 on a SUN397-shaped synthetic problem — 19 850 test x 19 850 unlabeled-train features, 1024-d, 397 classes; 25
-caches (TopK / TopKProb / per-class random / global random for k in 1..32, AllLogits) x 8 beta x 7 alpha = 1400
-accuracy records — through `ImageAttention` (one gather+normalise per cache, one attention launch per beta, one
+caches or more (TopK / TopKProb / per-class random / global random / per-gold for k in 1..32, AllLogits) x 8 beta x
+7 alpha accuracy records — through `ImageAttention` (one gather+normalise per cache, one attention launch per beta, one
 epilogue launch for all alphas).  Prints one JSON line: wall time of setup and of the sweep.
 
     python tools/bench_sweep.py
@@ -33,17 +33,25 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         tmp = Path(tmp)
         paths = {"q": tmp / "test_features.pt", "k": tmp / "train_features.pt", "l": tmp / "train_outs.pt",
-                 "t": tmp / "text.pt", "y": tmp / "labels.pt"}
+                 "t": tmp / "text.pt", "y": tmp / "labels.pt", "ky": tmp / "train_labels.pt"}
         torch.save(q_bank.cpu(), paths["q"])
         torch.save(k_bank.cpu(), paths["k"])
         torch.save(outs.cpu(), paths["l"])
         torch.save(text.cpu(), paths["t"])
         torch.save(labels.cpu(), paths["y"])
+        # gold labels of the train bank (the per-gold strategies and the cache-quality records need them): the
+        # zero-shot prediction, a quarter of them reassigned at random
+        g = torch.Generator(device=dev).manual_seed(7)
+        gold = outs.float().argmax(dim=1)
+        flip = torch.rand(nk, generator=g, device=dev) < 0.25
+        gold = torch.where(flip, torch.randint(0, c, (nk,), generator=g, device=dev), gold)
+        torch.save(gold.cpu(), paths["ky"])
         del q_bank, k_bank, outs
         conf = Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf" / "image_attention.yaml"
         cfg = load_config(conf, {"data": {"image_features_path": str(paths["q"]), "text_features_path": str(paths["t"]),
                                           "labels_path": str(paths["y"])},
-                                 "cache": {"image_features_path": str(paths["k"]), "image_outs_path": str(paths["l"])}})
+                                 "cache": {"image_features_path": str(paths["k"]), "image_outs_path": str(paths["l"]),
+                                           "labels_path": str(paths["ky"])}})
         times = []
         for rep in range(2):                                       # second repetition: warm allocator / page cache
             trainer = ImageAttention(cfg, tmp / f"run{rep}")
