@@ -46,18 +46,49 @@ bank_hist_kernel(const int16_t* __restrict__ labels, int64_t n_keys, int32_t C, 
   }
 }
 
-// thread per class: exclusive scan of its column over the chunks (in place), class total out
-__global__ void __launch_bounds__(256)
+// exclusive scan of every class column over the chunks (in place), class total out.  Block = 32 classes x 32 slices
+// of the chunk range: a thread sums its slice (independent, coalesced 128-byte loads), the 32 slice sums of a class
+// are scanned through shared memory, and the slice is rewritten with its running prefix.  (A thread per class walking
+// all 1252 chunks of the ImageNet bank serially took 0.32 ms on four SMs.)
+__global__ void __launch_bounds__(1024)
 bank_colscan_kernel(int32_t* __restrict__ counts, int64_t n_chunks, int32_t C, int64_t* __restrict__ totals) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  int32_t run = 0;
-  for (int64_t b = 0; b < n_chunks; ++b) {
-    const int32_t v = counts[b * C + c];
-    counts[b * C + c] = run;
-    run += v;
+  __shared__ int32_t part[32][33];
+  const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int64_t per = (n_chunks + 31) / 32;
+  const int64_t b0 = j * per, b1 = (b0 + per < n_chunks) ? b0 + per : n_chunks;
+  int32_t sum = 0;
+  if (c < C) {
+#pragma unroll 8
+    for (int64_t b = b0; b < b1; ++b) sum += counts[b * C + c];
   }
-  totals[c] = run;
+  part[j][cl] = sum;
+  __syncthreads();
+  if (j == 0) {
+    int32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int32_t v = part[i][cl];
+      part[i][cl] = run;
+      run += v;
+    }
+    if (c < C) totals[c] = run;
+  }
+  __syncthreads();
+  if (c < C) {
+    int32_t run = part[j][cl];
+    for (int64_t b = b0; b < b1; b += 8) {       // eight loads in flight, then the eight prefixes
+      int32_t v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (b + i < b1) ? counts[(b + i) * C + c] : 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (b + i < b1) {
+          counts[(b + i) * C + c] = run;
+          run += v[i];
+        }
+    }
+  }
 }
 
 // one block: seg_start[c] = sum_{c' < c} pad16(total[c']) (in place over totals), seg_start[C] = n_sorted
@@ -193,7 +224,7 @@ int sc_hard_bank_layout(const int16_t* labels16, int64_t n_keys, int32_t n_class
   SC_CUDA(cudaMemsetAsync(perm, 0xFF, static_cast<size_t>(capacity) * 8, st));            // -1
   SC_CUDA(cudaMemsetAsync(group_class, 0xFF, static_cast<size_t>(capacity / 16) * 2, st)); // -1
   if (n_keys > 0) bank_hist_kernel<<<static_cast<unsigned>(n_chunks), 256, 0, st>>>(labels16, n_keys, n_classes, w.counts);
-  bank_colscan_kernel<<<static_cast<unsigned>(sc::ceil_div(n_classes, 256)), 256, 0, st>>>(w.counts, n_chunks, n_classes,
+  bank_colscan_kernel<<<static_cast<unsigned>(sc::ceil_div(n_classes, 32)), 1024, 0, st>>>(w.counts, n_chunks, n_classes,
                                                                                           w.seg_start);
   bank_segscan_kernel<<<1, 1024, 0, st>>>(w.seg_start, n_classes, n_sorted);
   if (n_keys > 0)

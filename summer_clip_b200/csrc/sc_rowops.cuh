@@ -68,12 +68,12 @@ __device__ __forceinline__ uint32_t max_nan_x2<float>(uint32_t a, uint32_t) { re
 // of its 16-byte loads before the first use; vectors past the end of the row are filled with -inf, which is the
 // identity of every pass below (never the maximum unless the whole row is -inf, never equal to a finite
 // maximum, exp(scale * -inf - tmax) = 0 for scale > 0), so the passes run without per-vector predicates.
-// argmax(): max.NaN for the value (packed pairs for 16-bit storage: 0.5 instructions per element), then the FIRST
-// index at which it occurs: first_index() when one lane holds the maximum (the usual case: ~12 instructions per
-// row), else "last hit in reverse order" (3 per element) — instead of the ~20-instruction ordered compare per
-// element of sc::better(); rows that contain a NaN (the max comes back NaN) take the exact path.  Semantics are
-// those of row_argmax / torch.max(dim=1): larger value wins, NaN is largest, equal values -> smaller index.
-// argmax_expsum(): the same plus sum_c exp(scale l_c - scale l_max) from the registers.
+// argmax(): max.NaN for the value (packed pairs for 16-bit storage: 0.5 instructions per element), then "last hit
+// in reverse order" for the FIRST index at which it occurs (3 per element) — instead of the ~20-instruction
+// ordered compare per element of sc::better(); rows that contain a NaN (the max comes back NaN) take the exact
+// path.  Semantics are those of row_argmax / torch.max(dim=1): larger value wins, NaN is largest, equal values
+// -> smaller index.  argmax_expsum(): the index pass and sum_c exp(scale l_c - scale l_max) in ONE pass over the
+// registers (one conversion per element).
 template <typename T, int NV>
 struct RegRow {
   static constexpr int kN = 16 / sizeof(T);
@@ -98,8 +98,8 @@ struct RegRow {
   __device__ __forceinline__ int col(int u, int t) const { return (lane + 32 * u) * kN + t; }
   __device__ __forceinline__ float x(int u, int t) const { return to_f32<T>(reinterpret_cast<const T*>(&v[u])[t]); }
 
-  // this lane's maximum, NaN-propagating
-  __device__ __forceinline__ float lane_max() const {
+  // row maximum, NaN-propagating, reduced over the warp
+  __device__ __forceinline__ float max_value() const {
     float mx = __int_as_float(0xff800000);   // -inf
     if constexpr (sizeof(T) == 2) {
       uint32_t m2 = ninf_word();             // the maximum is exact in the storage type: take it pairwise there
@@ -119,55 +119,9 @@ struct RegRow {
         for (int t = 0; t < kN; ++t) mx = max_nan(mx, x(u, t));
       }
     }
-    return mx;
-  }
-  static __device__ __forceinline__ float warp_max_nan(float mx) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     return mx;
-  }
-  // row maximum, NaN-propagating, reduced over the warp
-  __device__ __forceinline__ float max_value() const { return warp_max_nan(lane_max()); }
-  // FIRST index at which the (NaN-free) row maximum mx occurs, per element: "last hit in reverse order"
-  __device__ __forceinline__ int scan_index(float mx) const {
-    int idx = 0x7fffffff;
-#pragma unroll
-    for (int u = NV - 1; u >= 0; --u) {
-#pragma unroll
-      for (int t = kN - 1; t >= 0; --t) idx = (x(u, t) == mx) ? col(u, t) : idx;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
-    return idx;
-  }
-  // The same index for ~12 instructions per ROW instead of 2 per element when exactly ONE lane holds the maximum
-  // (lane_mx == mx there): that lane parks its NV raw vectors in `park` (NV uint4 of shared memory owned by this
-  // warp), lane e tests element e, and a ballot gives the first.  Several holders (ties across lanes, the all -inf
-  // row) take the per-element scan; the branch is warp uniform.
-  __device__ __forceinline__ int first_index(float mx, float lane_mx, uint4* park) const {
-    const unsigned holders = __ballot_sync(0xffffffffu, lane_mx == mx);
-    if (__popc(holders) != 1) return scan_index(mx);
-    const int src = __ffs(holders) - 1;
-    __syncwarp();                            // the previous row's readers are done with `park`
-    if (lane == src) {
-#pragma unroll
-      for (int u = 0; u < NV; ++u) park[u] = v[u];
-    }
-    __syncwarp();
-    constexpr int kE = NV * kN;              // elements a lane holds, in ascending column order
-    const T* elems = reinterpret_cast<const T*>(park);
-    int idx = 0x7fffffff;
-#pragma unroll
-    for (int e0 = 0; e0 < kE; e0 += 32) {
-      const int e = e0 + lane;
-      const bool hit = e < kE && to_f32<T>(elems[e]) == mx;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (m != 0u && idx == 0x7fffffff) {
-        const int ee = e0 + __ffs(m) - 1;
-        idx = (src + 32 * (ee / kN)) * kN + ee % kN;
-      }
-    }
-    return idx;
   }
   // exact ordered compare for rows that contain a NaN (warp-uniform slow path)
   __device__ __forceinline__ MaxIdx argmax_exact() const {
@@ -184,23 +138,40 @@ struct RegRow {
   __device__ __forceinline__ MaxIdx argmax() const {
     const float mx = max_value();
     if (mx != mx) return argmax_exact();
-    return MaxIdx{mx, scan_index(mx)};
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int u = NV - 1; u >= 0; --u) {
+#pragma unroll
+      for (int t = kN - 1; t >= 0; --t) idx = (x(u, t) == mx) ? col(u, t) : idx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+    return MaxIdx{mx, idx};
   }
-  __device__ __forceinline__ MaxIdx argmax(uint4* park) const {
-    const float lmx = lane_max(), mx = warp_max_nan(lmx);
-    if (mx != mx) return argmax_exact();
-    return MaxIdx{mx, first_index(mx, lmx, park)};
-  }
-  // argmax(park) plus sum_c exp(scale * l_c - scale * l_max) (scale > 0).  The sum runs in reverse vector order
-  // within a lane, then the xor tree.
-  __device__ __forceinline__ MaxIdx argmax_expsum(float scale, float& sum, uint4* park) const {
-    const float lmx = lane_max(), mx = warp_max_nan(lmx);
+  // argmax() plus sum_c exp(scale * l_c - scale * l_max) (scale > 0) in one pass over the registers.  The sum
+  // runs in reverse vector order within a lane, then the xor tree.
+  __device__ __forceinline__ MaxIdx argmax_expsum(float scale, float& sum) const {
+    const float mx = max_value();
     if (mx != mx) {
       sum = mx;
       return argmax_exact();
     }
-    sum = expsum(scale, __fmul_rn(mx, scale));
-    return MaxIdx{mx, first_index(mx, lmx, park)};
+    const float tmax = __fmul_rn(mx, scale);
+    int idx = 0x7fffffff;
+    float s = 0.f;
+#pragma unroll
+    for (int u = NV - 1; u >= 0; --u) {
+#pragma unroll
+      for (int t = kN - 1; t >= 0; --t) {
+        const float xv = x(u, t);
+        idx = (xv == mx) ? col(u, t) : idx;
+        s += exp_neg_fast(__fmul_rn(xv, scale) - tmax);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) idx = min(idx, __shfl_xor_sync(0xffffffffu, idx, o));
+    sum = warp_sum(s);
+    return MaxIdx{mx, idx};
   }
   // sum_c exp(scale * l_c - tmax), scale > 0
   __device__ __forceinline__ float expsum(float scale, float tmax) const {

@@ -49,8 +49,6 @@ rowconf_reg_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, fl
                    float* __restrict__ conf, int32_t* __restrict__ label) {
   constexpr int kN = 16 / sizeof(T);
   constexpr int kRows = sizeof(T) == 2 ? 2 : 1;      // 16-bit rows are 2 KB: keep two of them in flight per warp
-  __shared__ uint4 park_s[8][NV];                    // RegRow::first_index: the row of the lane that holds the maximum
-  uint4* park = park_s[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int nv = static_cast<int>(C / kN);
   const int64_t warps_per_grid = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -70,10 +68,10 @@ rowconf_reg_kernel(const T* __restrict__ L, int64_t N, int64_t C, int64_t ld, fl
         float cf;
         if (mode == SC_CONF_PROB) {
           float sum;
-          m = row[i].argmax_expsum(scale, sum, park);
+          m = row[i].argmax_expsum(scale, sum);
           cf = 1.0f / sum;
         } else {
-          m = row[i].argmax(park);
+          m = row[i].argmax();
           cf = m.v;
         }
         if (lane == 0) {
