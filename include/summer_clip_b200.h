@@ -184,6 +184,12 @@ int sc_hard_bank_inverse(const int64_t* perm, int64_t n_sorted_rows, int64_t n_k
 int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
                          const int64_t* idx, int64_t n_out, const int64_t* dst_row, void* dst, int dst_dtype,
                          int64_t D_pad, int normalize, void* stream);
+/* sc_normalize_cast that also returns the inverse column norms: inv_norm[o] = 1 / |src[:, idx[o]]| (fp32, computed
+ * from the source values whether or not `normalize` is set).  normalize = 0 gives the transposed RAW bank plus the
+ * factors that normalise it later (sc_rowconf_from_rows). */
+int sc_transpose_norms(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
+                       const int64_t* idx, int64_t n_out, void* dst, int dst_dtype, int64_t D_pad, int normalize,
+                       float* inv_norm, void* stream);
 
 /* sc_attn_fwd for one-hot cache values on a LABEL-SORTED key bank (same result as sc_attn_fwd on
  * Vt = one_hot(label)^T; the sum over keys does not depend on their order):
@@ -292,6 +298,13 @@ int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void*
 int sc_rowconf_from_split(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t C,
                           int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
                           void* stream);
+/* The same for image features that are EXACT in fp16 (the reference's cached fp16 banks): A [M, D_pad] holds the
+ * RAW rows (sc_transpose_norms: transposed, not normalised) and row_scale[m] = 1 / |row m|, so there is no lo part
+ * and two operand passes suffice:  L[m, c] = scale * row_scale[m] * sum_d A[m,d] (Bh[c,d] + Bl[c,d]).
+ * row_scale may be NULL (rows already unit length and exact in fp16). */
+int sc_rowconf_from_rows(const void* A, const float* row_scale, const void* Bh, const void* Bl, int64_t M, int64_t C,
+                         int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
+                         void* stream);
 
 /* Epilogue (image_attention.py:111-112, clip_searcher/utils.py:15-21, tip_adapter/utils.py:10-15):
  * for every alpha a: out = Z + O * alpha  (O optionally divided by rowsum[q] first), prediction =

@@ -62,6 +62,8 @@ SIGNATURES = {
     "sc_hard_bank_inverse": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "sc_normalize_scatter": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                      c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "sc_transpose_norms": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int,
+                                   c_int64, c_int, c_void_p, c_void_p]),
     "sc_attn_hard_supported": (c_int, [c_int64]),
     "sc_attn_hard_splits": (c_int, [c_int64, c_int64, c_int]),
     "sc_attn_hard_splits_for": (c_int, [c_int64, c_int64, c_int64, c_int, c_int64, c_int, c_int]),
@@ -79,6 +81,8 @@ SIGNATURES = {
                                  c_void_p, c_int64, c_void_p]),
     "sc_rowconf_from_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,
                                       c_int, c_void_p, c_void_p, c_void_p]),
+    "sc_rowconf_from_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,
+                                     c_int, c_void_p, c_void_p, c_void_p]),
     "sc_epilogue": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, POINTER(c_float),
                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sc_epilogue_parts": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64,

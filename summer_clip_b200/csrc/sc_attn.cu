@@ -32,7 +32,8 @@ int attn_rowmax_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int6
                        float* rowmax, cudaStream_t st);
 int rowconf_fused_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                          const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
-                         int64_t D_pad, float scale, float prob_scale, int prob, float* conf, int* label, cudaStream_t st);
+                         int64_t D_pad, float scale, const float* row_scale, float prob_scale, int prob, float* conf,
+                         int* label, cudaStream_t st);
 int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                       const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
                       int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st);
@@ -269,23 +270,37 @@ int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void*
   return SC_OK;
 }
 
-int sc_rowconf_from_split(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t C,
-                          int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
-                          void* stream) {
-  SC_REQUIRE(Ah && Al && Bh && Bl && conf && label, SC_EINVAL, "sc_rowconf_from_split: null pointer");
-  SC_REQUIRE(M > 0 && C > 0, SC_ESHAPE, "sc_rowconf_from_split: bad shape");
-  SC_REQUIRE(mode == SC_CONF_RAW || mode == SC_CONF_PROB, SC_EINVAL, "sc_rowconf_from_split: bad mode %d", mode);
-  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_rowconf_from_split: D_pad=%lld must be a multiple of 64",
-             (long long)D_pad);
+static int rowconf_fused(const char* who, const void* Ah, const void* Al, const float* row_scale, const void* Bh,
+                         const void* Bl, int64_t M, int64_t C, int64_t D_pad, float scale, float prob_scale, int mode,
+                         float* conf, int32_t* label, void* stream) {
+  SC_REQUIRE(Ah && Bh && Bl && conf && label, SC_EINVAL, "%s: null pointer", who);
+  SC_REQUIRE(M > 0 && C > 0, SC_ESHAPE, "%s: bad shape", who);
+  SC_REQUIRE(mode == SC_CONF_RAW || mode == SC_CONF_PROB, SC_EINVAL, "%s: bad mode %d", who, mode);
+  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "%s: D_pad=%lld must be a multiple of 64", who, (long long)D_pad);
   SC_REQUIRE((reinterpret_cast<uintptr_t>(Ah) | reinterpret_cast<uintptr_t>(Al) | reinterpret_cast<uintptr_t>(Bh) |
               reinterpret_cast<uintptr_t>(Bl)) % 16 == 0,
-             SC_EALIGN, "sc_rowconf_from_split: operands must be 16-byte aligned");
-  SC_REQUIRE(M < (1ll << 31) && C < (1ll << 31) - 512, SC_ESHAPE, "sc_rowconf_from_split: M/C exceed int32 coordinates");
-  int rc = sc::rowconf_fused_launch(&make_tmap, Ah, Al, Bh, Bl, M, C, D_pad, scale, prob_scale, mode == SC_CONF_PROB ? 1 : 0,
-                                    conf, label, static_cast<cudaStream_t>(stream));
+             SC_EALIGN, "%s: operands must be 16-byte aligned", who);
+  SC_REQUIRE(M < (1ll << 31) && C < (1ll << 31) - 512, SC_ESHAPE, "%s: M/C exceed int32 coordinates", who);
+  int rc = sc::rowconf_fused_launch(&make_tmap, Ah, Al, Bh, Bl, M, C, D_pad, scale, row_scale, prob_scale,
+                                    mode == SC_CONF_PROB ? 1 : 0, conf, label, static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+int sc_rowconf_from_split(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t C,
+                          int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
+                          void* stream) {
+  SC_REQUIRE(Al != nullptr, SC_EINVAL, "sc_rowconf_from_split: null pointer");
+  return rowconf_fused("sc_rowconf_from_split", Ah, Al, nullptr, Bh, Bl, M, C, D_pad, scale, prob_scale, mode, conf, label,
+                       stream);
+}
+
+int sc_rowconf_from_rows(const void* A, const float* row_scale, const void* Bh, const void* Bl, int64_t M, int64_t C,
+                         int64_t D_pad, float scale, float prob_scale, int mode, float* conf, int32_t* label,
+                         void* stream) {
+  return rowconf_fused("sc_rowconf_from_rows", A, nullptr, row_scale, Bh, Bl, M, C, D_pad, scale, prob_scale, mode, conf,
+                       label, stream);
 }
 
 int sc_attn_fwd_shifted(const void* Qn, const void* Kn, const void* Vt, int op_dtype, int64_t Nq, int64_t Nk,

@@ -64,6 +64,9 @@ struct SParams {
   float* conf;
   int* label;
   int conf_prob;             // 0: conf = row max; 1: conf = max softmax(prob_scale * row) = 1 / sum exp2(c1[0] (v - max))
+  const float* row_scale;    // kRowConf: optional per-row factor on top of `scale` (1 / norm of a raw feature row)
+  int passes;                // kGemm: operand passes per S tile: 3 = (A hi, B hi), (A hi, B lo), (A lo, B hi);
+                             // 2 = A is exact in fp16 (no lo part): (A, B hi), (A, B lo)
 };
 
 struct Bars {
@@ -134,7 +137,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr bool kF8 = (kOp == SC_E4M3);
   constexpr int kChunkElems = kF8 ? 2 * kBK : kBK;      // elements in a 128-byte operand row
   constexpr bool kGemm = (kKind == kGemmOut || kKind == kRowConf);      // split-fp16 operands, 3 passes per S tile
-  constexpr int kPasses = kGemm ? 3 : 1;      // operand passes accumulated into one S tile
+  const int n_pass = kGemm ? p.passes : 1;    // operand passes accumulated into one S tile
 
 #ifdef SC_ATTN_TIMING_EXPERIMENTS
   long long clk_c0 = 0;
@@ -194,7 +197,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
       }
 #pragma unroll 1
-      for (int ps = 0; ps < kPasses; ++ps) {
+      for (int ps = 0; ps < n_pass; ++ps) {
         // kGemm passes: (A hi, B hi), (A hi, B lo), (A lo, B hi)
         const CUtensorMap* mq = (kGemm && ps == 2) ? &tmQ2 : &tmQ;
         const CUtensorMap* mk = (kGemm && ps == 1) ? &tmK2 : &tmK;
@@ -227,7 +230,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t tmem_s = tmem_base + sb * 256;
         const uint32_t sfull = smem_u32(&bars->s_full[sb]);
 #pragma unroll 1
-        for (int dd = 0; dd < nd * kPasses; ++dd) {
+        for (int dd = 0; dd < nd * n_pass; ++dd) {
           if (!ready) mbar_wait(full0 + stage * 8, phase);
           tc_fence_after();
           const bool wrap = (stage + 1 == kNS);
@@ -236,7 +239,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           ready = __all_sync(0xffffffffu,
                              umma4_cg2_probe<kF8>(tmem_s, a_desc, a_desc + 2, a_desc + 4, a_desc + 6, b_desc, b_desc + 2,
                                              b_desc + 4, b_desc + 6, idesc, dd != 0 ? 1u : 0u, en, empty0 + stage * 8,
-                                             pair_mask, sfull, pair_mask, dd == nd * kPasses - 1 ? 1u : 0u,
+                                             pair_mask, sfull, pair_mask, dd == nd * n_pass - 1 ? 1u : 0u,
                                              full0 + (wrap ? 0 : stage + 1) * 8, wrap ? phase ^ 1u : phase));
           if (wrap) { stage = 0; phase ^= 1u; } else { ++stage; }
         }
@@ -254,6 +257,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float best = -INFINITY, m_run = -1e30f, acc = 0.f;
       int bidx = 0;
       const float c1 = p.c1[0];
+      const float rs = (p.row_scale != nullptr && qg < p.Nq) ? p.scale * p.row_scale[qg] : p.scale;
 #pragma unroll 1
       for (int st = 0; st < nsteps; ++st) {
         const int b = st & 1;
@@ -271,7 +275,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float cm = -1e30f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float v = (j < nvalid) ? __uint_as_float(rg[j]) * p.scale : -INFINITY;
+            const float v = (j < nvalid) ? __uint_as_float(rg[j]) * rs : -INFINITY;
             if (v > best) { best = v; bidx = nb + j; }
             cm = fmaxf(cm, v);
           }
@@ -282,7 +286,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             float sacc = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float e = ex2_approx(c1 * (__uint_as_float(rg[j]) * p.scale - mn));
+              const float e = ex2_approx(c1 * (__uint_as_float(rg[j]) * rs - mn));
               sacc += (j < nvalid) ? e : 0.f;
             }
             acc += sacc;
@@ -751,11 +755,12 @@ int attn_seg_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t
 // with ALL column steps of a row tile in one work item and the row reduction in the consumer warps.
 int rowconf_fused_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                          const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
-                         int64_t D_pad, float scale, float prob_scale, int prob, float* conf, int* label, cudaStream_t st) {
+                         int64_t D_pad, float scale, const float* row_scale, float prob_scale, int prob, float* conf, int* label,
+                         cudaStream_t st) {
   CUtensorMap tmA, tmA2, tmB, tmB2;
   int rc;
   if ((rc = make_tmap(&tmA, Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
-  if ((rc = make_tmap(&tmA2, Al, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmA2, Al ? Al : Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;   // Al == null: 2 passes
   if ((rc = make_tmap(&tmB, Bh, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
   if ((rc = make_tmap(&tmB2, Bl, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
   SParams p = {};
@@ -780,6 +785,8 @@ int rowconf_fused_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, in
   p.conf = conf;
   p.label = label;
   p.conf_prob = prob;
+  p.row_scale = row_scale;
+  p.passes = Al ? 3 : 2;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), 1u);
   SC_REQUIRE(grid.y <= 65535, SC_ESHAPE, "sc_rowconf_from_split: too many row tiles; chunk the rows");
   return launch_seg<SC_F16, kRowConf, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);
@@ -858,6 +865,7 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.ldz = ldz;
   p.n_cols = static_cast<int>(N);
   p.scale = scale;
+  p.passes = 3;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
   SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
   return launch_seg<SC_F16, kGemmOut, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);

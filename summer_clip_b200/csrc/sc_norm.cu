@@ -15,7 +15,8 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d,
                       int64_t stride_n, const int64_t* __restrict__ idx, int64_t n_out,
-                      TO* __restrict__ dst, int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
+                      TO* __restrict__ dst, int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row,
+                      float* __restrict__ inv_out) {
   __shared__ float tile[64][33];
   __shared__ float red[8][32];
   __shared__ float inv_norm[32];
@@ -33,7 +34,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
   __syncthreads();
   const int64_t my_off = col_off[tx];
 
-  if (normalize) {
+  if (normalize || inv_out != nullptr) {
     float ss = 0.f;
     if (my_off >= 0) {
 #pragma unroll 8
@@ -49,6 +50,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += red[j][tx];
       inv_norm[tx] = sqrtf(s);   // the NORM; we divide below like the reference does
+      if (inv_out != nullptr && n0 + tx < n_out) inv_out[n0 + tx] = 1.0f / sqrtf(s);
     }
     __syncthreads();
   }
@@ -91,7 +93,7 @@ norm_transpose_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t s
 template <typename T, typename TO>
 __global__ void __launch_bounds__(512)
 norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_d, TO* __restrict__ dst,
-                  int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
+                  int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row, float* __restrict__ inv_out) {
   extern __shared__ uint16_t strip[];            // [32 columns][pitch]: column-major, pitch = D_even + 2 halves
   __shared__ float red[16][32];
   __shared__ float inv_s[32];
@@ -130,7 +132,9 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) t += red[j][lane];
-    inv_s[lane] = normalize ? 1.0f / sqrtf(t) : 1.0f;
+    const float inv = 1.0f / sqrtf(t);
+    inv_s[lane] = normalize ? inv : 1.0f;
+    if (inv_out != nullptr && col_ok) inv_out[n0 + lane] = inv;
   }
   __syncthreads();
   // phase B: warp w writes the output rows of columns w and w + 16; lane handles the pair d = d0 + 2 lane, +1
@@ -159,11 +163,11 @@ norm_strip_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t strid
 
 template <typename T, typename TO>
 int launch_norm_strip(const void* src, int64_t D, int64_t N, int64_t stride_d, void* dst, int64_t D_pad, int normalize,
-                      const int64_t* dst_row, cudaStream_t st) {
+                      const int64_t* dst_row, float* inv_out, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(32) * ((D + 1) / 2 * 2 + 2) * 2;
   SC_CUDA(cudaFuncSetAttribute(norm_strip_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   norm_strip_kernel<T, TO><<<static_cast<unsigned>(sc::ceil_div(N, 32)), 512, smem, st>>>(
-      static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize, dst_row);
+      static_cast<const T*>(src), D, N, stride_d, static_cast<TO*>(dst), D_pad, normalize, dst_row, inv_out);
   return SC_OK;
 }
 
@@ -172,24 +176,27 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 norm_rows_kernel(const T* __restrict__ src, int64_t D, int64_t N, int64_t stride_n,
                  const int64_t* __restrict__ idx, int64_t n_out, TO* __restrict__ dst,
-                 int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row) {
+                 int64_t D_pad, int normalize, const int64_t* __restrict__ dst_row, float* __restrict__ inv_out) {
   const int lane = threadIdx.x & 31;
   int64_t o = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (o >= n_out) return;
+  const int64_t o_in = o;
   const int64_t n = idx ? idx[o] : o;
   if (dst_row != nullptr) o = dst_row[o];
   if (o < 0) return;
   const bool ok = (n >= 0 && n < N);
   const T* row = src + (ok ? n : 0) * stride_n;
   float nrm = 1.f;
-  if (normalize) {
+  if (normalize || inv_out != nullptr) {
     float ss = 0.f;
     if (ok)
       for (int64_t d = lane; d < D; d += 32) {
         const float v = sc::to_f32<T>(row[d]);
         ss = fmaf(v, v, ss);
       }
-    nrm = sqrtf(sc::warp_sum(ss));
+    const float full = sqrtf(sc::warp_sum(ss));
+    if (inv_out != nullptr && lane == 0) inv_out[o_in] = 1.0f / full;
+    if (normalize) nrm = full;
   }
   for (int64_t d = 2 * lane; d < D_pad; d += 64) {
     float a = 0.f, b = 0.f;
@@ -354,7 +361,7 @@ extern "C" int sc_normalize_split(const void* src, int src_dtype, int64_t D, int
 
 static int normalize_impl(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d, int64_t stride_n,
                           const int64_t* idx, int64_t n_out, void* dst, int dst_dtype, int64_t D_pad, int normalize,
-                          const int64_t* dst_row, void* stream) {
+                          const int64_t* dst_row, float* inv_out, void* stream) {
   SC_REQUIRE(src && dst, SC_EINVAL, "sc_normalize_cast: null pointer");
   SC_REQUIRE(D > 0 && N >= 0 && n_out >= 0, SC_ESHAPE, "sc_normalize_cast: bad shape");
   SC_REQUIRE(D_pad >= D && D_pad % 64 == 0, SC_ESHAPE,
@@ -369,8 +376,8 @@ static int normalize_impl(const void* src, int src_dtype, int64_t D, int64_t N, 
       static_cast<size_t>(D) * 33 * 2 <= 200 * 1024) {
     int rc = SC_OK;
     SC_DISPATCH_OP8(dst_dtype, TO, {
-      if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, st);
-      else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, st);
+      if (src_dtype == SC_F16) rc = launch_norm_strip<__half, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, inv_out, st);
+      else rc = launch_norm_strip<__nv_bfloat16, TO>(src, D, N, stride_d, dst, D_pad, normalize, dst_row, inv_out, st);
     });
     if (rc != SC_OK) return rc;
   } else if (stride_d == 1 && stride_n != 1) {
@@ -379,7 +386,7 @@ static int normalize_impl(const void* src, int src_dtype, int64_t D, int64_t N, 
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_rows_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_n, idx, n_out,
-                            static_cast<TO*>(dst), D_pad, normalize, dst_row)));
+                            static_cast<TO*>(dst), D_pad, normalize, dst_row, inv_out)));
     });
   } else {
     const unsigned blocks = static_cast<unsigned>(sc::ceil_div(n_out, 32));
@@ -387,7 +394,7 @@ static int normalize_impl(const void* src, int src_dtype, int64_t D, int64_t N, 
       SC_DISPATCH_DTYPE(src_dtype, T,
                         (norm_transpose_kernel<T, TO><<<blocks, 256, 0, st>>>(
                             static_cast<const T*>(src), D, N, stride_d, stride_n, idx, n_out,
-                            static_cast<TO*>(dst), D_pad, normalize, dst_row)));
+                            static_cast<TO*>(dst), D_pad, normalize, dst_row, inv_out)));
     });
   }
   SC_CUDA(cudaGetLastError());
@@ -399,7 +406,15 @@ extern "C" int sc_normalize_cast(const void* src, int src_dtype, int64_t D, int6
                                  int64_t n_out, void* dst, int dst_dtype, int64_t D_pad,
                                  int normalize, void* stream) {
   return normalize_impl(src, src_dtype, D, N, stride_d, stride_n, idx, n_out, dst, dst_dtype, D_pad, normalize, nullptr,
-                        stream);
+                        nullptr, stream);
+}
+
+extern "C" int sc_transpose_norms(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
+                                  int64_t stride_n, const int64_t* idx, int64_t n_out, void* dst, int dst_dtype,
+                                  int64_t D_pad, int normalize, float* inv_norm, void* stream) {
+  SC_REQUIRE(inv_norm != nullptr, SC_EINVAL, "sc_transpose_norms: null inv_norm");
+  return normalize_impl(src, src_dtype, D, N, stride_d, stride_n, idx, n_out, dst, dst_dtype, D_pad, normalize, nullptr,
+                        inv_norm, stream);
 }
 
 extern "C" int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, int64_t N, int64_t stride_d,
@@ -407,7 +422,7 @@ extern "C" int sc_normalize_scatter(const void* src, int src_dtype, int64_t D, i
                                     void* dst, int dst_dtype, int64_t D_pad, int normalize, void* stream) {
   SC_REQUIRE(dst_row != nullptr, SC_EINVAL, "sc_normalize_scatter: null dst_row");
   return normalize_impl(src, src_dtype, D, N, stride_d, stride_n, idx, n_out, dst, dst_dtype, D_pad, normalize, dst_row,
-                        stream);
+                        nullptr, stream);
 }
 
 extern "C" int sc_mean_normalize_rows(const void* src, int dtype, int64_t E, int64_t N, int64_t D, int64_t stride_e,

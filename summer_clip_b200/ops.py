@@ -88,10 +88,11 @@ def pad_classes(C: int) -> int:
 
 def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Tensor] = None,
                    normalize: bool = True, op_dtype: Optional[torch.dtype] = None,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [D, N] if feature_major (the reference's on-disk layout, save_features.py:36) else [N, D];
     any strides.  Returns [n_out, D_pad] of op_dtype, rows L2-normalised, optionally gathered by idx.
-    `out` (optional) is a preallocated contiguous [>= n_out, D_pad] buffer of op_dtype."""
+    `out` (optional) is a preallocated contiguous [>= n_out, D_pad] buffer of op_dtype.  `inv_norm` (optional,
+    fp32 [>= n_out]) receives 1 / |column| of the source (sc_transpose_norms) whether or not `normalize` is set."""
     _cuda(x, "x")
     assert x.dim() == 2
     if feature_major:
@@ -121,9 +122,15 @@ def normalize_cast(x: torch.Tensor, feature_major: bool, idx: Optional[torch.Ten
         # (CacheValues.hard_bank, _BankCache) notice that a preallocated bank was refilled
         torch.autograd.graph.increment_version(out)
     with torch.cuda.device(x.device):
-        check(_lib.load().sc_normalize_cast(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
-                                            _ptr(out), _code(out), D_pad, int(normalize), _stream()),
-              "sc_normalize_cast")
+        if inv_norm is None:
+            check(_lib.load().sc_normalize_cast(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
+                                                _ptr(out), _code(out), D_pad, int(normalize), _stream()),
+                  "sc_normalize_cast")
+        else:
+            assert inv_norm.is_cuda and inv_norm.dtype == torch.float32 and inv_norm.is_contiguous() and inv_norm.numel() >= n_out
+            check(_lib.load().sc_transpose_norms(_ptr(x), _code(x), D, N, stride_d, stride_n, _ptr(idx), n_out,
+                                                 _ptr(out), _code(out), D_pad, int(normalize), _ptr(inv_norm), _stream()),
+                  "sc_transpose_norms")
     return out
 
 
@@ -163,18 +170,29 @@ def rowconf_from_features(X: torch.Tensor, feature_major: bool, T: torch.Tensor,
     (confidence fp32 [N], predicted label int32 [N]) straight from the image features X ([D, N] if feature_major)
     and the text classifier T [D, C] — save_image_outs.py:25 fused with TopK[Prob]Strategy's row scan."""
     _cuda(X, "X"), _cuda(T, "T")
-    xh, xl = normalize_split(X, feature_major, normalize=True)
     th, tl = t_split if t_split is not None else text_split(T)
-    N, D_pad = xh.shape
     C = th.shape[0]
+    N = X.shape[1] if feature_major else X.shape[0]
     conf = torch.empty(N, dtype=torch.float32, device=X.device)
     label = torch.empty(N, dtype=torch.int32, device=X.device)
     if N == 0:
         return conf, label
+    mode = SC_CONF_PROB if prob else SC_CONF_RAW
+    if X.dtype == torch.float16:
+        # the raw features are exact in fp16: transposed copy + 1/norm per row, two operand passes instead of the
+        # three of a split (hi, lo) pair, and half the bytes written
+        inv = torch.empty(N, dtype=torch.float32, device=X.device)
+        xr = normalize_cast(X, feature_major, normalize=False, op_dtype=torch.float16, inv_norm=inv)
+        with torch.cuda.device(X.device):
+            check(_lib.load().sc_rowconf_from_rows(_ptr(xr), _ptr(inv), _ptr(th), _ptr(tl), N, C, xr.shape[1], float(scale),
+                                                   float(prob_scale), mode, _ptr(conf), _ptr(label), _stream()),
+                  "sc_rowconf_from_rows")
+        return conf, label
+    xh, xl = normalize_split(X, feature_major, normalize=True)
     with torch.cuda.device(X.device):
-        check(_lib.load().sc_rowconf_from_split(_ptr(xh), _ptr(xl), _ptr(th), _ptr(tl), N, C, D_pad, float(scale),
-                                                float(prob_scale), SC_CONF_PROB if prob else SC_CONF_RAW, _ptr(conf),
-                                                _ptr(label), _stream()), "sc_rowconf_from_split")
+        check(_lib.load().sc_rowconf_from_split(_ptr(xh), _ptr(xl), _ptr(th), _ptr(tl), N, C, xh.shape[1], float(scale),
+                                                float(prob_scale), mode, _ptr(conf), _ptr(label), _stream()),
+              "sc_rowconf_from_split")
     return conf, label
 
 

@@ -477,6 +477,20 @@ def test_pseudo_labels_without_the_logits_bank(ops, golden_dir, tmp_path):
     torch.testing.assert_close(conf.cpu().double(), ref_conf, rtol=0, atol=5e-6)       # 22-bit operands, fp32 accumulate
     agree = (label.cpu() == ref_label).float().mean().item()
     assert agree >= 0.999, agree                                               # a flipped label needs a top-2 gap < 1e-6
+    # fp16 features take the two-pass route (raw rows + 1/norm, sc_rowconf_from_rows); the same values as fp32 take the
+    # three-pass split route (sc_rowconf_from_split): same answer
+    conf3, label3 = ops.rowconf_from_features(Kb.float(), True, Tb)
+    torch.testing.assert_close(conf, conf3, rtol=0, atol=5e-6)
+    assert (label == label3).float().mean().item() >= 0.999
+    for prob_scale in (1.0, 100.0):
+        cp2, lp2 = ops.rowconf_from_features(Kb, True, Tb, prob=True, prob_scale=prob_scale)
+        ref_p = torch.softmax(prob_scale * Lb, dim=1).max(dim=1).values
+        torch.testing.assert_close(cp2.cpu().double(), ref_p, rtol=2e-3, atol=0)
+        assert torch.equal(lp2, label)
+    # row-major fp16 features (stride_d == 1 route of the transposing kernel)
+    conf_r, label_r = ops.rowconf_from_features(Kb.t().contiguous(), False, Tb)
+    torch.testing.assert_close(conf_r, conf, rtol=0, atol=5e-6)
+    assert (label_r == label).float().mean().item() >= 0.999
     # the sweep driver with cache.image_outs_path = null: same records as with the stored bank
     from summer_clip_b200.clip_searcher.image_attention import run
     small = orc.synthetic_banks(300, 2000, 128, 30, seed=53, sigma=0.5, sigma_text=0.8, shared=3.0)
@@ -589,3 +603,24 @@ def test_dense_value_sidecar_and_streamed_load_vs_oracle(ops, tmp_path, monkeypa
     bank_io.save_query_bank(qn, tmp_path / "q", "q", clip_logits=res["clip_logits"])
     q2, z2 = bank_io.load_query_bank(tmp_path / "q", "cuda", "q")
     assert torch.equal(q2, qn) and torch.equal(z2, res["clip_logits"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_transpose_norms(ops, dtype):
+    """sc_transpose_norms: the transposed bank (normalised or raw) plus 1 / |column|, through all three kernel routes
+    (16-bit feature-major strip, gathered tile, row-major warp-per-row)."""
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(200, 1001, generator=g) * 0.3).to(dtype).cuda()              # [D, N], odd N
+    want_inv = 1.0 / x.float().norm(dim=0)
+    idx = torch.randperm(1001, generator=g)[:300].cuda()
+    for src, fm, sel in ((x, True, None), (x, True, idx), (x.t().contiguous(), False, None), (x.t().contiguous(), False, idx)):
+        n_out = 1001 if sel is None else 300
+        for normalize in (False, True):
+            inv = torch.full((n_out,), -1.0, device="cuda")
+            out = ops.normalize_cast(src, fm, idx=sel, normalize=normalize, op_dtype=torch.float16, inv_norm=inv)
+            w = want_inv if sel is None else want_inv[sel]
+            torch.testing.assert_close(inv, w, rtol=2e-6, atol=0)
+            cols = x.float() if sel is None else x.float()[:, sel]
+            ref = (cols * w if normalize else cols).t()
+            torch.testing.assert_close(out[:, :200].float(), ref.half().float(), rtol=0, atol=1e-3 if normalize else 0)
+            assert torch.equal(out, ops.normalize_cast(src, fm, idx=sel, normalize=normalize, op_dtype=torch.float16))

@@ -157,7 +157,30 @@ def hbm_sections(peaks, quick, dev, hbm):
     idx = torch.randperm(n, device=dev)[:16000]
     med, _ = timed(lambda: ops.normalize_cast(bank, True, idx=idx), iters=5)
     emit(config="k_norm", kind="gather_normalize_cast_16k_columns", ms=med)
-    del bank, out
+    del out
+
+    # ---- pseudo-labels straight from the features and the text classifier (the [N, C] logits bank never exists),
+    # and the whole cache build: features -> (conf, label) -> per-class top-16 -> label-sorted normalised key bank
+    g = torch.Generator(device=dev).manual_seed(6)
+    text = torch.nn.functional.normalize(torch.randn(dim, c, generator=g, device=dev), dim=0)
+    t_split = ops.text_split(text)
+    med, _ = timed(lambda: ops.rowconf_from_features(bank, True, text, scale=100.0, prob=True, prob_scale=1.0, t_split=t_split),
+                   iters=5)
+    emit(config="pseudo_labels", kind="rowconf_from_features_prob", n=n, dim=dim, n_classes=c, ms=med,
+         executed_tflops=2 * 2.0 * n * dim * c / (med * 1e-3) / 1e12,
+         note="fp16 features: raw transposed copy + 1/norm (sc_transpose_norms), two tensor-core passes against the "
+              "split classifier with the row scan in the consumer warps (sc_rowconf_from_rows)")
+
+    def build():
+        conf, label = ops.rowconf_from_features(bank, True, text, scale=100.0, prob=True, prob_scale=1.0, t_split=t_split)
+        idx, _ = ops.topk_per_class(conf, label, c, 16)
+        sel = idx.flatten()
+        sel = sel[sel >= 0]
+        return ops.hard_bank_build(label[sel], c, bank, True, idx=sel)
+    med, _ = timed(build, iters=3)
+    emit(config="pseudo_labels", kind="features_to_top16_per_class_bank", ms=med,
+         note="pseudo-labels + per-class top-16 + gather/normalise/label-sort of the selected 16k keys")
+    del bank
     torch.cuda.empty_cache()
 
 
