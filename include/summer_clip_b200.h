@@ -95,7 +95,9 @@ int sc_rowconf(const void* L, int dtype, int64_t N, int64_t C, int64_t ld, float
 /* select_topk_per_label (cache_strategy.py:48-59): for every class c in [0, C) the indices of
  * the min(k, n_c) most confident rows whose label is c, most confident first; ties are broken by
  * the smaller row index.  out_idx is int64 [C, k] (unused slots = -1), out_count int32 [C].
- * The reference's concatenated result is, for c ascending, out_idx[c, :out_count[c]]. */
+ * The reference's concatenated result is, for c ascending, out_idx[c, :out_count[c]].  N == 0 (an empty row shard;
+ * conf / label may be NULL) gives all -1.  Rows sharded over ranks: each rank's [C, k] candidates (confidence, global
+ * row) are all-gathered and merged under the same order (summer_clip_b200/selection.py). */
 size_t sc_topk_workspace_bytes(int64_t N, int32_t C);
 int sc_topk_per_class(const float* conf, const int32_t* label, int64_t N, int32_t C, int32_t k,
                       int64_t* out_idx, int32_t* out_count, void* workspace, size_t ws_bytes,

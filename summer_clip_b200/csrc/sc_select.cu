@@ -298,7 +298,8 @@ size_t sc_topk_workspace_bytes(int64_t N, int32_t C) { return topk_ws_bytes(N, C
 int sc_topk_per_class(const float* conf, const int32_t* label, int64_t N, int32_t C, int32_t k,
                       int64_t* out_idx, int32_t* out_count, void* workspace, size_t ws_bytes,
                       void* stream) {
-  SC_REQUIRE(conf && label && out_idx && out_count && workspace, SC_EINVAL, "sc_topk_per_class: null pointer");
+  SC_REQUIRE(((conf && label) || N == 0) && out_idx && out_count && workspace, SC_EINVAL,
+             "sc_topk_per_class: null pointer");       // an empty shard (N == 0) has no rows to point at
   SC_REQUIRE(N >= 0 && N < 0x7FFFFFFFll && C > 0 && k > 0, SC_ESHAPE, "sc_topk_per_class: bad shape");
   SC_REQUIRE(k <= kMaxK, SC_EUNSUPPORTED, "sc_topk_per_class: k=%d exceeds %d", k, kMaxK);
   SC_REQUIRE(ws_bytes >= topk_ws_bytes(N, C), SC_EINVAL, "sc_topk_per_class: workspace too small");

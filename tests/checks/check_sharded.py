@@ -5,6 +5,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -75,6 +76,27 @@ for hard in (True, False):
     good = e <= 2e-3
     ok &= good
     print(f"rank {rank} softmax mode tau=100 hard={hard}: max-abs vs oracle {e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+
+# row-sharded pseudo-label selection: every rank scans ITS rows of the train bank (stored logits, and
+# features + text classifier without a logits bank), per-class top-k candidates all-gathered and merged
+from summer_clip_b200 import selection
+from summer_clip_b200.clip_searcher.cache_strategy import LazyLogitsBank
+banks = orc.synthetic_banks(8, 6001, 256, 100, seed=8, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=torch.float16)
+K, L, T = (banks[n] for n in ("cache_image_features", "cache_image_outs", "text_features"))
+n = K.shape[1]
+r_lo, r_hi = n * rank // world, n * (rank + 1) // world
+L_exact = (orc.normalize_columns(K.double()).t() @ T.double()).float()     # what the lazy bank computes (L itself is fp16-rounded)
+for prob_scale in (None, orc.CLIP_SCALE):
+    want = orc.topk_select(L.float(), 8) if prob_scale is None else orc.topk_prob_select(L.float(), 8, prob_scale)
+    got = selection.topk_select_sharded(L[r_lo:r_hi].to(dev), 8, prob_scale, dist.group.WORLD)
+    good = np.array_equal(got.cpu().numpy(), want)
+    lazy = LazyLogitsBank(K[:, r_lo:r_hi].to(dev), T.to(dev))
+    got_lazy = selection.topk_select_sharded(lazy, 8, prob_scale, dist.group.WORLD).cpu().numpy()
+    want_lazy = orc.topk_select(L_exact, 8) if prob_scale is None else orc.topk_prob_select(L_exact, 8, prob_scale)
+    same = got_lazy.shape == want_lazy.shape and float((got_lazy == want_lazy).mean()) >= 0.99    # a flip needs a gap < 1e-6
+    ok &= good and same
+    print(f"rank {rank} row-sharded selection prob_scale={prob_scale}: {got.numel()} picked, equals oracle={good}, "
+          f"without the logits bank equals oracle={same} {'OK' if good and same else 'FAIL'}", flush=True)
 
 dist.barrier()
 print(f"rank {rank} SHARDED {'OK' if ok else 'FAIL'}", flush=True)

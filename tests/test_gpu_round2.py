@@ -624,3 +624,22 @@ def test_transpose_norms(ops, dtype):
             ref = (cols * w if normalize else cols).t()
             torch.testing.assert_close(out[:, :200].float(), ref.half().float(), rtol=0, atol=1e-3 if normalize else 0)
             assert torch.equal(out, ops.normalize_cast(src, fm, idx=sel, normalize=normalize, op_dtype=torch.float16))
+
+
+def test_row_sharded_selection_equals_whole_bank(ops):
+    """SURVEY.md 8e "Selection kernel": per-shard sc_topk_per_class candidates (selection.local_candidates) merged
+    (selection.merge_candidates) == the whole-bank selection == the oracle, for uneven and empty shards, tied
+    confidences, and both confidence kinds; 1000 classes x 16 at 200k rows."""
+    from summer_clip_b200 import selection
+    g = torch.Generator().manual_seed(31)
+    for n, c, k, cuts in ((5000, 37, 6, (0, 1700, 1700, 5000)), (200_000, 1000, 16, (0, 60_000, 130_001, 200_000))):
+        L = (0.25 + 0.02 * torch.randn(n, c, generator=g)).half().cuda()
+        for prob in (False, True):
+            conf, label = ops.rowconf(L, scale=orc.CLIP_SCALE if prob else 1.0, prob=prob)
+            whole = ops.select_topk_per_label(conf, label, c, k)
+            cands = [selection.local_candidates(conf[lo:hi], label[lo:hi], c, k, lo) for lo, hi in zip(cuts, cuts[1:])]
+            merged = selection.merge_candidates(torch.stack([a for a, _ in cands]), torch.stack([b for _, b in cands]), k)
+            flat = merged.reshape(-1)
+            assert torch.equal(flat[flat >= 0], whole)
+            want = orc.select_topk_per_label(label.cpu().numpy(), conf.cpu().numpy(), k)
+            assert np.array_equal(whole.cpu().numpy(), want)

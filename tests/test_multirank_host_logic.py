@@ -54,6 +54,62 @@ def test_key_sharded_exchange_two_ranks_gloo(tmp_path, nq):
         assert float(np.load(tmp_path / f"err_{r}.npy")) < 1e-4
 
 
+def _oracle_local_topk(conf: torch.Tensor, label: torch.Tensor, n_classes: int, k: int, row_offset: int):
+    """Stand-in for sc_topk_per_class + selection.local_candidates on CPU: the oracle's select_topk_per_label per
+    class, as (confidence [C, k], global row [C, k]; -1 = no candidate)."""
+    cc = torch.zeros((n_classes, k), dtype=torch.float32)
+    cr = torch.full((n_classes, k), -1, dtype=torch.int64)
+    picked = orc.select_topk_per_label(label.numpy(), conf.numpy(), k)
+    for c in range(n_classes):
+        mine = [int(i) for i in picked if int(label[i]) == c]
+        for j, i in enumerate(mine):
+            cc[c, j], cr[c, j] = conf[i], i + row_offset
+    return cc, cr
+
+
+def _select_worker(rank: int, world: int, port: int, cut: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from summer_clip_b200 import selection
+        banks = orc.synthetic_banks(4, 900, 32, 17, seed=92, sigma=0.5, sigma_text=0.8, shared=3.0)
+        conf, label = orc.row_confidence(banks["cache_image_outs"], prob=True, scale=orc.CLIP_SCALE)
+        conf = (conf * 64).round() / 64                                  # many equal confidences: ties -> smaller row
+        lo, hi = (0, cut) if rank == 0 else (cut, 900)                   # rank shards are consecutive row ranges
+        offs = selection.row_offsets(hi - lo, torch.device("cpu"), dist.group.WORLD)
+        assert offs == [0, cut, 900]
+        cc, cr = _oracle_local_topk(conf[lo:hi], label[lo:hi], 17, 5, offs[rank])
+        got = selection.exchange_and_merge(cc, cr, 5, dist.group.WORLD)
+        flat = got.reshape(-1)
+        np.save(os.path.join(out_dir, f"sel_{rank}.npy"), flat[flat >= 0].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cut", [450, 13, 0])
+def test_sharded_selection_two_ranks_gloo(tmp_path, cut):
+    """SURVEY.md 8e "Selection kernel": per-rank per-class top-k candidates, all-gathered and merged, equal the
+    reference's select_topk_per_label over the whole bank (uneven and empty shards; tied confidences)."""
+    port = _free_port()
+    mp.spawn(_select_worker, args=(2, port, cut, str(tmp_path)), nprocs=2, join=True)
+    banks = orc.synthetic_banks(4, 900, 32, 17, seed=92, sigma=0.5, sigma_text=0.8, shared=3.0)
+    conf, label = orc.row_confidence(banks["cache_image_outs"], prob=True, scale=orc.CLIP_SCALE)
+    conf = (conf * 64).round() / 64
+    want = orc.select_topk_per_label(label.numpy(), conf.numpy(), 5)
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"sel_{r}.npy"), want)
+
+
+def test_merge_candidates_total_order():
+    """NaN above +inf, equal confidences by row, -inf real candidates before missing ones, fewer than k candidates."""
+    from summer_clip_b200.selection import merge_candidates
+    nan, inf = float("nan"), float("inf")
+    conf = torch.tensor([[[0.5, 0.5, 0.0]], [[nan, inf, -inf]], [[0.5, 0.0, 0.0]]])          # [W=3, C=1, k=3]
+    row = torch.tensor([[[7, 9, -1]], [[20, 21, 22]], [[3, -1, -1]]])
+    assert merge_candidates(conf, row, 3).tolist() == [[20, 21, 3]]
+    assert merge_candidates(conf, row, 8).tolist() == [[20, 21, 3, 7, 9, 22, -1, -1]]
+
+
 def test_shard_and_slice_arithmetic():
     from summer_clip_b200.searcher import query_slice, shard_range
     for n in (1, 127, 128, 1000, 1281167):
