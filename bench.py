@@ -212,7 +212,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from summer_clip_b200 import build as _build, ops
-    from summer_clip_b200.searcher import ClipSearcher, exchange_partials, query_slice, shard_range
+    from summer_clip_b200.searcher import ClipSearcher, query_slice, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

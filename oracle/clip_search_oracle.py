@@ -24,7 +24,7 @@ Deviations from the reference, all documented in DESIGN.md:
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -7,7 +7,6 @@ Acceptance (BASELINE.json north_star): pseudo-label indices and top-k sets bit-e
 max-abs after softmax; argmax agreement >= 99.9 %.
 """
 import json
-import math
 from pathlib import Path
 
 import numpy as np

@@ -23,7 +23,6 @@ def _worker(rank: int, world: int, port: int, nq: int, out_dir: str) -> None:
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from summer_clip_b200 import ops
         from summer_clip_b200.searcher import exchange_partials, query_slice, shard_range
         banks = orc.synthetic_banks(nq, 700, 64, 23, seed=91, sigma=0.5, sigma_text=0.8, shared=3.0)
         Q, K, L = (banks[n] for n in ("test_image_features", "cache_image_features", "cache_image_outs"))

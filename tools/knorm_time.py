@@ -1,4 +1,4 @@
-import os, sys
+import sys
 sys.path.insert(0, "/root/repo")
 import torch
 from summer_clip_b200 import ops

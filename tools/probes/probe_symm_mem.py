@@ -1,5 +1,5 @@
 """Probe: does torch.distributed._symmetric_memory work on this box (peer-mapped buffers + device barrier)?"""
-import os, sys, time
+import os, time
 import torch
 import torch.distributed as dist
 
