@@ -116,6 +116,12 @@ def zero_shot_logits(test_image_features: torch.Tensor, text_features: torch.Ten
     return 100.0 * norm.t() @ text_features
 
 
+def image_outs(image_features: torch.Tensor, text_features: torch.Tensor) -> torch.Tensor:
+    """clip_searcher/save_image_outs.py:21-25 — the logits bank normalise_cols(X)^T @ T (no x100), [N, C]."""
+    norm = image_features / image_features.norm(dim=0, keepdim=True)
+    return norm.t() @ text_features
+
+
 def accuracy_counts(output: torch.Tensor, target: torch.Tensor, topk: Sequence[int] = (1, 5)) -> List[float]:
     """clip_adapter/train_adapter.py:156-159 — number of rows whose target is within the top-k."""
     pred = output.topk(max(topk), 1, True, True)[1].t()

@@ -228,13 +228,13 @@ def run_trainer(trainer_cls, cfg, run_dir=".") -> "ImageAttention":
     return trainer
 
 
-def run(argv: tp.Optional[tp.Sequence[str]] = None) -> ImageAttention:
-    """`image_attention.py [CONFIG.yaml | --config-dir DIR [--config-name NAME]] [key=value | group=option ...]` —
-    the hydra command line of the reference (image_attention.py:123-125): a primary config with a defaults list is
-    composed from its directory, `key=value` overrides are applied after composition."""
+def compose_from_argv(argv: tp.Optional[tp.Sequence[str]], default_name: str) -> Config:
+    """`[CONFIG.yaml | --config-dir DIR [--config-name NAME]] [key=value | group=option ...]` — the hydra command line
+    of the reference's entry points: a primary config with a defaults list is composed from its directory,
+    `key=value` overrides are applied after composition."""
     argv = list(sys.argv[1:] if argv is None else argv)
     conf_dir = Path(__file__).resolve().parent.parent / "conf"
-    name = "image_attention"
+    name = default_name
     rest: tp.List[str] = []
     i = 0
     while i < len(argv):
@@ -248,7 +248,12 @@ def run(argv: tp.Optional[tp.Sequence[str]] = None) -> ImageAttention:
         else:
             rest.append(a)
         i += 1
-    cfg = compose(conf_dir, name, rest)
+    return compose(conf_dir, name, rest)
+
+
+def run(argv: tp.Optional[tp.Sequence[str]] = None) -> ImageAttention:
+    """The reference's `image_attention.py` command line (image_attention.py:123-125)."""
+    cfg = compose_from_argv(argv, "image_attention")
     return run_trainer(ImageAttention, cfg, run_dir=(cfg.get("run_dir") or "."))
 
 

@@ -642,3 +642,26 @@ def test_row_sharded_selection_equals_whole_bank(ops):
             assert torch.equal(flat[flat >= 0], whole)
             want = orc.select_topk_per_label(label.cpu().numpy(), conf.cpu().numpy(), k)
             assert np.array_equal(whole.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_save_image_outs_entry_point(ops, tmp_path, dtype):
+    """clip_searcher/save_image_outs.py: the logits-bank producer run from its composed YAML writes
+    normalise(X)^T @ T in the feature dtype; the bank it writes drives the same selection as the lazy bank."""
+    from summer_clip_b200.clip_searcher.cache_strategy import LazyLogitsBank, TopKStrategy
+    from summer_clip_b200.clip_searcher.save_image_outs import run
+    banks = orc.synthetic_banks(4, 3001, 192, 57, seed=61, sigma=0.5, sigma_text=0.8, shared=3.0, dtype=dtype)
+    K, T = banks["cache_image_features"], banks["text_features"]
+    torch.save(K, tmp_path / "k.pt")
+    torch.save(T, tmp_path / "t.pt")
+    trainer = run([f"data.image_features_path={tmp_path / 'k.pt'}", f"data.text_features_path={tmp_path / 't.pt'}",
+                   "data.rows_per_chunk=1000", f"run_dir={tmp_path}"])
+    got = torch.load(tmp_path / "image_outs.pt")
+    assert got.dtype == dtype and got.shape == (3001, 57) and got.device.type == "cpu"
+    want = orc.image_outs(K.double(), T.double())
+    tol = 2e-6 if dtype == torch.float32 else 1e-3                                  # fp16: the storage rounding
+    torch.testing.assert_close(got.double(), want, rtol=0, atol=tol)
+    assert torch.equal(trainer.image_outs.cpu(), got)
+    lazy = LazyLogitsBank(K.cuda(), T.cuda())
+    a, b = TopKStrategy(4).select(K.cuda(), got.cuda()), TopKStrategy(4).select(K.cuda(), lazy)
+    assert a.shape == b.shape and (a == b).float().mean().item() >= (0.999 if dtype == torch.float32 else 0.9)

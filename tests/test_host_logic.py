@@ -123,6 +123,13 @@ def test_reference_yaml_tree_composes_unmodified():
     assert b <= a and a - b == {"cache.labels_path", "data.clip_logits_path", "data.labels_path", "data.text_features_path"}
     assert theirs.cache_strategies.topk_prob == ours.cache_strategies.topk_prob
     assert theirs.cache.alpha == ours.cache.alpha and theirs.cache_weights_strategy == ours.cache_weights_strategy
+    # the logits-bank producer's config (save_image_outs.py): the reference's keys plus the text classifier file
+    ours = compose(Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf", "save_image_outs")
+    theirs = compose(ref, "save_image_outs")
+    a = {k for k in keys(ours) if not k.startswith(skip)}
+    b = {k for k in keys(theirs) if not k.startswith(skip)}
+    assert b <= a and a - b == {"data.text_features_path", "data.rows_per_chunk"}
+    assert theirs.data.output_image_outs == ours.data.output_image_outs == "image_outs.pt" and theirs.exp == ours.exp
     for name in ("tip_adapter", "tip_adapter_imagenet"):
         t, o = compose(ref, name), compose(Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf", name)
         for k in ("search_hp", "search_scale", "search_step", "init_beta", "init_alpha", "dataset", "shots", "backbone", "augment_epoch"):
