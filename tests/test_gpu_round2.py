@@ -665,3 +665,27 @@ def test_save_image_outs_entry_point(ops, tmp_path, dtype):
     lazy = LazyLogitsBank(K.cuda(), T.cuda())
     a, b = TopKStrategy(4).select(K.cuda(), got.cuda()), TopKStrategy(4).select(K.cuda(), lazy)
     assert a.shape == b.shape and (a == b).float().mean().item() >= (0.999 if dtype == torch.float32 else 0.9)
+
+
+def test_tip_adapter_entry_point_for_the_other_datasets(ops, golden_dir, tmp_path):
+    """tip_adapter/tip_adapter.py: the same trainer composed from conf/tip_adapter.yaml (search_scale [20, 10],
+    init_beta 1, init_alpha 3): head accuracy and search_hp against the oracle's restatement of the reference lines."""
+    from summer_clip_b200.tip_adapter.tip_adapter import run
+    r2 = np.load(golden_dir / "round2.npz")
+    names = {"train_features_path": "tip_train_features", "train_labels_path": "tip_train_labels",
+             "test_features_path": "tip_test_features", "test_labels_path": "tip_test_labels", "clip_weights_path": "tip_clip_weights"}
+    over = [f"run_dir={tmp_path}", "search_step=[10,4]"]
+    for key, arr in names.items():
+        path = tmp_path / f"{arr}.pt"
+        torch.save(torch.from_numpy(r2[arr]), path)
+        over.append(f"{key}={path}")
+    tr = run(over)
+    assert tr.cfg["search_scale"] == [20, 10] and tr.cfg["init_beta"] == 1 and tr.cfg["init_alpha"] == 3
+    f32, k32 = torch.from_numpy(r2["tip_test_f"]).float(), torch.from_numpy(r2["tip_cache_keys"]).float()
+    v32, w32 = torch.from_numpy(r2["tip_cache_values"]).float(), torch.from_numpy(r2["tip_clip_weights"]).float()
+    tl = torch.from_numpy(r2["tip_test_labels"])
+    n = tl.shape[0]
+    assert abs(tr.result["tip_acc"] - orc.cls_acc(orc.tip_head(f32, k32, v32, w32, 1.0, 3.0), tl)) <= 100.0 / n + 1e-9
+    bb, ba, best = orc.search_hp([20, 10], [10, 4], k32, v32, f32, tl, w32)
+    got = orc.cls_acc(orc.tip_head(f32, k32, v32, w32, tr.result["best_beta"], tr.result["best_alpha"]), tl)
+    assert abs(got - best) <= 100.0 / n + 1e-9          # fp16 operands may pick another grid point of the same accuracy
