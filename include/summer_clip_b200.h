@@ -290,6 +290,11 @@ int sc_normalize_split(const void* src, int src_dtype, int64_t D, int64_t N, int
                        int64_t stride_n, void* hi, void* lo, int64_t D_pad, int normalize, void* stream);
 int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
                      int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream);
+/* The same product for A rows that are EXACT in fp16 (raw fp16 feature banks: sc_transpose_norms gives the transposed
+ * rows and row_scale[m] = 1 / |row m|): two operand passes,
+ *     Z[m, n] = scale * row_scale[m] * sum_d A[m,d] (Bh[n,d] + Bl[n,d]);   row_scale may be NULL (= 1). */
+int sc_gemm_rows_nt(const void* A, const float* row_scale, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                    int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream);
 
 /* Pseudo-labels WITHOUT the logits bank (save_image_outs.py:25 fused with cache_strategy.py:67-70 / :79-81): the
  * rows of L = scale * A @ B^T (A = split(normalised image features) [M, D_pad], B = split(T^T) [C, D_pad], as for

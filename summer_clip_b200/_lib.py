@@ -79,6 +79,8 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     "sc_gemm_split_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
                                  c_void_p, c_int64, c_void_p]),
+    "sc_gemm_rows_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float,
+                                c_void_p, c_int64, c_void_p]),
     "sc_rowconf_from_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,
                                       c_int, c_void_p, c_void_p, c_void_p]),
     "sc_rowconf_from_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float,

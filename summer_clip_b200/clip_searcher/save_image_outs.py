@@ -49,7 +49,8 @@ class SaveImageOuts:
         out = torch.empty((n, c), dtype=X.dtype, device=self.device)
         for lo in range(0, n, chunk):
             hi = min(n, lo + chunk)
-            out[lo:hi] = ops.zero_shot_logits(X[:, lo:hi], True, T, scale=1.0, normalize=True, t_split=t_split).to(X.dtype)
+            out[lo:hi] = ops.zero_shot_logits(X[:, lo:hi], True, T, scale=1.0, normalize=True, t_split=t_split,
+                                                two_pass=True).to(X.dtype)          # fp16 banks: raw rows + 1/norm
         path = Path(self.cfg["data"]["output_image_outs"])
         if not path.is_absolute():
             path = self.run_dir / path

@@ -36,7 +36,7 @@ int rowconf_fused_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, in
                          int* label, cudaStream_t st);
 int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                       const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
-                      int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st);
+                      int64_t D_pad, float scale, const float* row_scale, float* Z, int64_t ldz, cudaStream_t st);
 }  // namespace sc
 
 namespace {
@@ -254,20 +254,31 @@ int sc_attn_fwd_hard(const void* Qn, const void* Ks, const int16_t* group_class,
                                 ldo, stream);
 }
 
-int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
-                     int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream) {
-  SC_REQUIRE(Ah && Al && Bh && Bl && Z, SC_EINVAL, "sc_gemm_split_nt: null pointer");
-  SC_REQUIRE(M > 0 && N > 0 && ldz >= N, SC_ESHAPE, "sc_gemm_split_nt: bad shape");
-  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "sc_gemm_split_nt: D_pad=%lld must be a multiple of 64",
-             (long long)D_pad);
+static int gemm_nt(const char* who, const void* Ah, const void* Al, const float* row_scale, const void* Bh, const void* Bl,
+                   int64_t M, int64_t N, int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream) {
+  SC_REQUIRE(Ah && Bh && Bl && Z, SC_EINVAL, "%s: null pointer", who);
+  SC_REQUIRE(M > 0 && N > 0 && ldz >= N, SC_ESHAPE, "%s: bad shape", who);
+  SC_REQUIRE(D_pad > 0 && D_pad % 64 == 0, SC_ESHAPE, "%s: D_pad=%lld must be a multiple of 64", who, (long long)D_pad);
   SC_REQUIRE((reinterpret_cast<uintptr_t>(Ah) | reinterpret_cast<uintptr_t>(Al) | reinterpret_cast<uintptr_t>(Bh) |
               reinterpret_cast<uintptr_t>(Bl)) % 16 == 0,
-             SC_EALIGN, "sc_gemm_split_nt: operands must be 16-byte aligned");
-  SC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) - 512, SC_ESHAPE, "sc_gemm_split_nt: M/N exceed int32 coordinates");
-  int rc = sc::gemm_split_launch(&make_tmap, Ah, Al, Bh, Bl, M, N, D_pad, scale, Z, ldz, static_cast<cudaStream_t>(stream));
+             SC_EALIGN, "%s: operands must be 16-byte aligned", who);
+  SC_REQUIRE(M < (1ll << 31) && N < (1ll << 31) - 512, SC_ESHAPE, "%s: M/N exceed int32 coordinates", who);
+  int rc = sc::gemm_split_launch(&make_tmap, Ah, Al, Bh, Bl, M, N, D_pad, scale, row_scale, Z, ldz,
+                                 static_cast<cudaStream_t>(stream));
   if (rc != SC_OK) return rc;
   SC_CUDA(cudaGetLastError());
   return SC_OK;
+}
+
+int sc_gemm_split_nt(const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                     int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream) {
+  SC_REQUIRE(Al != nullptr, SC_EINVAL, "sc_gemm_split_nt: null pointer");
+  return gemm_nt("sc_gemm_split_nt", Ah, Al, nullptr, Bh, Bl, M, N, D_pad, scale, Z, ldz, stream);
+}
+
+int sc_gemm_rows_nt(const void* A, const float* row_scale, const void* Bh, const void* Bl, int64_t M, int64_t N,
+                    int64_t D_pad, float scale, float* Z, int64_t ldz, void* stream) {
+  return gemm_nt("sc_gemm_rows_nt", A, nullptr, row_scale, Bh, Bl, M, N, D_pad, scale, Z, ldz, stream);
 }
 
 static int rowconf_fused(const char* who, const void* Ah, const void* Al, const float* row_scale, const void* Bh,

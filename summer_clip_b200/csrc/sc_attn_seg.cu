@@ -307,6 +307,7 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- GEMM mode: Z[q, n] = scale * S[q, n]; thread = output row, 32 consecutive columns per TMEM load
       const int qg = q0 + row;
       float* zrow = p.Z + static_cast<long long>(qg) * p.ldz;
+      const float rs = (p.row_scale != nullptr && qg < p.Nq) ? p.scale * p.row_scale[qg] : p.scale;
       const bool vec4 = (p.ldz % 4 == 0) && (reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
 #pragma unroll 1
       for (int st = 0; st < nsteps; ++st) {
@@ -325,12 +326,12 @@ sc_attn_seg_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(zrow + nb + j) =
-                    make_float4(__uint_as_float(rg[j]) * p.scale, __uint_as_float(rg[j + 1]) * p.scale,
-                                __uint_as_float(rg[j + 2]) * p.scale, __uint_as_float(rg[j + 3]) * p.scale);
+                    make_float4(__uint_as_float(rg[j]) * rs, __uint_as_float(rg[j + 1]) * rs,
+                                __uint_as_float(rg[j + 2]) * rs, __uint_as_float(rg[j + 3]) * rs);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nb + j < p.n_cols) zrow[nb + j] = __uint_as_float(rg[j]) * p.scale;
+                if (nb + j < p.n_cols) zrow[nb + j] = __uint_as_float(rg[j]) * rs;
             }
           }
         }
@@ -840,11 +841,11 @@ int attn_rowmax_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int6
 // operands given as fp16 (hi, lo) pairs, on the attention kernel's pipeline (one 256-row step of B per work item).
 int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64_t, int64_t, int, bool),
                       const void* Ah, const void* Al, const void* Bh, const void* Bl, int64_t M, int64_t N,
-                      int64_t D_pad, float scale, float* Z, int64_t ldz, cudaStream_t st) {
+                      int64_t D_pad, float scale, const float* row_scale, float* Z, int64_t ldz, cudaStream_t st) {
   CUtensorMap tmA, tmA2, tmB, tmB2;
   int rc;
   if ((rc = make_tmap(&tmA, Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
-  if ((rc = make_tmap(&tmA2, Al, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;
+  if ((rc = make_tmap(&tmA2, Al ? Al : Ah, M, D_pad, D_pad, kBQ, true)) != SC_OK) return rc;   // Al == null: 2 passes
   if ((rc = make_tmap(&tmB, Bh, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
   if ((rc = make_tmap(&tmB2, Bl, N, D_pad, D_pad, kBKeys, true)) != SC_OK) return rc;
   SParams p = {};
@@ -865,7 +866,8 @@ int gemm_split_launch(int (*make_tmap)(CUtensorMap*, const void*, int64_t, int64
   p.ldz = ldz;
   p.n_cols = static_cast<int>(N);
   p.scale = scale;
-  p.passes = 3;
+  p.row_scale = row_scale;
+  p.passes = Al ? 3 : 2;
   dim3 grid(2u, static_cast<unsigned>(ceil_div(M, 2 * kBQ)), static_cast<unsigned>(p.splits));
   SC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, SC_ESHAPE, "sc_gemm_split_nt: too many tiles; chunk the rows");
   return launch_seg<SC_F16, kGemmOut, 1>(grid, st, tmA, tmB, tmA2, tmB2, p);

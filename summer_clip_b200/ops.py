@@ -659,6 +659,28 @@ def gemm_split_nt(a: Tuple[torch.Tensor, torch.Tensor], b: Tuple[torch.Tensor, t
     return out
 
 
+def gemm_rows_nt(a: torch.Tensor, row_scale: Optional[torch.Tensor], b: Tuple[torch.Tensor, torch.Tensor], scale: float = 1.0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Z [M, N] fp32 = scale * row_scale[:, None] * A @ B^T for fp16 rows A [M, D_pad] that need no lo part (raw fp16
+    feature rows) and a split-fp16 B = (hi, lo) [N, D_pad]: two operand passes instead of gemm_split_nt's three."""
+    bh, bl = b
+    M, D_pad = a.shape
+    N = bh.shape[0]
+    assert bh.shape[1] == D_pad and all(t.dtype == torch.float16 and t.is_contiguous() and t.is_cuda for t in (a, bh, bl))
+    if row_scale is not None:
+        assert row_scale.is_cuda and row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() >= M
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (M, N)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sc_gemm_rows_nt(_ptr(a), _ptr(row_scale), _ptr(bh), _ptr(bl), M, N, D_pad, float(scale), _ptr(out),
+                                          out.stride(0), _stream()), "sc_gemm_rows_nt")
+    return out
+
+
+_TWO_PASS_MIN_ROWS = 1 << 17      # zero_shot_logits: fp16 banks of at least this many rows skip the hi/lo split
+
+
 def text_split(T: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Split-fp16 rows of T^T for a classifier T [D, C] (as given: not re-normalised)."""
     return normalize_split(T, feature_major=True, normalize=False)
@@ -666,9 +688,11 @@ def text_split(T: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scale: float = 100.0,
                      normalize: bool = True, tensor_cores: Optional[bool] = None,
-                     t_split: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+                     t_split: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                     two_pass: Optional[bool] = None) -> torch.Tensor:
     """Z = scale * normalise(X)^T @ T in fp32 (image_attention.py:80-83).  T is [D, C].  Default route: split-fp16
-    operands on the tensor cores (`normalize_split` + `gemm_split_nt`); `tensor_cores=False` (or
+    operands on the tensor cores (`normalize_split` + `gemm_split_nt`; `two_pass` — default for fp16 X of bank size:
+    raw rows + 1/norm, `gemm_rows_nt`, two passes instead of three); `tensor_cores=False` (or
     SUMMER_CLIP_B200_ZS_SIMT=1) selects the fp32 SIMT kernel (A/B runs, cross-check in the tests).  `t_split` =
     `text_split(T)` computed once by the caller (ClipSearcher does) saves two tiny launches per call."""
     _cuda(X, "X"), _cuda(T, "T")
@@ -682,7 +706,22 @@ def zero_shot_logits(X: torch.Tensor, feature_major: bool, T: torch.Tensor, scal
     if tensor_cores is None:
         tensor_cores = not os.environ.get("SUMMER_CLIP_B200_ZS_SIMT")
     if tensor_cores and N > 0:
-        return gemm_split_nt(normalize_split(X, feature_major, normalize), t_split if t_split is not None else text_split(T), scale)
+        ts = t_split if t_split is not None else text_split(T)
+        if two_pass is None:
+            # bank-sized products (the logits-bank producer, pseudo-labels) take the two-pass route; a query batch
+            # keeps the three-pass split the search pipeline was tuned with (50k queries: 0.3 ms either way, and the
+            # end-to-end bench measured the split's side-stream kernels a few ms kinder to the attention launch)
+            two_pass = N >= _TWO_PASS_MIN_ROWS
+        if X.dtype == torch.float16 and two_pass:
+            # fp16 rows are exact: the raw transposed rows (+ 1/norm per row) against the split classifier, two
+            # passes; rows that already are [N, D_pad] K-major go in as they are
+            inv = torch.empty(N, dtype=torch.float32, device=X.device) if normalize else None
+            if not normalize and not feature_major and X.is_contiguous() and D == pad_dim(D) and X.data_ptr() % 16 == 0:
+                xr = X
+            else:
+                xr = normalize_cast(X, feature_major, normalize=False, op_dtype=torch.float16, inv_norm=inv)
+            return gemm_rows_nt(xr, inv, ts, scale)
+        return gemm_split_nt(normalize_split(X, feature_major, normalize), ts, scale)
     if T.stride(1) != 1:
         T = T.contiguous()
     C = T.shape[1]

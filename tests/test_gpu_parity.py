@@ -615,6 +615,11 @@ def test_zero_shot_logits_tensor_core_route(ops, shape):
     assert (rec[:, :D] - torch.nn.functional.normalize(Xd, dim=1)).abs().max().item() < 3e-7      # 22 bits of each value
     raw = ops.zero_shot_logits(X, fm, T, scale=1.0, normalize=False)                              # the L producer
     assert (raw.double() - Xd @ T.double()).abs().max().item() < 1e-4 * max(1.0, float(Xd.abs().max()) * D ** 0.5)
+    if dtype == torch.float16:      # the two-pass route of bank-sized fp16 inputs (sc_transpose_norms + sc_gemm_rows_nt)
+        Z2 = ops.zero_shot_logits(X, fm, T, two_pass=True)
+        assert (Z2.double() - ref).abs().max().item() < 3e-4
+        raw2 = ops.zero_shot_logits(X, fm, T, scale=1.0, normalize=False, two_pass=True)
+        assert (raw2.double() - Xd @ T.double()).abs().max().item() < 1e-4 * max(1.0, float(Xd.abs().max()) * D ** 0.5)
 
 
 def test_sidecar_bank_gives_the_same_search(ops, tmp_path):
