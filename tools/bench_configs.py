@@ -171,6 +171,12 @@ def hbm_sections(peaks, quick, dev, hbm):
          note="fp16 features: raw transposed copy + 1/norm (sc_transpose_norms), two tensor-core passes against the "
               "split classifier with the row scan in the consumer warps (sc_rowconf_from_rows)")
 
+    for two_pass in (True, False):
+        med, _ = timed(lambda: ops.zero_shot_logits(bank, True, text, scale=1.0, t_split=t_split, two_pass=two_pass), iters=3)
+        emit(config="pseudo_labels", kind="logits_bank_producer", two_pass=two_pass, n=n, dim=dim, n_classes=c, ms=med,
+             note="save_image_outs.py:25 at ImageNet scale: the [N, C] fp32 bank written (5.1 GB)")
+    torch.cuda.empty_cache()
+
     def build():
         conf, label = ops.rowconf_from_features(bank, True, text, scale=100.0, prob=True, prob_scale=1.0, t_split=t_split)
         idx, _ = ops.topk_per_class(conf, label, c, 16)
