@@ -251,6 +251,7 @@ ATTN_CASES = [
 
 
 def main(argv):
+    argv = argv or ["all"]
     if argv[0] == "all":
         rc = 0
         me = os.path.abspath(__file__)
