@@ -46,10 +46,7 @@ class ImageAttention:
 
     # ---- setup hooks, in the order of BaseTrainer.setup (utils/trainer.py:62-70)
     def setup_device(self) -> None:
-        dev = (self.cfg.get("meta") or {}).get("device") or "cuda"
-        self.device = torch.device(dev)
-        if self.device.type != "cuda":
-            raise ops._lib.SummerClipError("image_attention runs on the CUDA path only (no CPU fallback)")
+        self.device = ops.require_cuda_device((self.cfg.get("meta") or {}).get("device"), "image_attention")
 
     def setup_logger(self) -> None:
         name = (self.cfg.get("exp") or {}).get("name", "image_attention")

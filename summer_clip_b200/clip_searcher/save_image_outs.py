@@ -29,10 +29,7 @@ class SaveImageOuts:
         self.run_dir = Path(run_dir)
 
     def setup(self) -> None:
-        dev = (self.cfg.get("meta") or {}).get("device") or "cuda"
-        self.device = torch.device(dev)
-        if self.device.type != "cuda":
-            raise ops._lib.SummerClipError("save_image_outs runs on the CUDA path only (no CPU fallback)")
+        self.device = ops.require_cuda_device((self.cfg.get("meta") or {}).get("device"), "save_image_outs")
         data = self.cfg["data"]
         if not data.get("text_features_path"):
             raise ops._lib.SummerClipError("save_image_outs needs data.text_features_path (the text classifier T [D, C]; "

@@ -47,6 +47,16 @@ def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def require_cuda_device(dev, who: str) -> torch.device:
+    """The device an entry point runs on: a CUDA device that exists, or a loud error (there is no CPU fallback)."""
+    device = torch.device(dev or "cuda")
+    if device.type != "cuda":
+        raise _lib.SummerClipError(f"{who} runs on the CUDA path only (no CPU fallback): meta.device={dev!r}")
+    if not torch.cuda.is_available():
+        raise _lib.SummerClipError(f"{who}: no CUDA device is available and the CLIP-search path has no CPU fallback")
+    return device
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

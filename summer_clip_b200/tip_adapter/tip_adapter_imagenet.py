@@ -45,10 +45,7 @@ class TipAdapterTrainer:
         self.run_dir = Path(run_dir)
 
     def setup_device(self) -> None:
-        dev = (self.cfg.get("meta") or {}).get("device") or "cuda"
-        self.device = torch.device(dev)
-        if self.device.type != "cuda":
-            raise ops._lib.SummerClipError("tip_adapter runs on the CUDA path only (no CPU fallback)")
+        self.device = ops.require_cuda_device((self.cfg.get("meta") or {}).get("device"), "tip_adapter")
 
     def setup_logger(self) -> None:
         name = (self.cfg.get("exp") or {}).get("name", "tip_adapter")

@@ -134,3 +134,31 @@ def test_reference_yaml_tree_composes_unmodified():
         t, o = compose(ref, name), compose(Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf", name)
         for k in ("search_hp", "search_scale", "search_step", "init_beta", "init_alpha", "dataset", "shots", "backbone", "augment_epoch"):
             assert t[k] == o[k], (name, k)
+
+
+def test_entry_points_fail_loudly_without_a_cuda_device(tmp_path):
+    """No CPU fallback anywhere on the product path: the three entry points refuse `meta.device=cpu`, and a machine
+    without a GPU (this container) gets the library's own error, not a silent slow path."""
+    import torch
+    from summer_clip_b200._lib import SummerClipError
+    from summer_clip_b200.clip_searcher import image_attention, save_image_outs
+    from summer_clip_b200.tip_adapter import tip_adapter, tip_adapter_imagenet
+    for mod in (image_attention, save_image_outs, tip_adapter, tip_adapter_imagenet):
+        with pytest.raises(SummerClipError, match="no CPU fallback"):
+            mod.run(["meta.device=cpu", f"run_dir={tmp_path}", "data.text_features_path=/nonexistent.pt"])
+        if not torch.cuda.is_available():
+            with pytest.raises(SummerClipError, match="no CPU fallback"):
+                mod.run([f"run_dir={tmp_path}", "data.text_features_path=/nonexistent.pt"])
+
+
+def test_command_line_of_the_entry_points(tmp_path):
+    """`[CONFIG.yaml | --config-dir DIR --config-name NAME] [key=value ...]` like the reference's hydra entry points."""
+    from pathlib import Path
+    from summer_clip_b200.clip_searcher.image_attention import compose_from_argv
+    conf = Path(__file__).resolve().parent.parent / "summer_clip_b200" / "conf"
+    a = compose_from_argv(["cache.alpha=[2.0]"], "image_attention")
+    b = compose_from_argv(["--config-dir", str(conf), "--config-name", "image_attention", "cache.alpha=[2.0]"], "ignored")
+    c = compose_from_argv([str(conf / "image_attention.yaml"), "cache.alpha=[2.0]"], "ignored")
+    assert a == b == c and a.cache.alpha == [2.0]
+    assert compose_from_argv([], "save_image_outs").data.output_image_outs == "image_outs.pt"
+    assert compose_from_argv(["search_step=[5,5]"], "tip_adapter").search_step == [5, 5]
