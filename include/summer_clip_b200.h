@@ -31,7 +31,9 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 2
+/* 3 = 2 + sc_rowconf_from_rows, sc_gemm_rows_nt, sc_transpose_norms (additive); sc_topk_per_class accepts an empty
+ * shard (N == 0, NULL rows).  Nothing of version 2 changed its signature or meaning. */
+#define SC_ABI_VERSION 3
 
 /* element types of caller buffers.  SC_E4M3 (8-bit float, 4 exponent / 3 mantissa bits) is an OPERAND type only:
  * sc_normalize_cast can write it and sc_attn_fwd_hard[_multi] can read it (tcgen05 kind::f8f6f4, fp32 accumulate:

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     for name in _declared_symbols():
         assert hasattr(raw, name), f"{name} declared in include/summer_clip_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(_declared_symbols())
-    assert cuda_lib.sc_version() == 2
+    assert cuda_lib.sc_version() == 3
 
 
 def test_geometry_helpers(cuda_lib):
