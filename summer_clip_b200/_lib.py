@@ -96,6 +96,9 @@ class SummerClipError(RuntimeError):
     pass
 
 
+ABI_VERSION = 3          # SC_ABI_VERSION of include/summer_clip_b200.h these signatures were written against
+
+
 _lib = None
 
 
@@ -120,6 +123,9 @@ def load() -> ctypes.CDLL:
             raise SummerClipError(f"{_LIB_PATH} does not export {name}") from exc
         fn.restype = restype
         fn.argtypes = argtypes
+    if lib.sc_version() != ABI_VERSION:
+        raise SummerClipError(f"{_LIB_PATH} implements ABI version {lib.sc_version()}, these bindings expect {ABI_VERSION}: "
+                              "rebuild it with `python -m summer_clip_b200.build`")
     _lib = lib
     return lib
 

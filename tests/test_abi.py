@@ -28,7 +28,9 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     for name in _declared_symbols():
         assert hasattr(raw, name), f"{name} declared in include/summer_clip_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(_declared_symbols())
-    assert cuda_lib.sc_version() == 3
+    assert cuda_lib.sc_version() == 3 == _lib.ABI_VERSION
+    header = (Path(__file__).resolve().parent.parent / "include" / "summer_clip_b200.h").read_text()
+    assert int(re.search(r"#define SC_ABI_VERSION (\d+)", header).group(1)) == _lib.ABI_VERSION
 
 
 def test_geometry_helpers(cuda_lib):
