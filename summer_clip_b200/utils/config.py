@@ -3,7 +3,7 @@ here): OmegaConf-style `${a.b.c}` interpolation plus the part of Hydra's default
 configs use (conf/image_attention.yaml:1-19, conf/tip_adapter*.yaml:1-4, conf/img_attn_dataset/*.yaml:1-2):
 
   - name                      a config of the same directory, merged at the parent's package
-  - group: option             conf/<group>/<option>.yaml placed under the key `group`
+  - group: option             conf/<group>/<option>.yaml (or the key <option> of conf/<group>.yaml) under the key `group`
   - group@pkg.path: option    ... placed under `pkg.path` (relative to the parent's package)
   - /group: option            group path taken from the config root instead of the parent's directory
   - _self_                    where the file's own keys merge (last when absent, Hydra >= 1.1)
@@ -87,13 +87,26 @@ def _set_at(root: dict, package: tp.Sequence[str], content: tp.Mapping) -> None:
     merge(cur, content)
 
 
+def _load_node(conf_root: Path, rel: str) -> dict:
+    """The mapping of config `rel`: conf_root/<rel>.yaml (Hydra's layout: one file per group option), or — this
+    package's own conf/ keeps the options of a group together — the key <option> of conf_root/<group>.yaml."""
+    path = conf_root / (rel + ".yaml")
+    if path.exists():
+        with open(path) as f:
+            return yaml.safe_load(f) or {}
+    group, _, option = rel.rpartition("/")
+    pack = conf_root / (group + ".yaml")
+    if group and pack.exists():
+        with open(pack) as f:
+            options = yaml.safe_load(f) or {}
+        if option in options:
+            return dict(options[option] or {})
+    raise FileNotFoundError(f"config {rel!r} not found under {conf_root}")
+
+
 def _compose_file(conf_root: Path, rel: str, package: tp.List[str], out: dict, choices: tp.Mapping[str, str]) -> None:
     """Merge conf_root/<rel>.yaml (and, recursively, its defaults list) into `out` at `package`."""
-    path = conf_root / (rel + ".yaml")
-    if not path.exists():
-        raise FileNotFoundError(f"config {rel!r} not found under {conf_root}")
-    with open(path) as f:
-        content = yaml.safe_load(f) or {}
+    content = _load_node(conf_root, rel)
     defaults = content.pop("defaults", None) or []
     if "_self_" not in defaults:
         defaults = list(defaults) + ["_self_"]
