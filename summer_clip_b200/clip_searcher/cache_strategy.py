@@ -63,39 +63,48 @@ def _rowconf(image_outs, scale: float = 1.0, prob: bool = False):
     return ops.rowconf(image_outs, scale=scale, prob=prob)
 
 
+Banks = tp.Tuple[torch.Tensor, torch.Tensor]      # (image features [D, n], logits [n, C])
+
+
 class CacheStrategy(ABC):
+    """What `cache_strategies.<name>` instantiates (the reference's interface, cache_strategy.py:10-15): the train bank
+    in, the cache bank out."""
+
     @abstractmethod
-    def transform(self, image_features: torch.Tensor, image_outs: torch.Tensor) \
-            -> tp.Tuple[torch.Tensor, torch.Tensor]:
-        pass
+    def transform(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> Banks:
+        raise NotImplementedError
 
 
 class IndexedCacheStrategy(CacheStrategy):
+    """A strategy that is a row selection (cache_strategy.py:18-27): `select` names the rows, `transform` gathers
+    the feature columns and the logits rows (the sweep driver calls `select` itself and fuses the gather into the
+    normalise kernel; `transform` is for callers that want the reference's tensors)."""
+
     @abstractmethod
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        pass
+        raise NotImplementedError
 
-    def transform(self, image_features: torch.Tensor, image_outs: torch.Tensor) \
-            -> tp.Tuple[torch.Tensor, torch.Tensor]:
-        samples_inds = self.select(image_features, image_outs)
-        return image_features[:, samples_inds], image_outs[samples_inds]
+    def transform(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> Banks:
+        rows = self.select(image_features, image_outs)
+        return image_features[:, rows], image_outs[rows]
 
 
 class AllLogitsStrategy(IndexedCacheStrategy):
+    """Every train image is a cache key (cache_strategy.py:30-32)."""
+
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
         return torch.arange(image_outs.shape[0], device=image_outs.device)
 
 
 class ThresholdStrategy(IndexedCacheStrategy):
+    """Rows whose confidence (max softmax probability, or max logit) reaches `threshold` (cache_strategy.py:35-45)."""
+
     def __init__(self, threshold: float, use_softmax: bool = True) -> None:
-        super().__init__()
-        self.threshold = threshold
-        self.use_softmax = use_softmax
+        self.threshold, self.use_softmax = threshold, use_softmax
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        max_probs, _ = _rowconf(image_outs, scale=1.0, prob=self.use_softmax)
-        confidence_mask = (max_probs >= self.threshold)
-        return confidence_mask.nonzero().squeeze(1)
+        confidence, _ = _rowconf(image_outs, scale=1.0, prob=self.use_softmax)
+        return torch.nonzero(confidence >= self.threshold).flatten()
 
 
 def select_topk_per_label(image_labels: torch.Tensor, image_logits: torch.Tensor, topk: int,
@@ -107,26 +116,26 @@ def select_topk_per_label(image_labels: torch.Tensor, image_logits: torch.Tensor
 
 
 class TopKStrategy(IndexedCacheStrategy):
+    """Per predicted class, the `topk` rows with the largest max logit (cache_strategy.py:62-70)."""
+
     def __init__(self, topk: int) -> None:
-        super().__init__()
         self.topk = topk
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        image_logits, label_preds = _rowconf(image_outs, prob=False)
-        return select_topk_per_label(label_preds, image_logits, self.topk, image_outs.shape[1])
+        confidence, predicted = _rowconf(image_outs, prob=False)
+        return select_topk_per_label(predicted, confidence, self.topk, image_outs.shape[1])
 
 
 class TopKProbStrategy(IndexedCacheStrategy):
+    """The same ranking on max softmax(scale * logits) (cache_strategy.py:73-81).  The [N, C] probabilities are
+    never materialised: the row maximum of a softmax is 1 / sum_c exp(scale (l_c - l_max))."""
+
     def __init__(self, topk: int, scale: float) -> None:
-        super().__init__()
-        self.scale = scale
-        self.topk = topk
-        self.topk_strategy = TopKStrategy(topk)
+        self.topk, self.scale = topk, scale
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        # softmax(image_outs * scale) never materialised: its row max is 1 / sum_c exp(scale (l_c - l_max))
-        image_probs, label_preds = _rowconf(image_outs, scale=self.scale, prob=True)
-        return select_topk_per_label(label_preds, image_probs, self.topk, image_outs.shape[1])
+        confidence, predicted = _rowconf(image_outs, scale=self.scale, prob=True)
+        return select_topk_per_label(predicted, confidence, self.topk, image_outs.shape[1])
 
 
 class TopKPerGoldStrategy(IndexedCacheStrategy):
@@ -166,44 +175,55 @@ class TopKPerGoldProbStrategy(IndexedCacheStrategy):
 
 
 class GlobalRandomSampleStrategy(IndexedCacheStrategy):
+    """`topk` x C rows drawn from the whole bank without replacement (cache_strategy.py:103-110).  The draw is the HOST
+    numpy generator's, as in the reference, so that a seeded run (`meta.random_state`) picks the same cache."""
+
     def __init__(self, topk: int) -> None:
-        super().__init__()
         self.topk = topk
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        samples_num = self.topk * image_outs.shape[1]
-        samples_num = min(samples_num, image_outs.shape[0])
-        samples_ids = np.random.choice(image_outs.shape[0], size=samples_num, replace=False)
-        return torch.LongTensor(samples_ids).to(image_outs.device)
+        n_rows, n_classes = image_outs.shape[0], image_outs.shape[1]
+        drawn = np.random.choice(n_rows, size=min(self.topk * n_classes, n_rows), replace=False)
+        return torch.from_numpy(drawn).to(device=image_outs.device, dtype=torch.int64)
 
 
 def select_k_random_per_label(image_labels: torch.Tensor, k: int) -> torch.Tensor:
-    """cache_strategy.py:113-124 — host numpy RNG, label order and draw order as in the reference."""
-    samples_ids = []
-    for label in image_labels.unique():
-        label_inds = (image_labels == label).nonzero().squeeze(1)
-        label_k = min(k, label_inds.shape[0])
-        label_samples_inds_np = np.random.choice(label_inds.shape[0], size=label_k, replace=False)
-        label_samples_inds = torch.LongTensor(label_samples_inds_np).to(label_inds.device)
-        samples_ids.append(label_inds[label_samples_inds])
-    return torch.cat(samples_ids)
+    """Up to k random rows of every label (cache_strategy.py:113-124).  Reproduces the reference's stream: labels in
+    ascending order (`unique`), one `np.random.choice(n_c, min(k, n_c), replace=False)` per label, drawn positions
+    mapped back through the label's rows in ascending order.  The members of all labels come from ONE stable sort of
+    the label vector instead of one N-long comparison per label."""
+    labels = image_labels.detach().to("cpu", torch.int64)
+    order = torch.argsort(labels, stable=True)                    # rows grouped by label, ascending inside a group
+    _, counts = torch.unique_consecutive(labels[order], return_counts=True)
+    picked, start = [], 0
+    for n_c in counts.tolist():
+        members = order[start:start + n_c]
+        positions = np.random.choice(n_c, size=min(k, n_c), replace=False)
+        picked.append(members[torch.from_numpy(positions)])
+        start += n_c
+    if not picked:
+        return torch.zeros(0, dtype=torch.int64, device=image_labels.device)
+    return torch.cat(picked).to(image_labels.device)
 
 
 class PerGoldClassRandomSampleStrategy(IndexedCacheStrategy):
+    """`topk` random rows per GOLD class (cache_strategy.py:127-138); labels come from `cache_labels`
+    (cache.labels_path) or, like the reference, from a `cache_dataset` of (image, label) pairs."""
+
     def __init__(self, topk: int, cache_dataset=None, cache_labels: tp.Optional[torch.Tensor] = None) -> None:
-        super().__init__()
         self.topk = topk
-        self.cache_labels = cache_labels if cache_labels is not None else load_labels(cache_dataset)
+        self.cache_labels = load_labels(cache_dataset) if cache_labels is None else cache_labels
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
         return select_k_random_per_label(self.cache_labels, self.topk).to(image_outs.device)
 
 
 class PerPredClassRandomSampleStrategy(IndexedCacheStrategy):
+    """`topk` random rows per PREDICTED class (cache_strategy.py:141-149)."""
+
     def __init__(self, topk: int) -> None:
-        super().__init__()
         self.topk = topk
 
     def select(self, image_features: torch.Tensor, image_outs: torch.Tensor) -> torch.Tensor:
-        _, label_preds = _rowconf(image_outs, prob=False)
-        return select_k_random_per_label(label_preds, self.topk)
+        _, predicted = _rowconf(image_outs, prob=False)
+        return select_k_random_per_label(predicted, self.topk)

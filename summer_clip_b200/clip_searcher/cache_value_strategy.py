@@ -97,9 +97,7 @@ class SoftmaxCacheStrategy(CacheValueStrategy):
     """cache_value_strategy.py:20-28 — softmax(clip_scale * scale * cache_outs, dim=1)."""
 
     def __init__(self, clip_scale: float, scale: float) -> None:
-        super().__init__()
-        self.clip_scale = clip_scale
-        self.scale = scale
+        self.clip_scale, self.scale = clip_scale, scale
 
     def transform(self, cache_outs: torch.Tensor, idx: tp.Optional[torch.Tensor] = None) -> CacheValues:
         vt = ops.values_prepare(cache_outs, cache_outs.shape[1], idx=idx, softmax_scale=self.clip_scale * self.scale)

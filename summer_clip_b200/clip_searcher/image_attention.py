@@ -67,9 +67,10 @@ class ImageAttention:
             self.save_labels()
 
     def save_labels(self) -> None:
-        self.gold_labels_saver.save_named_tensor(self.test_labels, "test_labels")
-        if self.cache_labels is not None:
-            self.gold_labels_saver.save_named_tensor(self.cache_labels, "cache_labels")
+        """`run_saves.save_labels`: the gold labels next to the log, under the reference's names (image_attention.py:33-36)."""
+        for name, labels in (("test_labels", self.test_labels), ("cache_labels", self.cache_labels)):
+            if labels is not None:
+                self.gold_labels_saver.save_named_tensor(labels, name)
 
     def setup_model(self) -> None:
         self.searcher = ClipSearcher(self.device)
@@ -131,14 +132,17 @@ class ImageAttention:
 
     @torch.no_grad()
     def train_loop(self) -> None:
+        # the zero-shot record first (image_attention.py:90-98): same keys, same order
         clip_logits = self.clip_logits
-        eval_top1, eval_top5 = compute_accuracy(clip_logits, self.test_labels)
-        zeroshot_info: tp.Dict[str, tp.Any] = dict(acc1=eval_top1, acc5=eval_top5)
-        if self.cfg.run_saves.save_preds:
-            zeroshot_info["preds_path"] = str(self.preds_saver.save_tensor(self.logits_to_preds(clip_logits)))
-        if self.cfg.run_saves.save_logits:
-            zeroshot_info["logits_path"] = str(self.preds_saver.save_tensor(clip_logits))
-        self.logger.log_info(dict(**zeroshot_info, type="zero_shot"))
+        acc1, acc5 = compute_accuracy(clip_logits, self.test_labels)
+        record: tp.Dict[str, tp.Any] = {"acc1": acc1, "acc5": acc5}
+        saves = self.cfg.run_saves
+        if saves.save_preds:
+            record["preds_path"] = str(self.preds_saver.save_tensor(self.logits_to_preds(clip_logits)))
+        if saves.save_logits:
+            record["logits_path"] = str(self.preds_saver.save_tensor(clip_logits))
+        record["type"] = "zero_shot"
+        self.logger.log_info(record)
 
         alphas = [float(a) for a in self.cfg.cache.alpha]
         n_q = self.test_labels.shape[0]

@@ -11,9 +11,9 @@ from .. import ops
 
 
 def load_labels(dataset) -> torch.Tensor:
-    """utils.py:10-12 — labels of a (image, label) dataset as an IntTensor."""
-    labels = [label for _, label in dataset]  # type: ignore
-    return torch.IntTensor(labels)
+    """int32 labels of an iterable of (image, label) pairs — what the reference's `load_labels` (clip_searcher/utils.py:
+    10-12) returns for the per-gold strategies' `cache_dataset`."""
+    return torch.tensor([int(pair[1]) for pair in dataset], dtype=torch.int32)
 
 
 def accuracy_counts(outputs: torch.Tensor, target: torch.Tensor) -> tp.Tuple[int, int]:
@@ -33,36 +33,22 @@ def compute_accuracy(outputs: torch.Tensor, target: torch.Tensor, topk=(1, 5)) -
     return [100.0 * c1 / n, 100.0 * c5 / n]
 
 
-class FilesNamesManager:
-    """utils.py:24-37."""
-
-    def __init__(self, dir_path: Path, files_ext: str) -> None:
-        self.dir_path = Path(dir_path).resolve()
-        self.files_ext = files_ext
-        self.dir_path.mkdir(parents=True, exist_ok=True)
-        self.counter = 0
-
-    def next_path(self) -> Path:
-        new_path = self.get_path(str(self.counter))
-        self.counter += 1
-        return new_path
-
-    def get_path(self, file_name: str) -> Path:
-        return self.dir_path / f"{file_name}{self.files_ext}"
-
-
 class TensorsNumpySaver:
-    """utils.py:40-52."""
+    """Numbered / named `.npy` dumps in one directory, with the reference's interface (`TensorsNumpySaver`,
+    clip_searcher/utils.py:40-52: the records of the sweep carry the returned paths in `preds_path`,
+    `cache_inds_path`, ...): `save_tensor` writes `<directory>/<n>.npy` with n = 0, 1, 2, ... in call order,
+    `save_named_tensor` writes `<directory>/<name>.npy`; both return the absolute path."""
 
-    def __init__(self, dir_path: Path) -> None:
-        self.files_names_manager = FilesNamesManager(dir_path, files_ext=".npy")
-
-    def save_tensor(self, tensor: torch.Tensor) -> Path:
-        tensor_path = self.files_names_manager.next_path()
-        return self.save_named_tensor(tensor, tensor_path.with_suffix("").name)
+    def __init__(self, dir_path: tp.Union[str, Path]) -> None:
+        self.directory = Path(dir_path).resolve()
+        self.directory.mkdir(parents=True, exist_ok=True)
+        self._saved = 0
 
     def save_named_tensor(self, tensor: torch.Tensor, file_name: str) -> Path:
-        tensor_np = tensor.cpu().numpy()
-        tensor_path = self.files_names_manager.get_path(file_name)
-        np.save(tensor_path, tensor_np)
-        return tensor_path
+        target = self.directory / (file_name + ".npy")
+        np.save(target, tensor.detach().cpu().numpy())
+        return target
+
+    def save_tensor(self, tensor: torch.Tensor) -> Path:
+        index, self._saved = self._saved, self._saved + 1
+        return self.save_named_tensor(tensor, str(index))

@@ -125,26 +125,26 @@ class TipAdapterHead:
 
 def search_hp(cfg, cache_keys, cache_values, features, labels, clip_weights, adapter=None, head=None):
     """tip_adapter/utils.py:99-129.  `head` (optional): a TipAdapterHead already built from the same operands."""
-    best_beta, best_alpha = 0, 0
-    if cfg['search_hp'] == True:  # noqa: E712  (the reference's own test)
-        beta_list = [i * (cfg['search_scale'][0] - 0.1) / cfg['search_step'][0] + 0.1 for i in range(cfg['search_step'][0])]
-        alpha_list = [i * (cfg['search_scale'][1] - 0.1) / cfg['search_step'][1] + 0.1 for i in range(cfg['search_step'][1])]
+    if cfg['search_hp'] is not True and cfg['search_hp'] != 1:
+        return 0, 0
 
-        if head is None:
-            head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
-        n = labels.shape[0]
-        counts = head.top1_counts_many(beta_list, alpha_list, labels).cpu()                             # one D2H
+    def grid(axis: int) -> tp.List[float]:          # i * (scale - 0.1) / steps + 0.1, i < steps (utils.py:103-104)
+        scale, steps = cfg['search_scale'][axis], cfg['search_step'][axis]
+        return [i * (scale - 0.1) / steps + 0.1 for i in range(steps)]
 
-        best_acc = 0
-        for bi, beta in enumerate(beta_list):
-            for ai, alpha in enumerate(alpha_list):
-                acc = 100 * int(counts[bi, ai]) / n
-                if acc > best_acc:
-                    print("New best setting, beta: {:.2f}, alpha: {:.2f}; accuracy: {:.2f}".format(beta, alpha, acc))
-                    best_acc = acc
-                    best_beta = beta
-                    best_alpha = alpha
-
-        print("\nAfter searching, the best accuarcy: {:.2f}.\n".format(best_acc))
-
-    return best_beta, best_alpha
+    betas, alphas = grid(0), grid(1)
+    if head is None:
+        head = TipAdapterHead(cache_keys, cache_values, features, clip_weights, adapter)
+    # every (beta, alpha) top-1 count on the device, ONE copy to the host; the scan below only replays the reference's
+    # "strictly better keeps the first" rule and its progress lines (the messages are its user-visible output)
+    correct = head.top1_counts_many(betas, alphas, labels).cpu().tolist()
+    n = labels.shape[0]
+    best = (0.0, 0, 0)                               # (accuracy, beta, alpha)
+    for beta, row in zip(betas, correct):
+        for alpha, hits in zip(alphas, row):
+            acc = 100 * int(hits) / n
+            if acc > best[0]:
+                best = (acc, beta, alpha)
+                print(f"New best setting, beta: {beta:.2f}, alpha: {alpha:.2f}; accuracy: {acc:.2f}")
+    print(f"\nAfter searching, the best accuarcy: {best[0]:.2f}.\n")
+    return best[1], best[2]

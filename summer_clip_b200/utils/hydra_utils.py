@@ -17,24 +17,24 @@ _PREFIX_MAP = (("summer_clip.", "summer_clip_b200."),)
 
 
 def load_obj(obj_path: str, default_obj_path: str = "") -> tp.Any:
-    """hydra_utils.py:9-27 — import `pkg.mod.Name`."""
-    obj_path_list = obj_path.rsplit(".", 1)
-    obj_path = obj_path_list.pop(0) if len(obj_path_list) > 1 else default_obj_path
-    obj_name = obj_path_list[0]
-    module_obj = importlib.import_module(obj_path)
-    if not hasattr(module_obj, obj_name):
-        raise AttributeError(f"Object `{obj_name}` cannot be loaded from `{obj_path}`.")
-    return getattr(module_obj, obj_name)
+    """The object a dotted path names (`pkg.mod.Name`; a bare `Name` is looked up in `default_obj_path`) — the
+    reference's helper of the same name (hydra_utils.py:9-27)."""
+    module_name, dot, attr = obj_path.rpartition(".")
+    if not dot:
+        module_name = default_obj_path
+    module = importlib.import_module(module_name)
+    try:
+        return getattr(module, attr)
+    except AttributeError:
+        raise AttributeError(f"Object `{attr}` cannot be loaded from `{module_name}`.") from None
 
 
-def type_full_name(type_: type) -> tp.Optional[str]:
-    """hydra_utils.py:30-36."""
+def type_full_name(type_: tp.Optional[type]) -> tp.Optional[str]:
+    """`module.QualifiedName` of a class, bare for builtins (hydra_utils.py:30-36)."""
     if type_ is None:
         return None
-    module = type_.__module__
-    if module is None or module == str.__module__:
-        return type_.__name__
-    return f"{module}.{type_.__name__}"
+    owner = getattr(type_, "__module__", None)
+    return type_.__name__ if owner in (None, "builtins") else owner + "." + type_.__name__
 
 
 def resolve_target(target: str) -> str:
