@@ -1,5 +1,8 @@
+"""Event-timed column-normalise + transpose + cast of the 1.28M x 1024 fp16 key bank (sc_normalize_cast)."""
+import os
 import sys
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from summer_clip_b200 import ops
 n, dim = 1281167, 1024
